@@ -1,0 +1,168 @@
+"""Seeded synthetic inputs for the GRL hot path.
+
+Everything here is *data generation*, not algorithm: it is shared by the tests,
+the golden-vector script (oracle/make_golden.py), smoke() and bench.py so that
+the reference, the oracle and the CUDA path all see identical tensors.
+
+numpy's PCG64 `default_rng` is used (stream stability is guaranteed by numpy),
+never torch's global RNG, so fixtures regenerate bit-identically anywhere.
+
+Parameter names/shapes follow the reference `state_dict` keys:
+  reid/models/basebranch.py:38-50   (GCE: glo_fc, corr_atte)
+  reid/models/grl_model.py:88-128   (TRL: *_f1, *_f2, channel_atte_*, uncorr_memo_*)
+"""
+from __future__ import annotations
+
+import math
+import re
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+C_FEAT = 2048      # layer4 channels           (basebranch.py:43)
+C_GLO = 1024       # glo_fc width              (basebranch.py:38)
+C_MID = 256        # corr_atte middle width    (basebranch.py:45)
+C_MEMO = 512       # BasicBlock planes         (grl_model.py:92)
+C_SE = 128         # 2048 // 16                (grl_model.py:104)
+H_MAP, W_MAP = 16, 8   # hard-coded spatial size (basebranch.py:59)
+S_MAP = H_MAP * W_MAP
+
+
+def head_param_shapes() -> "OrderedDict[str, tuple]":
+    """state_dict keys (minus `backbone.base.*`) of ResNet50_GRL_Model's head."""
+    d: "OrderedDict[str, tuple]" = OrderedDict()
+
+    def bn(prefix, n):
+        d[prefix + ".weight"] = (n,)
+        d[prefix + ".bias"] = (n,)
+        d[prefix + ".running_mean"] = (n,)
+        d[prefix + ".running_var"] = (n,)
+        d[prefix + ".num_batches_tracked"] = ()
+
+    d["backbone.glo_fc.0.weight"] = (C_GLO, C_FEAT)
+    d["backbone.glo_fc.0.bias"] = (C_GLO,)
+    bn("backbone.glo_fc.1", C_GLO)
+    d["backbone.corr_atte.0.weight"] = (C_GLO, C_FEAT + C_GLO, 1, 1)
+    bn("backbone.corr_atte.1", C_GLO)
+    d["backbone.corr_atte.2.weight"] = (C_MID, C_GLO, 1, 1)
+    bn("backbone.corr_atte.3", C_MID)
+    d["backbone.corr_atte.5.weight"] = (1, C_MID, 1, 1)
+    bn("backbone.corr_atte.6", 1)
+    t = "temporal_learning_block."
+    for direction, atte in (("forward", "foreward"), ("backward", "backward")):
+        m = t + "uncorr_memo_" + direction
+        d[m + ".conv1.weight"] = (C_MEMO, C_FEAT, 1, 1)
+        bn(m + ".bn1", C_MEMO)
+        d[m + ".conv2.weight"] = (C_MEMO, C_MEMO, 1, 1)
+        bn(m + ".bn2", C_MEMO)
+        d[m + ".conv3.weight"] = (C_FEAT, C_MEMO, 1, 1)
+        bn(m + ".bn3", C_FEAT)
+        for f in ("_f1", "_f2"):
+            d[t + direction + f + ".0.weight"] = (C_FEAT, C_FEAT, 1, 1)
+            d[t + direction + f + ".0.bias"] = (C_FEAT,)
+        d[t + "channel_atte_" + atte + "_corr.0.weight"] = (C_SE, C_FEAT)
+        d[t + "channel_atte_" + atte + "_corr.2.weight"] = (C_FEAT, C_SE)
+    return d
+
+
+_BN_RE = re.compile(r"(\.bn[123]|glo_fc\.1|corr_atte\.[136])\.(weight|bias)$")
+
+
+def _is_bn(name: str) -> bool:
+    return _BN_RE.search(name) is not None
+
+
+def make_head_params(seed: int = 0, randomize_bn: bool = True, dtype=torch.float32):
+    """PyTorch-default-style init (U(-1/sqrt(fan_in), +1/sqrt(fan_in))) from PCG64.
+
+    With `randomize_bn` the BN affine parameters and running buffers are perturbed
+    so that eval-mode and backward tests are not degenerate (gamma=1, beta=0,
+    mean=0, var=1 would hide mistakes in exactly those terms).
+    """
+    rng = np.random.default_rng(seed)
+    out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for name, shape in head_param_shapes().items():
+        if name.endswith("num_batches_tracked"):
+            out[name] = torch.zeros((), dtype=torch.int64)
+            continue
+        if name.endswith("running_mean"):
+            v = rng.standard_normal(shape, dtype=np.float32) * 0.05 if randomize_bn else np.zeros(shape, np.float32)
+        elif name.endswith("running_var"):
+            v = rng.uniform(0.5, 1.5, shape).astype(np.float32) if randomize_bn else np.ones(shape, np.float32)
+        elif _is_bn(name):
+            if name.endswith(".weight"):
+                v = rng.uniform(0.6, 1.4, shape).astype(np.float32) if randomize_bn else np.ones(shape, np.float32)
+            else:
+                v = (rng.standard_normal(shape, dtype=np.float32) * 0.1) if randomize_bn else np.zeros(shape, np.float32)
+        else:
+            fan_in = shape[1] if len(shape) > 1 else None
+            if fan_in is None:  # conv / linear bias: fan_in of the owning layer
+                fan_in = C_FEAT
+            bound = 1.0 / math.sqrt(fan_in)
+            v = rng.uniform(-bound, bound, shape).astype(np.float32)
+        out[name] = torch.from_numpy(np.ascontiguousarray(v)).to(dtype)
+    return out
+
+
+def make_head_input(B: int, T: int, seed: int = 123, dtype=torch.float32) -> torch.Tensor:
+    """Structured layer4-like maps, NCHW [B*T, 2048, 16, 8].
+
+    x = relu(mu[b,c] + 0.3 phi[b,t,c] + 0.5 sigma[b,t,h,w] + 0.5 eps): clips differ
+    (so glo_fc's BatchNorm1d over B samples is well conditioned) and frames/pixels
+    differ inside a clip (so the correlation map is not constant).
+    """
+    rng = np.random.default_rng(seed)
+    mu = rng.standard_normal((B, 1, C_FEAT, 1, 1), dtype=np.float32)
+    phi = rng.standard_normal((B, T, C_FEAT, 1, 1), dtype=np.float32)
+    sig = rng.standard_normal((B, T, 1, H_MAP, W_MAP), dtype=np.float32)
+    eps = rng.standard_normal((B, T, C_FEAT, H_MAP, W_MAP), dtype=np.float32)
+    x = np.maximum(mu + 0.3 * phi + 0.5 * sig + 0.5 * eps, 0.0).astype(np.float32)
+    return torch.from_numpy(x.reshape(B * T, C_FEAT, H_MAP, W_MAP)).to(dtype)
+
+
+def make_head_grads(B: int, T: int, seed: int = 1, dtype=torch.float32):
+    """Upstream gradients on (f_uncorr [B,2048], f_corr [B,T,2048])."""
+    rng = np.random.default_rng(seed)
+    gu = rng.standard_normal((B, C_FEAT), dtype=np.float32)
+    gc = rng.standard_normal((B, T, C_FEAT), dtype=np.float32)
+    return torch.from_numpy(gu).to(dtype), torch.from_numpy(gc).to(dtype)
+
+
+def make_eval_set(num_q: int, num_g_extra: int, dim: int, seed: int = 0, num_ids: int = 625,
+                  num_cams: int = 6, noise: float = 0.3, distractors: float = 0.1,
+                  missing_query_frac: float = 0.02):
+    """Clustered re-ID features + ids shaped like ATTEvaluator.evaluate's inputs.
+
+    Mirrors reid/evaluator/attevaluator.py:143-145: the gallery is
+    `cat(queries, extra gallery)`, so every query's own copy (same pid, same cam)
+    is in the gallery and must be removed as junk (eva_functions.py:153-154).
+    A few queries get a pid that never appears elsewhere -> "no valid match"
+    (eva_functions.py:159-161).  pid 0 rows act as distractors.
+    Returns float32 features (unit norm) and int64 pid / camid arrays.
+    """
+    rng = np.random.default_rng(seed)
+    cent = rng.standard_normal((num_ids + 1, dim), dtype=np.float32)
+    q_pid = rng.integers(1, num_ids + 1, num_q)
+    q_cam = rng.integers(0, num_cams, num_q)
+    n_missing = int(round(missing_query_frac * num_q))
+    if n_missing:
+        # ids above num_ids never occur in the extra gallery
+        q_pid[:n_missing] = num_ids + 1 + np.arange(n_missing)
+    g_pid_x = rng.integers(1, num_ids + 1, num_g_extra)
+    g_pid_x[rng.random(num_g_extra) < distractors] = 0
+    g_cam_x = rng.integers(0, num_cams, num_g_extra)
+
+    def feats(pid):
+        base = cent[np.minimum(pid, num_ids)]
+        # ids above num_ids share centroid `num_ids` but that is irrelevant: they have no positives
+        f = base + noise * rng.standard_normal(base.shape, dtype=np.float32)
+        f = f / np.linalg.norm(f, axis=1, keepdims=True)
+        return f.astype(np.float32)
+
+    qf = feats(q_pid)
+    gf_x = feats(g_pid_x)
+    gf = np.concatenate([qf, gf_x], 0)
+    g_pid = np.concatenate([q_pid, g_pid_x])
+    g_cam = np.concatenate([q_cam, g_cam_x])
+    return qf, gf, q_pid.astype(np.int64), g_pid.astype(np.int64), q_cam.astype(np.int64), g_cam.astype(np.int64)

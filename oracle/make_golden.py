@@ -1,0 +1,146 @@
+"""ORACLE tooling — generate tests/golden/*.npz by running the REAL reference.
+
+Run in the authoring container only (needs /root/reference, which does not exist on
+the GPU box):      python oracle/make_golden.py
+
+Recipe: put /root/reference on sys.path; stub
+`torch.utils.model_zoo.load_url` (no network) and let ResNet.load_state_dict
+ignore the resulting None; build `ResNet50_GRL_Model`; replace `backbone.base`
+with Identity so seeded synthetic layer4 maps feed GCE directly; load the seeded
+head parameters of grl_b200.synth into the reference's own state_dict.  The
+reference modules then run *unmodified* (Backbone.forward, TRLBlock.forward, the
+corr_bn/uncorr_bn tail, cosin_dist, pairwise_distance_tensor, evaluate).
+
+Fixtures hold only outputs (+ small gradient samples); inputs/params regenerate
+bit-identically from their PCG64 seeds.
+"""
+from __future__ import annotations
+
+import io
+import os
+import sys
+import contextlib
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference():
+    sys.path.insert(0, REF)
+    import torch.utils.model_zoo as model_zoo
+    model_zoo.load_url = lambda *a, **k: None                      # stub 1: no network
+    with contextlib.redirect_stdout(io.StringIO()):
+        from reid.models import resnets1
+        _orig = resnets1.ResNet.load_state_dict
+        resnets1.ResNet.load_state_dict = lambda self, sd, *a, **k: None if sd is None else _orig(self, sd, *a, **k)
+        from reid.models.grl_model import ResNet50_GRL_Model
+        from reid.evaluator import attevaluator, eva_functions
+    return ResNet50_GRL_Model, attevaluator, eva_functions
+
+
+def build_reference_model(Model, params, dtype):
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = Model()
+    model.backbone.base = torch.nn.Identity()                      # stub 2: synthetic layer4 maps
+    sd = model.state_dict()
+    for k, v in params.items():
+        assert k in sd and tuple(sd[k].shape) == tuple(v.shape), k
+        sd[k] = v.clone()
+    model.load_state_dict(sd)
+    return model.to(dtype)
+
+
+def grad_sample(t: torch.Tensor, n=64):
+    f = t.detach().reshape(-1)
+    step = max(1, f.numel() // n)
+    return f[::step][:n].double().numpy().copy()
+
+
+def head_fixture(Model, name, B, T, training, dtype=torch.float64, with_grads=True):
+    from grl_b200 import synth
+    params = synth.make_head_params(0, dtype=torch.float32)
+    model = build_reference_model(Model, params, dtype)
+    model.train(training)
+    x = synth.make_head_input(B, T).to(dtype).requires_grad_(with_grads)
+    gu, gc = synth.make_head_grads(B, T)
+    gu, gc = gu.to(dtype), gc.to(dtype)
+    # Backbone.forward with base=Identity == GCE on layer4 maps (basebranch.py:52-68)
+    x_uncorr, x_corr, corr_map = model.backbone(x, B, T)
+    xu5 = x_uncorr.view(B, T, 2048, 16, 8)
+    xc5 = x_corr.view(B, T, 2048, 16, 8)
+    f_uncorr, f_corr = model.temporal_learning_block(xu5, xc5)      # grl_model.py:131-180
+    out = dict(B=B, T=T, training=int(training),
+               f_uncorr=f_uncorr.detach().double().numpy(), f_corr=f_corr.detach().double().numpy(),
+               corr_map=corr_map.detach().double().numpy(),
+               x_corr_sample=grad_sample(x_corr, 256), x_uncorr_sample=grad_sample(x_uncorr, 256))
+    # tail (grl_model.py:222-226)
+    xc_t = model.corr_bn(f_corr.view(B * T, 2048)).view(B, T, 2048)
+    xc_t = torch.nn.functional.normalize(xc_t, p=2, dim=2)
+    xu_t = torch.nn.functional.normalize(model.uncorr_bn(f_uncorr.view(B, 2048)).view(B, 2048), p=2, dim=1)
+    out["tail_x_corr"] = xc_t.detach().double().numpy()
+    out["tail_x_uncorr"] = xu_t.detach().double().numpy()
+    if with_grads:
+        loss = (f_uncorr * gu).sum() + (f_corr * gc).sum()
+        loss.backward()
+        out["dx_sample"] = grad_sample(x.grad, 512)
+        out["dx_norm"] = float(x.grad.norm())
+        names, norms, samples = [], [], []
+        for k, v in model.named_parameters():
+            if k in params and v.grad is not None:
+                names.append(k)
+                norms.append(float(v.grad.norm()))
+                samples.append(grad_sample(v.grad, 16) if v.grad.numel() >= 16 else
+                               np.pad(grad_sample(v.grad, 16), (0, 16 - v.grad.numel())))
+        out["grad_names"] = np.array(names)
+        out["grad_norms"] = np.array(norms)
+        out["grad_samples"] = np.stack(samples)
+    if training:
+        bufs = {k: v for k, v in model.state_dict().items() if k in params and ("running" in k or "num_batches" in k)}
+        out["buf_names"] = np.array(list(bufs.keys()))
+        out["buf_values"] = np.concatenate([v.double().reshape(-1).numpy() for v in bufs.values()])
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name, {k: getattr(v, "shape", v) for k, v in out.items() if k in ("f_uncorr", "f_corr")})
+
+
+def eval_fixture(att, eva, name, nq, ng_extra, dim, seed, noise, max_rank=100, quantize=None):
+    from grl_b200 import synth
+    qf, gf, qp, gp, qc, gc = synth.make_eval_set(nq, ng_extra, dim, seed=seed, num_ids=25, noise=noise,
+                                                 missing_query_frac=0.05)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d_cos = att.cosin_dist(torch.from_numpy(qf), torch.from_numpy(gf)).numpy()
+        d_l2 = att.pairwise_distance_tensor(torch.from_numpy(qf), torch.from_numpy(gf)).numpy()
+    if quantize:
+        d_cos = (np.round(d_cos * quantize) / quantize).astype(np.float32)    # force exact ties
+    with contextlib.redirect_stdout(io.StringIO()):
+        cmc, mAP = eva.evaluate(d_cos, qp, gp, qc, gc, max_rank=max_rank)
+        cmc_l2, mAP_l2 = eva.evaluate(d_l2, qp, gp, qc, gc, max_rank=max_rank)
+        rank1 = att.evaluate_seq(d_cos, qp, qc, gp, gc, path=None)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), nq=nq, ng_extra=ng_extra, dim=dim, seed=seed, noise=noise,
+                        max_rank=max_rank, quantize=quantize or 0, d_cos=d_cos, d_l2=d_l2,
+                        cmc=cmc, mAP=mAP, cmc_l2=cmc_l2, mAP_l2=mAP_l2, rank1=rank1)
+    print("wrote", name, "mAP %.4f rank1 %.4f" % (mAP, cmc[0]))
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    Model, att, eva = import_reference()
+    head_fixture(Model, "head_train_b2t3", 2, 3, True)
+    head_fixture(Model, "head_train_b4t2", 4, 2, True)
+    head_fixture(Model, "head_eval_b3t4", 3, 4, False, with_grads=False)
+    eval_fixture(att, eva, "eval_small", 60, 240, 64, seed=3, noise=1.5)
+    # NOTE: the reference itself raises (ragged all_cmc, eva_functions.py:164,180) when junk removal leaves
+    # fewer than max_rank gallery rows, so "num_g < max_rank" (:136-138) cannot be pinned; use max_rank=10.
+    eval_fixture(att, eva, "eval_rank10", 20, 100, 32, seed=4, noise=1.0, max_rank=10)
+    eval_fixture(att, eva, "eval_ties", 40, 160, 16, seed=5, noise=1.0, quantize=8)  # exact ties
+
+
+if __name__ == "__main__":
+    main()
