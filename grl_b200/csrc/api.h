@@ -1,0 +1,82 @@
+// grl_b200 — internal host-side declarations shared by the translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/grl_b200.h"
+#include "gemm.cuh"
+
+typedef CUresult (*grl_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct grl_handle {
+    int device;
+    int num_sms;
+    long long launches;
+    grl_encode_tiled_fn encode;
+    char err[512];
+};
+
+namespace grl {
+
+int set_error(grl_handle* h, int code, const char* fmt, ...);
+
+#define GRL_CUDA(h, expr)                                                                              \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return grl::set_error((h), GRL_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                  __FILE__, __LINE__);                                                 \
+    } while (0)
+
+#define GRL_LAUNCH_CHECK(h)                                                                            \
+    do {                                                                                               \
+        (h)->launches++;                                                                               \
+        cudaError_t _e = cudaGetLastError();                                                           \
+        if (_e != cudaSuccess)                                                                         \
+            return grl::set_error((h), GRL_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                                  __FILE__, __LINE__);                                                 \
+    } while (0)
+
+#define GRL_TRY(expr)            \
+    do {                         \
+        int _r = (expr);         \
+        if (_r != GRL_OK) return _r; \
+    } while (0)
+
+// A GEMM operand given as bf16 hi/lo planes.
+struct Operand {
+    const __nv_bfloat16* hi;
+    const __nv_bfloat16* lo;
+    long long ld;        // leading dimension in elements
+    long long bstride;   // batch stride in elements (ignored when batch == 1)
+    int mn_major;        // 0: [rows][K], 1: [K][rows]
+};
+
+// D[z] = A[z] * B[z]^T with the fused epilogue `epi`; bn = 0 picks the N tile automatically.
+int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, const Operand& A, const Operand& B,
+                GemmEpi epi, int bn);
+
+// fp32 [rows][cols] (ld_src) -> bf16 hi/lo planes [rows][cols] (ld_dst); optional per-row scale.
+int split_planes(grl_handle* h, cudaStream_t st, const float* src, long long ld_src, __nv_bfloat16* hi,
+                 __nv_bfloat16* lo, long long ld_dst, long long rows, int cols);
+// fp32 [rows][cols] -> transposed planes [cols][rows] (ld_dst = leading dim of the transposed planes)
+int split_planes_transposed(grl_handle* h, cudaStream_t st, const float* src, long long ld_src, __nv_bfloat16* hi,
+                            __nv_bfloat16* lo, long long ld_dst, int rows, int cols);
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline GemmEpi epi_default() {
+    GemmEpi e;
+    memset(&e, 0, sizeof(e));
+    e.alpha = 1.f;
+    e.grp_rows = 1;
+    return e;
+}
+
+}  // namespace grl

@@ -1,0 +1,346 @@
+// grl_b200 — split-bf16 ("bf16x3") tcgen05 GEMM for sm_100a.
+//
+//   D[z][m][n] = sum_k A[z][m][k] * B[z][n][k]        (fp32 accumulate in TMEM)
+//
+// A and B are given as two bf16 planes each (hi, lo) with x ~= hi + lo (16 mantissa
+// bits).  Three MMAs per k-step (hi*hi + lo*hi + hi*lo) give ~2e-5 relative error
+// per contraction, which is what GRL's 1e-3 parity bar on a >=30-deep GEMM chain
+// needs; single-pass bf16/tf32 does not.
+//
+// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0   : TMA producer   — cp.async.bulk.tensor into a ring of smem stages,
+//              hi planes and lo planes complete on separate mbarriers so the
+//              hi*hi MMAs start as soon as half a stage has landed
+//   warp 1   : MMA issuer     — one lane issues tcgen05.mma (UMMA 128 x BN x 16),
+//              tcgen05.commit frees smem stages / publishes the accumulator
+//   warps 2-5: epilogue       — tcgen05.ld 32x32b.x32 (thread == output row),
+//              fused bias / row-scale / ReLU / L2-distance / (v - sub)^2 column
+//              reductions / BatchNorm partial statistics / bf16 hi-lo re-split,
+//              overlapped with the next tile's MMAs via 2 TMEM accumulator stages
+//
+// Operand majors: K-major (rows x K, K contiguous) for fprop/dgrad; MN-major
+// (K x rows, rows contiguous) for wgrad, so activations/gradients are consumed
+// in their pixel-major layout without a transposed copy.  Both use SWIZZLE_128B.
+#pragma once
+#include "common.cuh"
+
+namespace grl {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmEpi {
+    // ---- outputs (all optional) ----
+    float* C;                 // fp32 [z][M][ldc]
+    long long ldc, c_bstride;
+    __nv_bfloat16* Phi;       // bf16 hi/lo planes of the stored value [z][M][ldp]
+    __nv_bfloat16* Plo;
+    long long ldp, p_bstride;
+    float* col_sum;           // [z][4*num_m_tiles][N] per-(tile,warp) column sums of the "stat value"
+    float* col_sq;            // same, squares
+    long long stat_bstride;
+    // ---- transforms: v = alpha*acc; v *= row_scale[m]; v += col_bias[n] + grp_bias[m/grp_rows][n]; relu ----
+    float alpha;
+    const float* row_scale;
+    long long rs_bstride;
+    const float* col_bias;
+    long long cb_bstride;
+    const float* grp_bias;
+    int grp_rows;
+    long long ld_gb;
+    int relu;
+    int accumulate;           // C += v (read-modify-write)
+    int mode;                 // 0 plain, 1 L2: v = sqrt(max(row_norm[m] + col_norm[n] - 2*acc, 1e-12))
+    const float* row_norm;
+    const float* col_norm;
+    // ---- "sub" mode (TRL f1): e = v - sub[sub_row][sub_col]; stat value = e (else v) ----
+    const float* sub;
+    long long ld_sub;
+    long long sub_tile_rows;  // sub_row = m_tile*sub_tile_rows + sub_row_off[z] + row_in_tile
+    long long sub_row_off[2];
+    long long sub_col_off[2];
+};
+
+struct GemmParams {
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    int M, N, K, batch;
+    int num_m_tiles, num_n_tiles;
+    GemmEpi epi;
+};
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int STAGES = (BN == 256) ? 2 : 3;
+    static constexpr int A_PLANE = GEMM_BM * GEMM_BK * 2;   // bytes per A plane per stage (16 KB)
+    static constexpr int B_PLANE = BN * GEMM_BK * 2;        // 16 / 32 KB
+    static constexpr int STAGE_BYTES = 2 * (A_PLANE + B_PLANE);
+    static constexpr int TMEM_COLS = 2 * BN;                // two accumulator stages
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_hi = bars;                    // [STAGES]
+    uint64_t* full_lo = bars + STAGES;           // [STAGES]
+    uint64_t* empty = bars + 2 * STAGES;         // [STAGES]
+    uint64_t* tmem_full = bars + 3 * STAGES;     // [2]
+    uint64_t* tmem_empty = bars + 3 * STAGES + 2;  // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.ta_hi); tma_prefetch_desc(&p.ta_lo);
+        tma_prefetch_desc(&p.tb_hi); tma_prefetch_desc(&p.tb_lo);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_hi[s], 1); mbar_init(&full_lo[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+    const int tiles_per_batch = p.num_m_tiles * p.num_n_tiles;
+    const int num_tiles = tiles_per_batch * p.batch;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int z = tile / tiles_per_batch;
+                const int r = tile - z * tiles_per_batch;
+                const int m0 = (r % p.num_m_tiles) * GEMM_BM;
+                const int n0 = (r / p.num_m_tiles) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int k0 = kb * GEMM_BK;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sA_hi = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sB_hi = sA_hi + Cfg::A_PLANE;
+                    uint8_t* sA_lo = sB_hi + Cfg::B_PLANE;
+                    uint8_t* sB_lo = sA_lo + Cfg::A_PLANE;
+                    mbar_arrive_expect_tx(&full_hi[stage], Cfg::A_PLANE + Cfg::B_PLANE);
+                    if (A_MN) {
+#pragma unroll
+                        for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_3d(sA_hi + j * 8192, &p.ta_hi, &full_hi[stage], m0 + 64 * j, k0, z);
+                    } else {
+                        tma_load_3d(sA_hi, &p.ta_hi, &full_hi[stage], k0, m0, z);
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) tma_load_3d(sB_hi + j * 8192, &p.tb_hi, &full_hi[stage], n0 + 64 * j, k0, z);
+                    } else {
+                        tma_load_3d(sB_hi, &p.tb_hi, &full_hi[stage], k0, n0, z);
+                    }
+                    mbar_arrive_expect_tx(&full_lo[stage], Cfg::A_PLANE + Cfg::B_PLANE);
+                    if (A_MN) {
+#pragma unroll
+                        for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_3d(sA_lo + j * 8192, &p.ta_lo, &full_lo[stage], m0 + 64 * j, k0, z);
+                    } else {
+                        tma_load_3d(sA_lo, &p.ta_lo, &full_lo[stage], k0, m0, z);
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) tma_load_3d(sB_lo + j * 8192, &p.tb_lo, &full_lo[stage], n0 + 64 * j, k0, z);
+                    } else {
+                        tma_load_3d(sB_lo, &p.tb_lo, &full_lo[stage], k0, n0, z);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            // K-major  SW128: 8-row groups 1024 B apart (SBO); LBO unused.   k-step (16 elems) = +32 B
+            // MN-major SW128: 64-element MN atoms BK*128 B apart (LBO), 8-row k groups 1024 B apart (SBO); k-step = 16 rows = +2048 B
+            constexpr uint32_t a_lbo = A_MN ? GEMM_BK * 128 : 16, b_lbo = B_MN ? GEMM_BK * 128 : 16;
+            constexpr uint32_t a_kstep = A_MN ? (2048 >> 4) : (32 >> 4), b_kstep = B_MN ? (2048 >> 4) : (32 >> 4);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const uint32_t sA_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sB_hi = sA_hi + Cfg::A_PLANE;
+                    const uint32_t sA_lo = sB_hi + Cfg::B_PLANE;
+                    const uint32_t sB_lo = sA_lo + Cfg::A_PLANE;
+                    const uint64_t dA_hi = make_smem_desc(sA_hi, a_lbo, 1024), dA_lo = make_smem_desc(sA_lo, a_lbo, 1024);
+                    const uint64_t dB_hi = make_smem_desc(sB_hi, b_lbo, 1024), dB_lo = make_smem_desc(sB_lo, b_lbo, 1024);
+                    mbar_wait(&full_hi[stage], phase);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_bf16(d_tmem, dA_hi + k * a_kstep, dB_hi + k * b_kstep, idesc, (kb | k) ? 1u : 0u);
+                    mbar_wait(&full_lo[stage], phase);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        umma_bf16(d_tmem, dA_lo + k * a_kstep, dB_hi + k * b_kstep, idesc, 1u);
+                        umma_bf16(d_tmem, dA_hi + k * a_kstep, dB_lo + k * b_kstep, idesc, 1u);
+                    }
+                    umma_commit(&empty[stage]);                 // smem stage reusable once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const GemmEpi& e = p.epi;
+        const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+        const int row_in_tile = quad * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int z = tile / tiles_per_batch;
+            const int r = tile - z * tiles_per_batch;
+            const int m_tile = r % p.num_m_tiles;
+            const int m0 = m_tile * GEMM_BM;
+            const int n0 = (r / p.num_m_tiles) * BN;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int grow = m0 + row_in_tile;
+            const bool row_ok = grow < p.M;
+            float rscale = 1.f, rnorm = 0.f;
+            if (row_ok) {
+                if (e.row_scale) rscale = e.row_scale[z * e.rs_bstride + grow];
+                if (e.mode == 1) rnorm = e.row_norm[grow];
+            }
+            const float* gb_row = e.grp_bias ? e.grp_bias + (long long)(grow / e.grp_rows) * e.ld_gb : nullptr;
+            const float* sub_row = nullptr;
+            if (e.sub) sub_row = e.sub + ((long long)m_tile * e.sub_tile_rows + e.sub_row_off[z] + row_in_tile) * e.ld_sub + e.sub_col_off[z];
+            float* c_row = e.C ? e.C + z * e.c_bstride + (long long)grow * e.ldc : nullptr;
+
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= p.N) break;                   // warp-uniform
+                float v[32];
+                tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN + c * 32), v);
+                tmem_ld_wait();
+                const bool full_chunk = col0 + 32 <= p.N;
+                if (e.mode == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float cn = (col0 + j < p.N) ? e.col_norm[col0 + j] : 0.f;
+                        v[j] = sqrtf(fmaxf(rnorm + cn - 2.f * v[j], 1e-12f));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= e.alpha * rscale;
+                    if (e.col_bias) {
+                        const float* cb = e.col_bias + z * e.cb_bstride + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (full_chunk || col0 + j < p.N) v[j] += __ldg(cb + j);
+                    }
+                    if (gb_row && row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (full_chunk || col0 + j < p.N) v[j] += __ldg(gb_row + col0 + j);
+                    }
+                    if (e.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                }
+                // ---- stores of v ----
+                if (row_ok) {
+                    if (c_row) {
+                        float* dst = c_row + col0;
+                        if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                            float4* d4 = reinterpret_cast<float4*>(dst);
+                            if (e.accumulate) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    float4 o = d4[j];
+                                    v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < p.N) {
+                                    if (e.accumulate) v[j] += dst[j];
+                                    dst[j] = v[j];
+                                }
+                        }
+                    }
+                    if (e.Phi && full_chunk) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(v[2 * j], h0, l0); split_bf16(v[2 * j + 1], h1, l1);
+                            hi[j] = pack_bf16(h0, h1); lo[j] = pack_bf16(l0, l1);
+                        }
+                        const long long off = z * e.p_bstride + (long long)grow * e.ldp + col0;
+                        uint4* ph = reinterpret_cast<uint4*>(e.Phi + off);
+                        uint4* pl = reinterpret_cast<uint4*>(e.Plo + off);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            ph[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            pl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    }
+                }
+                // ---- column reductions (BN statistics / squared-difference pooling) ----
+                if (e.col_sum || e.col_sq) {
+                    if (sub_row) {
+                        const float4* s4 = reinterpret_cast<const float4*>(sub_row + col0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 s = __ldg(s4 + j);
+                            v[4 * j] -= s.x; v[4 * j + 1] -= s.y; v[4 * j + 2] -= s.z; v[4 * j + 3] -= s.w;
+                        }
+                    }
+                    if (!row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
+                    const long long sidx = z * e.stat_bstride + (long long)(m_tile * 4 + quad) * p.N + col0 + lane;
+                    if (e.col_sq) {
+                        float w[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) w[j] = v[j] * v[j];
+                        const float s2 = warp_transpose_sum32(w);
+                        if (col0 + lane < p.N) e.col_sq[sidx] = s2;
+                    }
+                    if (e.col_sum) {
+                        const float s1 = warp_transpose_sum32(v);
+                        if (col0 + lane < p.N) e.col_sum[sidx] = s1;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace grl

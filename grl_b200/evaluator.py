@@ -1,0 +1,185 @@
+"""Drop-in mirror of the reference's matching / evaluation path on B200.
+
+Same names, argument meaning and return types as
+  reid/evaluator/attevaluator.py:15-46   evaluate_seq, pairwise_distance_tensor, cosin_dist
+  reid/evaluator/eva_functions.py:134-184 evaluate
+  reid/evaluator/attevaluator.py:49-163  ATTEvaluator
+but every hot call goes through the C ABI (include/grl_b200.h) into sm_100a kernels.
+No CPU fallback: tensors must live on a CUDA device (numpy inputs are copied there).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _as_cuda_f32(x, device=None):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not x.is_cuda:
+        x = x.to(device if device is not None else "cuda", non_blocking=True)
+    return x.contiguous().float()
+
+
+def _distance(qf, gf, metric):
+    qf = _as_cuda_f32(qf)
+    gf = _as_cuda_f32(gf, qf.device)
+    nq, ng = qf.size(0), gf.size(0)
+    q2 = qf.view(nq, -1)
+    g2 = gf.view(ng, -1)
+    dim = q2.size(1)
+    if g2.size(1) != dim:
+        raise RuntimeError("size mismatch, qf %s vs gf %s" % (tuple(q2.shape), tuple(g2.shape)))
+    if dim % 8:   # TMA rows must be 16-byte multiples: zero-pad the feature axis (does not change any distance)
+        pad = 8 - dim % 8
+        q2 = torch.nn.functional.pad(q2, (0, pad))
+        g2 = torch.nn.functional.pad(g2, (0, pad))
+        dim += pad
+    lib = _lib.load_library()
+    with torch.cuda.device(qf.device):
+        h = _lib.get_handle(qf.device)
+        dist = torch.empty((nq, ng), dtype=torch.float32, device=qf.device)
+        ws_bytes = lib.grl_distance_workspace_bytes(nq, ng, dim)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qf.device)
+        _lib.check(h, lib.grl_distance(h, metric, q2.data_ptr(), g2.data_ptr(), nq, ng, dim, dist.data_ptr(),
+                                       ws.data_ptr(), ws_bytes, _lib.stream_ptr(qf.device)), "grl_distance")
+    return dist
+
+
+def cosin_dist(qf, gf):
+    """attevaluator.py:44-46: `-torch.mm(qf, gf.t())` (split-bf16 tcgen05 GEMM, fp32 accumulate)."""
+    return _distance(qf, gf, 0)
+
+
+def pairwise_distance_tensor(query_x, gallery_x):
+    """attevaluator.py:33-41: sqrt(clamp(|x|^2 + |y|^2 - 2 x.y, min=1e-12))."""
+    return _distance(query_x, gallery_x, 1)
+
+
+def cmc_map_device(distmat, q_pids, g_pids, q_camids, g_camids, max_rank=100):
+    """Runs grl_cmc_map; returns device tensors (cmc_hits int32[max_rank], ap f64[nq], first_hit int32[nq])."""
+    dist = _as_cuda_f32(distmat)
+    dev = dist.device
+    nq, ng = dist.shape
+    ids = [torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).to(device=dev, dtype=torch.int64).contiguous()
+           for a in (q_pids, g_pids, q_camids, g_camids)]
+    if ids[0].numel() != nq or ids[1].numel() != ng or ids[2].numel() != nq or ids[3].numel() != ng:
+        raise RuntimeError("evaluate: id arrays do not match distmat shape %s" % ((nq, ng),))
+    max_rank = min(max_rank, ng)
+    lib = _lib.load_library()
+    with torch.cuda.device(dev):
+        h = _lib.get_handle(dev)
+        hits = torch.empty(max_rank, dtype=torch.int32, device=dev)
+        ap = torch.empty(nq, dtype=torch.float64, device=dev)
+        first = torch.empty(nq, dtype=torch.int32, device=dev)
+        _lib.check(h, lib.grl_cmc_map(h, dist.data_ptr(), dist.stride(0), ids[0].data_ptr(), ids[1].data_ptr(),
+                                      ids[2].data_ptr(), ids[3].data_ptr(), nq, ng, max_rank, hits.data_ptr(),
+                                      ap.data_ptr(), first.data_ptr(), _lib.stream_ptr(dev)), "grl_cmc_map")
+    return hits, ap, first
+
+
+def evaluate(distmat, q_pids, g_pids, q_camids, g_camids, max_rank=100):
+    """eva_functions.py:134-184.  Returns (all_cmc np.float32[max_rank], mAP float) like the reference.
+
+    `distmat` may be a CUDA tensor (stays on the device) or a numpy array (copied to the device).
+    When fewer than max_rank gallery rows exist, max_rank shrinks like :136-138 (the reference then
+    crashes on ragged rows if junk removal shortens them further; here the curve is simply padded).
+    """
+    num_q, num_g = distmat.shape
+    if num_g < max_rank:
+        max_rank = num_g
+        print("Note: number of gallery samples is quite small, got {}".format(num_g))
+    hits, ap, first = cmc_map_device(distmat, q_pids, g_pids, q_camids, g_camids, max_rank)
+    hits = hits.cpu().numpy()
+    ap = ap.cpu().numpy()
+    valid = ap >= 0
+    num_valid_q = float(valid.sum())
+    assert num_valid_q > 0, "Error: all query identities do not appear in gallery"
+    all_cmc = hits.astype(np.float32) / num_valid_q      # :179-180 (float32 sum, python-float divide)
+    mAP = np.mean(ap[valid])                             # :182
+    return all_cmc, mAP
+
+
+def evaluate_seq(distmat, query_pids, query_camids, gallery_pids, gallery_camids, path=None, cmc_topk=[1, 5, 10, 20]):
+    """attevaluator.py:15-30 (note the pids/camids argument order); prints like the reference, returns Rank-1."""
+    query_ids = np.array(query_pids)
+    gallery_ids = np.array(gallery_pids)
+    query_cams = np.array(query_camids)
+    gallery_cams = np.array(gallery_camids)
+    cmc_scores, mAP = evaluate(distmat, query_ids, gallery_ids, query_cams, gallery_cams)
+    print('Mean AP: {:4.1%}'.format(mAP))
+    for r in cmc_topk:
+        print("Rank-{:<3}: {:.1%}".format(r, cmc_scores[r - 1]))
+    print("------------------")
+    return cmc_scores[0]
+
+
+def argsort_rows(distmat):
+    """np.argsort(distmat, axis=1) (eva_functions.py:139) as a stable (distance, index) sort; ng <= 16384."""
+    dist = _as_cuda_f32(distmat)
+    nq, ng = dist.shape
+    lib = _lib.load_library()
+    with torch.cuda.device(dist.device):
+        h = _lib.get_handle(dist.device)
+        order = torch.empty((nq, ng), dtype=torch.int32, device=dist.device)
+        _lib.check(h, lib.grl_argsort_rows(h, dist.data_ptr(), dist.stride(0), nq, ng, order.data_ptr(),
+                                           _lib.stream_ptr(dist.device)), "grl_argsort_rows")
+    return order
+
+
+class ATTEvaluator(object):
+    """attevaluator.py:49-163 with the hot calls replaced; loaders/models are the caller's (PyTorch/cuDNN backbone)."""
+
+    def __init__(self, cnn_model, Siamese_model, only_eval):
+        super(ATTEvaluator, self).__init__()
+        self.cnn_model = cnn_model
+        self.siamese_model = Siamese_model
+        self.only_eval = only_eval
+
+    @torch.no_grad()
+    def extract_feature(self, data_loader):
+        self.cnn_model.eval()
+        self.siamese_model.eval()
+        qf, q_pids, q_camids = [], [], []
+        for i, inputs in enumerate(data_loader):
+            imgs, pids, camids = inputs
+            if self.only_eval:                                   # 'dense' mode, attevaluator.py:68-98
+                b, n, s, c, h, w = imgs.size()
+                imgs = imgs.view(b * n, s, c, h, w).cuda()
+                feats = []
+                for y in range(int(math.ceil(b * n * 1.0 / 8))):  # chunks of 8 clips (:72-77)
+                    clips = imgs[y * 8:(y + 1) * 8]
+                    x_uncorr, feats_corr = self.cnn_model(clips)
+                    out_frame = self.siamese_model.self_attention(feats_corr)
+                    feats.append(torch.cat((x_uncorr, out_frame, feats_corr.mean(dim=1)), dim=1))
+                feats = torch.cat(feats, 0).mean(dim=0)           # mean over clips (:83-84 / :94-95)
+                qf.append(feats.unsqueeze(0))
+            else:                                                 # one clip per tracklet (:100-117)
+                imgs = imgs.cuda()
+                x_uncorr, feats_corr = self.cnn_model(imgs)
+                out_frame = self.siamese_model.self_attention(feats_corr)
+                qf.append(torch.cat((x_uncorr, out_frame, feats_corr.mean(dim=1)), dim=1))
+            q_pids.extend(pids)
+            q_camids.extend(camids)
+        qf = torch.cat(qf, 0)
+        return qf, np.asarray(q_pids), np.asarray(q_camids)
+
+    def evaluate(self, query, gallery, query_loader, gallery_loader, path, visual, rerank):
+        if visual:
+            raise NotImplementedError("rank visualisation is debug tooling outside the hot path (SURVEY.md §2)")
+        if rerank:
+            raise NotImplementedError("k-reciprocal re-ranking is a 'next' row (SURVEY.md §8(f)-3)")
+        qf, q_pids, q_camids = self.extract_feature(query_loader)
+        print('Done, obtained {}-by-{} matrix'.format(qf.size(0), qf.size(1)))
+        gf, g_pids, g_camids = self.extract_feature(gallery_loader)
+        gf = torch.cat((qf, gf), 0)                               # :143-145 queries join the gallery
+        g_pids = np.append(q_pids, g_pids)
+        g_camids = np.append(q_camids, g_camids)
+        print('Done, obtained {}-by-{} matrix'.format(gf.size(0), gf.size(1)))
+        print("Computing distance matrix")
+        distmat = cosin_dist(qf, gf)                              # stays on the device (no 74 MB D2H, :150)
+        return evaluate_seq(distmat, q_pids, q_camids, g_pids, g_camids, path)

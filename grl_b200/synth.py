@@ -1,7 +1,7 @@
 """Seeded synthetic inputs for the GRL hot path.
 
 Everything here is *data generation*, not algorithm: it is shared by the tests,
-the golden-vector script (oracle/make_golden.py), smoke() and bench.py so that
+the golden-vector script, smoke() and bench.py so that
 the reference, the oracle and the CUDA path all see identical tensors.
 
 numpy's PCG64 `default_rng` is used (stream stability is guaranteed by numpy),

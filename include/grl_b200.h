@@ -1,0 +1,203 @@
+/* grl_b200 — C ABI of the B200-native GRL hot path (sm_100a).
+ *
+ * The reference (flysnowtiger/GRL) is pure Python/PyTorch and has NO FFI: its seams for
+ * this path are Python call signatures.  Each entry point below names the reference
+ * interface it replaces (file:line under /root/reference); INTEGRATION.md shows the
+ * ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - All tensor pointers are DEVICE pointers (fp32, contiguous, row-major / NCHW) unless
+ *     the parameter name ends in `_host`.  The caller owns every buffer, including the
+ *     workspace; the library performs no hidden device allocation on the hot path.
+ *   - Work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*);
+ *     calls return without synchronising unless documented.
+ *   - Return 0 on success, a negative GRL_E* code otherwise; grl_last_error() gives text.
+ *     Nothing throws across the boundary.  There is no CPU fallback.
+ */
+#ifndef GRL_B200_H
+#define GRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define GRL_OK 0
+#define GRL_EINVAL (-1)   /* bad shape / alignment / null pointer / unsupported mode */
+#define GRL_ECUDA (-2)    /* CUDA runtime or driver error (message has the cudaError) */
+#define GRL_EARCH (-3)    /* device is not sm_100 */
+#define GRL_ENOMEM (-4)   /* caller-provided workspace too small */
+
+typedef struct grl_handle grl_handle;
+
+/* ---- lifecycle -------------------------------------------------------------------- */
+int grl_create(int device, grl_handle** out);
+void grl_destroy(grl_handle* h);
+const char* grl_last_error(const grl_handle* h);   /* h may be NULL: last create() error */
+const char* grl_version(void);
+int grl_num_sms(const grl_handle* h);
+
+/* ---- dense contraction primitive (test/debug surface of the tcgen05 kernel) -------- */
+/* D[z][m][n] = sum_k A[z][m][k] * B[z][n][k], split-bf16 (3 MMA) with fp32 accumulation.
+ * Operands are fp32; they are split into bf16 hi/lo planes inside `workspace`.
+ * a_mn_major/b_mn_major = 0: operand stored [rows][K] (K contiguous); 1: stored [K][rows].
+ * Epilogue: v = alpha*acc; v *= row_scale[m]; v += col_bias[n]; relu; optional C += v.
+ * Optional outputs: col_sum/col_sq [4*ceil(M/128)][N] per-(tile,warp) partial column sums,
+ * planes_hi/lo bf16 [M][N].  bn = 0 (auto) | 128 | 256 selects the N tile.                */
+typedef struct grl_gemm_desc {
+    int M, N, K, batch;
+    int a_mn_major, b_mn_major;
+    long long lda, ldb, ldc;            /* leading dimensions in elements */
+    long long a_bstride, b_bstride, c_bstride;
+    float alpha;
+    const float* row_scale;             /* [M] or NULL */
+    const float* col_bias;              /* [N] or NULL */
+    int relu, accumulate, bn;
+    float* col_sum;                     /* or NULL */
+    float* col_sq;                      /* or NULL */
+    uint16_t* planes_hi;                /* bf16 bits, or NULL */
+    uint16_t* planes_lo;
+} grl_gemm_desc;
+size_t grl_gemm_workspace_bytes(const grl_gemm_desc* d);
+int grl_gemm_bf16x3(grl_handle* h, const grl_gemm_desc* d, const float* A, const float* B, float* C,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- matching / evaluation ---------------------------------------------------------- */
+/* cosin_dist(qf, gf) = -qf @ gf.T           reid/evaluator/attevaluator.py:44-46
+ * pairwise_distance_tensor(qf, gf)          reid/evaluator/attevaluator.py:33-41
+ * q [nq][dim], g [ng][dim] fp32 -> dist [nq][ng] fp32.  metric: 0 = negative dot, 1 = L2. */
+#define GRL_METRIC_NEG_DOT 0
+#define GRL_METRIC_L2 1
+size_t grl_distance_workspace_bytes(int nq, int ng, int dim);
+int grl_distance(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim,
+                 float* dist, void* workspace, size_t workspace_bytes, void* stream);
+
+/* eva_functions.evaluate(distmat, q_pids, g_pids, q_camids, g_camids, max_rank)
+ *                                            reid/evaluator/eva_functions.py:134-184
+ * Sort-free: per query, rank of each positive = #kept gallery rows strictly closer (ties: lower
+ * index first == stable argsort).  Junk (same pid & same cam) removed, queries without a match
+ * skipped.  Outputs (device): cmc_hits int32[max_rank] (number of valid queries whose first hit
+ * is at rank <= r), ap double[nq] (-1 for skipped queries), first_hit int32[nq] (-1 skipped).
+ * The Python wrapper turns these into (np.float32[max_rank], float) exactly like :179-182.   */
+int grl_cmc_map(grl_handle* h, const float* dist, long long ld_dist, const int64_t* q_pid, const int64_t* g_pid,
+                const int64_t* q_cam, const int64_t* g_cam, int nq, int ng, int max_rank,
+                int32_t* cmc_hits, double* ap, int32_t* first_hit, void* stream);
+
+/* np.argsort(distmat, axis=1)                reid/evaluator/eva_functions.py:139
+ * Stable (distance, index) row sort, ng <= 16384.  order int32 [nq][ng].                    */
+int grl_argsort_rows(grl_handle* h, const float* dist, long long ld_dist, int nq, int ng, int32_t* order, void* stream);
+
+/* Gallery-sharded retrieval (BASELINE.json config 5; no reference counterpart: the reference
+ * materialises the full matrix and argsorts it on the CPU, eva_functions.py:139).
+ * grl_topk_rows: k smallest (distance, index) per row of a distance tile, merged into the running
+ * per-query lists top_d/top_i [nq][k] (initialise top_d to +inf, top_i to -1 via grl_topk_init).
+ * idx_base is added to column indices (global gallery index of column 0).
+ * grl_topk_merge: merges `nshards` lists laid out [nshards][nq][k] into out_d/out_i [nq][k],
+ * ties by lower global index, so the result does not depend on the shard count.              */
+int grl_topk_init(grl_handle* h, float* top_d, int64_t* top_i, int nq, int k, void* stream);
+int grl_topk_rows(grl_handle* h, const float* dist, long long ld_dist, int nq, int ncols, int k, int64_t idx_base,
+                  float* top_d, int64_t* top_i, void* stream);
+int grl_topk_merge(grl_handle* h, const float* all_d, const int64_t* all_i, int nshards, int nq, int k,
+                   float* out_d, int64_t* out_i, void* stream);
+
+/* ---- GCE + TRL head ------------------------------------------------------------------ */
+/* Parameter block: device pointers to the reference's own state_dict tensors (fp32), in the
+ * reference's names (reid/models/basebranch.py:38-50, reid/models/grl_model.py:88-128).
+ * BN buffers (running_mean / running_var) are updated in place in train mode exactly like
+ * torch.nn.BatchNorm (momentum 0.1, unbiased variance); num_batches_tracked is advanced by the
+ * Python wrapper (+1 per GCE BN, +T per TRL BN per forward).                                 */
+typedef struct grl_bn_params {
+    const float* weight;
+    const float* bias;
+    float* running_mean;
+    float* running_var;
+} grl_bn_params;
+
+typedef struct grl_head_params {
+    /* GCE (Backbone.glo_fc / Backbone.corr_atte) */
+    const float* glo_fc_w;      /* [1024][2048] */
+    const float* glo_fc_b;      /* [1024] */
+    grl_bn_params glo_bn;       /* BatchNorm1d(1024) */
+    const float* atte0_w;       /* [1024][3072]  conv1x1, no bias */
+    grl_bn_params atte_bn1;     /* BatchNorm2d(1024) */
+    const float* atte2_w;       /* [256][1024] */
+    grl_bn_params atte_bn3;     /* BatchNorm2d(256) */
+    const float* atte5_w;       /* [256] */
+    grl_bn_params atte_bn6;     /* BatchNorm2d(1) */
+    /* TRL, index 0 = forward direction, 1 = backward direction */
+    const float* f1_w[2];       /* [2048][2048] */
+    const float* f1_b[2];
+    const float* f2_w[2];
+    const float* f2_b[2];
+    const float* se1_w[2];      /* channel_atte_*_corr.0.weight [128][2048] */
+    const float* se2_w[2];      /* channel_atte_*_corr.2.weight [2048][128] */
+    const float* memo_conv1_w[2];   /* [512][2048] */
+    grl_bn_params memo_bn1[2];
+    const float* memo_conv2_w[2];   /* [512][512] */
+    grl_bn_params memo_bn2[2];
+    const float* memo_conv3_w[2];   /* [2048][512] */
+    grl_bn_params memo_bn3[2];
+} grl_head_params;
+
+/* Gradients w.r.t. the same tensors (fp32, same shapes); every pointer must be non-NULL.
+ * They are OVERWRITTEN (not accumulated) by grl_head_backward.                              */
+typedef struct grl_head_grads {
+    float* glo_fc_w; float* glo_fc_b; float* glo_bn_w; float* glo_bn_b;
+    float* atte0_w; float* atte_bn1_w; float* atte_bn1_b;
+    float* atte2_w; float* atte_bn3_w; float* atte_bn3_b;
+    float* atte5_w; float* atte_bn6_w; float* atte_bn6_b;
+    float* f1_w[2]; float* f1_b[2]; float* f2_w[2]; float* f2_b[2];
+    float* se1_w[2]; float* se2_w[2];
+    float* memo_conv1_w[2]; float* memo_bn1_w[2]; float* memo_bn1_b[2];
+    float* memo_conv2_w[2]; float* memo_bn2_w[2]; float* memo_bn2_b[2];
+    float* memo_conv3_w[2]; float* memo_bn3_w[2]; float* memo_bn3_b[2];
+} grl_head_grads;
+
+/* Workspace for B clips of T frames.  save_for_backward != 0 keeps every per-step activation
+ * (needed by grl_head_backward); 0 reuses one step slot (inference).                          */
+size_t grl_head_workspace_bytes(int B, int T, int save_for_backward);
+
+/* Fused GCE + TRL forward.
+ *   Backbone.forward after self.base     reid/models/basebranch.py:56-68
+ *   TRLBlock.forward                     reid/models/grl_model.py:131-180
+ * x         [B*T][2048][16][8]  layer4 maps (NCHW)
+ * train     1: BatchNorm batch statistics (+ running-buffer update), 0: running statistics
+ * f_uncorr  [B][2048]     f_corr [B][T][2048]     corr_map [B*T][1][16][8]
+ * x_uncorr / x_corr [B*T][2048][16][8]: optional (NULL to skip; the fused path never needs them). */
+int grl_head_forward(grl_handle* h, const grl_head_params* p, const float* x, int B, int T, int train,
+                     float* f_uncorr, float* f_corr, float* corr_map, float* x_uncorr, float* x_corr,
+                     void* workspace, size_t workspace_bytes, int save_for_backward, void* stream);
+
+/* Backward of grl_head_forward (autograd replacement for the same reference lines).  Needs the
+ * workspace of a train=1, save_for_backward=1 forward with the same (B,T) and unchanged params.
+ * d_f_uncorr [B][2048], d_f_corr [B][T][2048]; optional upstream grads of the stand-alone outputs
+ * d_x_uncorr / d_x_corr [B*T][2048][16][8] and d_corr_map [B*T][128] (NULL = zero).
+ * dx [B*T][2048][16][8]; grads: every parameter gradient.                                      */
+int grl_head_backward(grl_handle* h, const grl_head_params* p, const float* x, int B, int T,
+                      const float* d_f_uncorr, const float* d_f_corr,
+                      const float* d_x_uncorr, const float* d_x_corr, const float* d_corr_map,
+                      float* dx, const grl_head_grads* grads,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Debug/test: byte offset and size of a named intermediate inside the head workspace
+ * (e.g. "xp_hi", "y1", "m", "f2", "memo_h1").  Returns GRL_EINVAL for unknown names.         */
+int grl_head_ws_lookup(int B, int T, int save_for_backward, const char* name, size_t* offset, size_t* bytes);
+
+/* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches).   */
+long long grl_launch_count(const grl_handle* h);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRL_B200_H */

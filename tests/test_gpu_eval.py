@@ -1,0 +1,141 @@
+"""GPU parity: matching / evaluation kernels through the C ABI vs the oracle (tests only)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from grl_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from grl_b200 import _lib, evaluator
+    return _lib, evaluator
+
+
+def assert_same_ranking_up_to_ties(d_got, d_ref, tol=1e-5):
+    """Rankings must be identical except where the reference distances tie within `tol` (north-star)."""
+    o_got = np.argsort(d_got, axis=1, kind="stable")
+    o_ref = np.argsort(d_ref, axis=1, kind="stable")
+    diff = o_got != o_ref
+    if diff.any():
+        rows, cols = np.nonzero(diff)
+        a = d_ref[rows, o_got[rows, cols]]
+        b = d_ref[rows, o_ref[rows, cols]]
+        assert np.all(np.abs(a - b) <= tol), "ranking differs beyond ties: max gap %g" % np.abs(a - b).max()
+
+
+@pytest.mark.parametrize("nq,ng,dim", [(64, 300, 64), (200, 900, 2048), (130, 517, 6144), (33, 70, 100)])
+def test_distances_match_oracle(nq, ng, dim):
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    rng = np.random.default_rng(nq + ng)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    g = rng.standard_normal((ng, dim)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    g /= np.linalg.norm(g, axis=1, keepdims=True)
+    d = ev.cosin_dist(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda()).cpu().numpy()
+    ref64 = -(q.astype(np.float64) @ g.astype(np.float64).T)
+    assert np.abs(d - ref64).max() < 2e-6          # fp32 sgemm itself is ~1e-7 here
+    assert_same_ranking_up_to_ties(d, eo.cosin_dist(q, g))
+    l2 = ev.pairwise_distance_tensor(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda()).cpu().numpy()
+    ref_l2 = eo.pairwise_distance(q, g)
+    assert np.abs(l2 ** 2 - ref_l2 ** 2).max() < 5e-6
+    assert_same_ranking_up_to_ties(l2, ref_l2, tol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["eval_small", "eval_rank10", "eval_ties"])
+def test_evaluate_matches_reference_golden(golden_dir, name):
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    qf, gf, qp, gp, qc, gc = synth.make_eval_set(int(g["nq"]), int(g["ng_extra"]), int(g["dim"]), seed=int(g["seed"]),
+                                                 num_ids=25, noise=float(g["noise"]), missing_query_frac=0.05)
+    mr = int(g["max_rank"])
+    cmc, mAP = ev.evaluate(g["d_cos"], qp, gp, qc, gc, mr)
+    assert cmc.dtype == np.float32 and cmc.shape == (mr,)
+    if int(g["quantize"]) == 0:
+        assert np.array_equal(cmc, g["cmc"]) and abs(mAP - float(g["mAP"])) < 1e-12
+        # end to end from features: distance kernel + metric kernel
+        d = ev.cosin_dist(torch.from_numpy(qf).cuda(), torch.from_numpy(gf).cuda())
+        cmc2, mAP2 = ev.evaluate(d, qp, gp, qc, gc, mr)
+        assert np.abs(cmc2 - g["cmc"]).max() < 1e-4 and abs(mAP2 - float(g["mAP"])) < 1e-4
+    else:   # exact ties: the kernel is the stable-sort answer; numpy's introsort order is implementation-defined
+        cmc_s, mAP_s = eo.evaluate_literal(g["d_cos"], qp, gp, qc, gc, mr, kind="stable")
+        assert np.array_equal(cmc, cmc_s) and abs(mAP - mAP_s) < 1e-12
+
+
+def test_evaluate_mars_shape_vs_c_oracle():
+    _, ev = _mods()
+    from tests.test_oracle_eval import c_evaluate, load_c_oracle
+    qf, gf, qp, gp, qc, gc = synth.make_eval_set(1980, 7350, 2048, seed=0, noise=4.0)
+    d = ev.cosin_dist(torch.from_numpy(qf).cuda(), torch.from_numpy(gf).cuda())
+    cmc, mAP = ev.evaluate(d, qp, gp, qc, gc)
+    dn = d.cpu().numpy()
+    cmc_o, mAP_o, nv, ap_o = c_evaluate(load_c_oracle(), dn, qp, gp, qc, gc)
+    assert np.array_equal(cmc, cmc_o) and abs(mAP - mAP_o) < 1e-12
+    assert 0.05 < mAP < 0.999          # the synthetic set is neither trivial nor random
+    # against the fp32 CPU distance matrix (the reference's own arithmetic): within 1e-4
+    from oracle import eval_oracle as eo
+    cmc_r, mAP_r, _, _ = c_evaluate(load_c_oracle(), eo.cosin_dist(qf, gf), qp, gp, qc, gc)
+    assert np.abs(cmc - cmc_r).max() < 1e-4 and abs(mAP - mAP_r) < 1e-4
+
+
+def test_evaluate_many_positives_and_no_valid_query():
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    rng = np.random.default_rng(1)
+    nq, ng = 7, 3000
+    d = rng.standard_normal((nq, ng)).astype(np.float32)
+    qp = np.ones(nq, np.int64); qc = np.zeros(nq, np.int64)
+    gp = np.ones(ng, np.int64); gc = rng.integers(0, 3, ng)      # ~2000 positives per query: several smem rounds
+    cmc, mAP = ev.evaluate(d, qp, gp, qc, gc, 50)
+    cmc_o, mAP_o, _, _ = eo.evaluate_rankcount(d, qp, gp, qc, gc, 50)
+    assert np.array_equal(cmc, cmc_o) and abs(mAP - mAP_o) < 1e-12
+    with pytest.raises(AssertionError):
+        ev.evaluate(d, qp + 5, gp, qc, gc)
+
+
+def test_argsort_rows_is_stable_argsort():
+    _, ev = _mods()
+    rng = np.random.default_rng(2)
+    for nq, ng in ((5, 9330), (3, 1), (4, 1000)):
+        d = rng.standard_normal((nq, ng)).astype(np.float32)
+        d[:, ::5] = np.round(d[:, ::5])        # ties
+        d[0, :3] = [0.0, -0.0, 0.0]
+        order = ev.argsort_rows(torch.from_numpy(d).cuda()).cpu().numpy()
+        assert np.array_equal(order, np.argsort(d, axis=1, kind="stable"))
+
+
+def test_topk_stream_and_merge_shard_invariant():
+    _lib, ev = _mods()
+    from oracle import eval_oracle as eo
+    lib = _lib.load_library(); h = _lib.get_handle()
+    rng = np.random.default_rng(3)
+    nq, ng, k = 37, 20000, 100
+    d = rng.standard_normal((nq, ng)).astype(np.float32)
+    d[:, ::9] = d[:, 4:5]
+    v_ref, i_ref = eo.topk_stable(d, k)
+    dd = torch.from_numpy(d).cuda()
+    st = _lib.stream_ptr()
+
+    def run_shard(lo, hi, chunk):
+        td = torch.empty((nq, k), device="cuda"); ti = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        _lib.check(h, lib.grl_topk_init(h, td.data_ptr(), ti.data_ptr(), nq, k, st), "init")
+        for c0 in range(lo, hi, chunk):
+            c1 = min(hi, c0 + chunk)
+            tile = dd[:, c0:c1].contiguous()
+            _lib.check(h, lib.grl_topk_rows(h, tile.data_ptr(), tile.stride(0), nq, c1 - c0, k, c0, td.data_ptr(),
+                                            ti.data_ptr(), st), "topk")
+        return td, ti
+
+    for shards in (1, 2, 4, 8):
+        w = ng // shards
+        parts = [run_shard(s * w, (s + 1) * w, 1777) for s in range(shards)]
+        all_d = torch.stack([p[0] for p in parts]).contiguous(); all_i = torch.stack([p[1] for p in parts]).contiguous()
+        od = torch.empty((nq, k), device="cuda"); oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        _lib.check(h, lib.grl_topk_merge(h, all_d.data_ptr(), all_i.data_ptr(), shards, nq, k, od.data_ptr(), oi.data_ptr(), st), "merge")
+        assert np.array_equal(od.cpu().numpy(), v_ref) and np.array_equal(oi.cpu().numpy(), i_ref)
