@@ -1,0 +1,375 @@
+"""Host-side mirror of the reference's GCE + TRL modules on top of the C ABI.
+
+Reference interfaces kept (same attribute names => same state_dict keys, same call signatures):
+  Backbone(height, width).forward(x, b, t) -> (x_uncorr, x_corr, corr_map)   reid/models/basebranch.py:21-68
+  BasicBlock(inplanes, planes)                                                reid/models/grl_model.py:51-85
+  TRLBlock(feat_num).forward(x_uncorr, x_corr) -> (f_uncorr, f_corr)          reid/models/grl_model.py:87-180
+  ResNet50_GRL_Model(...).forward(inputs, training=True) -> (x_uncorr, x_corr) reid/models/grl_model.py:184-228
+  resnet50_grl(*args, **kwargs)                                               reid/models/grl_model.py:231-232
+
+All head math runs in libgrl_b200.so (sm_100a).  There is no PyTorch/CPU fallback: on a machine
+without the CUDA library or a B200 the forward raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import _lib
+
+TP = "temporal_learning_block."
+_DIRS = (("forward", "foreward"), ("backward", "backward"))
+
+
+def head_param_names():
+    """state_dict keys (relative to ResNet50_GRL_Model) consumed by the head, in a fixed order."""
+    names = ["backbone.glo_fc.0.weight", "backbone.glo_fc.0.bias", "backbone.glo_fc.1.weight", "backbone.glo_fc.1.bias",
+             "backbone.corr_atte.0.weight", "backbone.corr_atte.1.weight", "backbone.corr_atte.1.bias",
+             "backbone.corr_atte.2.weight", "backbone.corr_atte.3.weight", "backbone.corr_atte.3.bias",
+             "backbone.corr_atte.5.weight", "backbone.corr_atte.6.weight", "backbone.corr_atte.6.bias"]
+    for direction, atte in _DIRS:
+        m = TP + "uncorr_memo_" + direction
+        names += [TP + direction + "_f1.0.weight", TP + direction + "_f1.0.bias",
+                  TP + direction + "_f2.0.weight", TP + direction + "_f2.0.bias",
+                  TP + "channel_atte_" + atte + "_corr.0.weight", TP + "channel_atte_" + atte + "_corr.2.weight",
+                  m + ".conv1.weight", m + ".bn1.weight", m + ".bn1.bias",
+                  m + ".conv2.weight", m + ".bn2.weight", m + ".bn2.bias",
+                  m + ".conv3.weight", m + ".bn3.weight", m + ".bn3.bias"]
+    return names
+
+
+def head_buffer_names():
+    bn = ["backbone.glo_fc.1", "backbone.corr_atte.1", "backbone.corr_atte.3", "backbone.corr_atte.6"]
+    for direction, _ in _DIRS:
+        bn += [TP + "uncorr_memo_" + direction + ".bn%d" % k for k in (1, 2, 3)]
+    return bn
+
+
+def _bn(sd, prefix):
+    r = _lib.BnParams()
+    r.weight = sd[prefix + ".weight"].data_ptr()
+    r.bias = sd[prefix + ".bias"].data_ptr()
+    r.running_mean = sd[prefix + ".running_mean"].data_ptr()
+    r.running_var = sd[prefix + ".running_var"].data_ptr()
+    return r
+
+
+def pack_params(sd) -> _lib.HeadParams:
+    """Fill the C parameter block with device pointers of fp32, contiguous CUDA tensors."""
+    for k in head_param_names():
+        t = sd[k]
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError("grl_b200 head: parameter %s must be a contiguous float32 CUDA tensor" % k)
+    p = _lib.HeadParams()
+    p.glo_fc_w = sd["backbone.glo_fc.0.weight"].data_ptr()
+    p.glo_fc_b = sd["backbone.glo_fc.0.bias"].data_ptr()
+    p.glo_bn = _bn(sd, "backbone.glo_fc.1")
+    p.atte0_w = sd["backbone.corr_atte.0.weight"].data_ptr()
+    p.atte_bn1 = _bn(sd, "backbone.corr_atte.1")
+    p.atte2_w = sd["backbone.corr_atte.2.weight"].data_ptr()
+    p.atte_bn3 = _bn(sd, "backbone.corr_atte.3")
+    p.atte5_w = sd["backbone.corr_atte.5.weight"].data_ptr()
+    p.atte_bn6 = _bn(sd, "backbone.corr_atte.6")
+    for d, (direction, atte) in enumerate(_DIRS):
+        m = TP + "uncorr_memo_" + direction
+        p.f1_w[d] = sd[TP + direction + "_f1.0.weight"].data_ptr()
+        p.f1_b[d] = sd[TP + direction + "_f1.0.bias"].data_ptr()
+        p.f2_w[d] = sd[TP + direction + "_f2.0.weight"].data_ptr()
+        p.f2_b[d] = sd[TP + direction + "_f2.0.bias"].data_ptr()
+        p.se1_w[d] = sd[TP + "channel_atte_" + atte + "_corr.0.weight"].data_ptr()
+        p.se2_w[d] = sd[TP + "channel_atte_" + atte + "_corr.2.weight"].data_ptr()
+        p.memo_conv1_w[d] = sd[m + ".conv1.weight"].data_ptr()
+        p.memo_bn1[d] = _bn(sd, m + ".bn1")
+        p.memo_conv2_w[d] = sd[m + ".conv2.weight"].data_ptr()
+        p.memo_bn2[d] = _bn(sd, m + ".bn2")
+        p.memo_conv3_w[d] = sd[m + ".conv3.weight"].data_ptr()
+        p.memo_bn3[d] = _bn(sd, m + ".bn3")
+    return p
+
+
+def pack_grads(gd) -> _lib.HeadGrads:
+    g = _lib.HeadGrads()
+    g.glo_fc_w = gd["backbone.glo_fc.0.weight"].data_ptr()
+    g.glo_fc_b = gd["backbone.glo_fc.0.bias"].data_ptr()
+    g.glo_bn_w = gd["backbone.glo_fc.1.weight"].data_ptr()
+    g.glo_bn_b = gd["backbone.glo_fc.1.bias"].data_ptr()
+    g.atte0_w = gd["backbone.corr_atte.0.weight"].data_ptr()
+    g.atte_bn1_w = gd["backbone.corr_atte.1.weight"].data_ptr()
+    g.atte_bn1_b = gd["backbone.corr_atte.1.bias"].data_ptr()
+    g.atte2_w = gd["backbone.corr_atte.2.weight"].data_ptr()
+    g.atte_bn3_w = gd["backbone.corr_atte.3.weight"].data_ptr()
+    g.atte_bn3_b = gd["backbone.corr_atte.3.bias"].data_ptr()
+    g.atte5_w = gd["backbone.corr_atte.5.weight"].data_ptr()
+    g.atte_bn6_w = gd["backbone.corr_atte.6.weight"].data_ptr()
+    g.atte_bn6_b = gd["backbone.corr_atte.6.bias"].data_ptr()
+    for d, (direction, atte) in enumerate(_DIRS):
+        m = TP + "uncorr_memo_" + direction
+        g.f1_w[d] = gd[TP + direction + "_f1.0.weight"].data_ptr()
+        g.f1_b[d] = gd[TP + direction + "_f1.0.bias"].data_ptr()
+        g.f2_w[d] = gd[TP + direction + "_f2.0.weight"].data_ptr()
+        g.f2_b[d] = gd[TP + direction + "_f2.0.bias"].data_ptr()
+        g.se1_w[d] = gd[TP + "channel_atte_" + atte + "_corr.0.weight"].data_ptr()
+        g.se2_w[d] = gd[TP + "channel_atte_" + atte + "_corr.2.weight"].data_ptr()
+        g.memo_conv1_w[d] = gd[m + ".conv1.weight"].data_ptr()
+        g.memo_bn1_w[d] = gd[m + ".bn1.weight"].data_ptr()
+        g.memo_bn1_b[d] = gd[m + ".bn1.bias"].data_ptr()
+        g.memo_conv2_w[d] = gd[m + ".conv2.weight"].data_ptr()
+        g.memo_bn2_w[d] = gd[m + ".bn2.weight"].data_ptr()
+        g.memo_bn2_b[d] = gd[m + ".bn2.bias"].data_ptr()
+        g.memo_conv3_w[d] = gd[m + ".conv3.weight"].data_ptr()
+        g.memo_bn3_w[d] = gd[m + ".bn3.weight"].data_ptr()
+        g.memo_bn3_b[d] = gd[m + ".bn3.bias"].data_ptr()
+    return g
+
+
+def workspace_bytes(B, T, save):
+    return int(_lib.load_library().grl_head_workspace_bytes(B, T, 1 if save else 0))
+
+
+def ws_view(ws, B, T, save, name, dtype, shape):
+    """Debug/test: typed view of a named intermediate inside the head workspace."""
+    off, nbytes = C.c_size_t(), C.c_size_t()
+    rc = _lib.load_library().grl_head_ws_lookup(B, T, 1 if save else 0, name.encode(), C.byref(off), C.byref(nbytes))
+    if rc != 0:
+        raise KeyError(name)
+    return ws[off.value:off.value + nbytes.value].view(dtype).view(*shape) if shape else ws[off.value:off.value + nbytes.value].view(dtype)
+
+
+def _alloc_ws(nbytes, device):
+    # cudaMalloc'd blocks from the caching allocator are 512-byte aligned; over-allocate to get 1024
+    raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    shift = (-raw.data_ptr()) % 1024
+    return raw[shift:shift + nbytes]
+
+
+def head_forward_raw(sd, x, B, T, training, save, want_maps=False, ws=None):
+    """One grl_head_forward call.  Returns (f_uncorr, f_corr, corr_map, x_uncorr|None, x_corr|None, workspace)."""
+    if not x.is_cuda:
+        raise RuntimeError("grl_b200 head needs CUDA tensors (no CPU path exists)")
+    x = x.contiguous().float()
+    if x.dim() != 4 or x.size(0) != B * T or tuple(x.shape[1:]) != (2048, 16, 8):
+        raise RuntimeError("head input must be [b*t, 2048, 16, 8], got %s (b=%d, t=%d)" % (tuple(x.shape), B, T))
+    lib = _lib.load_library()
+    dev = x.device
+    with torch.cuda.device(dev):
+        h = _lib.get_handle(dev)
+        p = pack_params(sd)
+        nbytes = workspace_bytes(B, T, save)
+        if ws is None or ws.numel() < nbytes:
+            ws = _alloc_ws(nbytes, dev)
+        f_uncorr = torch.empty((B, 2048), device=dev)
+        f_corr = torch.empty((B, T, 2048), device=dev)
+        corr_map = torch.empty((B * T, 1, 16, 8), device=dev)
+        xu = torch.empty_like(x) if want_maps else None
+        xc = torch.empty_like(x) if want_maps else None
+        rc = lib.grl_head_forward(h, C.byref(p), x.data_ptr(), B, T, 1 if training else 0, f_uncorr.data_ptr(), f_corr.data_ptr(),
+                                  corr_map.data_ptr(), _lib.ptr(xu), _lib.ptr(xc), ws.data_ptr(), ws.numel(), 1 if save else 0,
+                                  _lib.stream_ptr(dev))
+        _lib.check(h, rc, "grl_head_forward")
+    return f_uncorr, f_corr, corr_map, xu, xc, ws
+
+
+def head_backward_raw(sd, x, B, T, ws, d_f_uncorr, d_f_corr, d_x_uncorr=None, d_x_corr=None, d_corr_map=None):
+    """One grl_head_backward call.  Returns (dx, {param name: grad})."""
+    lib = _lib.load_library()
+    dev = x.device
+    with torch.cuda.device(dev):
+        h = _lib.get_handle(dev)
+        p = pack_params(sd)
+        grads = {k: torch.empty_like(sd[k]) for k in head_param_names()}
+        g = pack_grads(grads)
+        dx = torch.empty_like(x)
+        cont = lambda t: None if t is None else t.contiguous().float()
+        d_f_uncorr, d_f_corr = cont(d_f_uncorr), cont(d_f_corr)
+        d_x_uncorr, d_x_corr, d_corr_map = cont(d_x_uncorr), cont(d_x_corr), cont(d_corr_map)
+        rc = lib.grl_head_backward(h, C.byref(p), x.data_ptr(), B, T, d_f_uncorr.data_ptr(), d_f_corr.data_ptr(),
+                                   _lib.ptr(d_x_uncorr), _lib.ptr(d_x_corr), _lib.ptr(d_corr_map), dx.data_ptr(), C.byref(g),
+                                   ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(h, rc, "grl_head_backward")
+    return dx, grads
+
+
+class _HeadFunction(torch.autograd.Function):
+    """autograd node for the fused head: (x, *params) -> (f_uncorr, f_corr, corr_map, x_uncorr, x_corr)."""
+
+    @staticmethod
+    def forward(ctx, x, B, T, training, want_maps, names, sd_buffers, *params):
+        sd = dict(zip(names, params))
+        sd.update(sd_buffers)
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for t in params))
+        if need_grad and not training:
+            raise RuntimeError("grl_b200 head: backward with eval-mode BatchNorm is not supported; call .train() "
+                               "or wrap inference in torch.no_grad()")
+        f_uncorr, f_corr, corr_map, xu, xc, ws = head_forward_raw(sd, x, B, T, training, save=need_grad, want_maps=want_maps)
+        ctx.B, ctx.T, ctx.names, ctx.sd_buffers, ctx.want_maps = B, T, names, sd_buffers, want_maps
+        ctx.ws = ws if need_grad else None
+        ctx.save_for_backward(x, *params)
+        if not want_maps:
+            xu = x.new_empty(0)
+            xc = x.new_empty(0)
+        if not want_maps:
+            ctx.mark_non_differentiable(xu, xc)
+        return f_uncorr, f_corr, corr_map, xu, xc
+
+    @staticmethod
+    def backward(ctx, g_fu, g_fc, g_map, g_xu, g_xc):
+        x, *params = ctx.saved_tensors
+        sd = dict(zip(ctx.names, params))
+        sd.update(ctx.sd_buffers)
+        B, T = ctx.B, ctx.T
+        zeros = lambda shape: torch.zeros(shape, device=x.device)
+        g_fu = zeros((B, 2048)) if g_fu is None else g_fu
+        g_fc = zeros((B, T, 2048)) if g_fc is None else g_fc
+        if not ctx.want_maps:
+            g_xu = g_xc = None
+        dx, grads = head_backward_raw(sd, x.contiguous().float(), B, T, ctx.ws, g_fu, g_fc, g_xu, g_xc, g_map)
+        ctx.ws = None
+        return (dx, None, None, None, None, None, None) + tuple(grads[k] for k in ctx.names)
+
+
+def _collect(module_sd_items, prefix_map):
+    out = {}
+    for name, t in module_sd_items:
+        out[prefix_map + name] = t
+    return out
+
+
+class _HeadState:
+    """Gathers parameters/buffers of a Backbone (GCE part) and a TRLBlock under the reference's key names."""
+
+    @staticmethod
+    def tensors(backbone, trl):
+        params, buffers = {}, {}
+        for n, t in backbone.named_parameters():
+            if not n.startswith("base."):
+                params["backbone." + n] = t
+        for n, t in backbone.named_buffers():
+            if not n.startswith("base."):
+                buffers["backbone." + n] = t
+        for n, t in trl.named_parameters():
+            params[TP + n] = t
+        for n, t in trl.named_buffers():
+            buffers[TP + n] = t
+        return params, buffers
+
+
+def run_head(backbone, trl, x, b, t, want_maps=False):
+    """Fused GCE+TRL through the C ABI with autograd.  x: layer4 maps [b*t, 2048, 16, 8]."""
+    params, buffers = _HeadState.tensors(backbone, trl)
+    names = head_param_names()
+    training = backbone.training
+    out = _HeadFunction.apply(x, b, t, training, want_maps, names, buffers, *[params[k] for k in names])
+    if training:    # num_batches_tracked bookkeeping (torch/nn/modules/batchnorm.py): +1 per BN call
+        with torch.no_grad():
+            for prefix in head_buffer_names():
+                steps = t if "uncorr_memo" in prefix else 1
+                buffers[prefix + ".num_batches_tracked"] += steps
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# Drop-in modules (same attribute names as the reference => identical state_dict keys)
+# --------------------------------------------------------------------------------------------
+def _resnet50_stride1_base():
+    """conv1..layer4 of a torchvision-style ResNet-50 with layer4 stride 1 (reid/models/resnets1.py:109).
+    Stays in PyTorch/cuDNN by design (north-star); weights are loaded by the caller via state_dict."""
+    import torchvision
+    r = torchvision.models.resnet50(weights=None)
+    r.layer4[0].conv2.stride = (1, 1)
+    r.layer4[0].downsample[0].stride = (1, 1)
+    return nn.Sequential(r.conv1, r.bn1, nn.ReLU(), r.maxpool, r.layer1, r.layer2, r.layer3, r.layer4)
+
+
+class Backbone(nn.Module):
+    """reid/models/basebranch.py:21-68.  `base` is cuDNN ResNet-50; GCE runs in libgrl_b200."""
+
+    def __init__(self, height=256, width=128, base=None):
+        super(Backbone, self).__init__()
+        self.base = _resnet50_stride1_base() if base is None else base
+        self.glo_fc = nn.Sequential(nn.Linear(2048, 1024), nn.BatchNorm1d(1024), nn.ReLU())
+        self.corr_atte = nn.Sequential(
+            nn.Conv2d(2048 + 1024, 1024, 1, 1, bias=False), nn.BatchNorm2d(1024),
+            nn.Conv2d(1024, 256, 1, 1, bias=False), nn.BatchNorm2d(256), nn.ReLU(),
+            nn.Conv2d(256, 1, 1, 1, bias=False), nn.BatchNorm2d(1))
+        self._trl_for_fused = None      # set by ResNet50_GRL_Model (not a submodule: no state_dict change)
+
+    def forward(self, x, b, t):
+        """Stand-alone call (returns the gated maps like the reference)."""
+        raise RuntimeError("Backbone.forward stand-alone needs a TRLBlock partner in this build; use "
+                           "ResNet50_GRL_Model (fused head) or grl_b200.head.run_head(..., want_maps=True)")
+
+
+class BasicBlock(nn.Module):
+    """reid/models/grl_model.py:51-85 (parameter container; the math runs inside the fused TRL kernels)."""
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super(BasicBlock, self).__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, kernel_size=1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU()
+
+
+class TRLBlock(nn.Module):
+    """reid/models/grl_model.py:87-180 (note the reference's spelling `channel_atte_foreward_corr`)."""
+
+    def __init__(self, feat_num):
+        super(TRLBlock, self).__init__()
+        self.feat_num = feat_num
+        self.feat_num_half = int(feat_num / 2)
+        self.uncorr_memo_forward = BasicBlock(2048, 512)
+        self.forward_f1 = nn.Sequential(nn.Conv2d(2048, 2048, 1, 1), nn.ReLU())
+        self.forward_f2 = nn.Sequential(nn.Conv2d(2048, 2048, 1, 1), nn.ReLU())
+        self.channel_atte_foreward_corr = nn.Sequential(nn.Linear(2048, 2048 // 16, bias=False), nn.ReLU(inplace=True),
+                                                        nn.Linear(2048 // 16, 2048, bias=False), nn.Sigmoid())
+        self.uncorr_memo_backward = BasicBlock(2048, 512)
+        self.backward_f1 = nn.Sequential(nn.Conv2d(2048, 2048, 1, 1), nn.ReLU())
+        self.backward_f2 = nn.Sequential(nn.Conv2d(2048, 2048, 1, 1), nn.ReLU())
+        self.channel_atte_backward_corr = nn.Sequential(nn.Linear(2048, 2048 // 16, bias=False), nn.ReLU(inplace=True),
+                                                        nn.Linear(2048 // 16, 2048, bias=False), nn.Sigmoid())
+
+
+class ResNet50_GRL_Model(nn.Module):
+    """reid/models/grl_model.py:184-228.  forward(inputs[B,T,3,H,W]) -> (x_uncorr [B,2048], x_corr [B,T,2048])."""
+
+    def __init__(self, num_feat=2048, num_features=512, height=256, width=128, pretrained=True, dropout=0, numclasses=0,
+                 base=None):
+        super(ResNet50_GRL_Model, self).__init__()
+        self.pretrained = pretrained
+        self.num_feat = num_feat
+        self.dropout = dropout
+        self.num_classes = numclasses
+        self.output_dim = num_features
+        self.backbone = Backbone(height=height, width=width, base=base)
+        self.temporal_learning_block = TRLBlock(2048)
+        self.corr_bn = nn.BatchNorm1d(2048)
+        nn.init.constant_(self.corr_bn.weight, 1)
+        nn.init.constant_(self.corr_bn.bias, 0)
+        self.uncorr_bn = nn.BatchNorm1d(2048)
+        nn.init.constant_(self.uncorr_bn.weight, 1)
+        nn.init.constant_(self.uncorr_bn.bias, 0)
+
+    def head(self, feat, b, t, want_maps=False):
+        """GCE + TRL on layer4 maps feat [b*t, 2048, 16, 8] (fused C-ABI call)."""
+        return run_head(self.backbone, self.temporal_learning_block, feat, b, t, want_maps)
+
+    def forward(self, inputs, training=True):
+        b, t, c, h, w = inputs.size()
+        im_input = inputs.view(b * t, c, h, w)
+        feat = self.backbone.base(im_input)                                  # PyTorch / cuDNN
+        f_uncorr, f_corr, _, _, _ = self.head(feat, b, t)                    # libgrl_b200 (sm_100a)
+        x_corr = self.corr_bn(f_corr.view(b * t, 2048)).view(b, t, 2048)     # grl_model.py:222-226 (tiny tail, PyTorch)
+        x_corr = F.normalize(x_corr, p=2, dim=2)
+        x_uncorr = self.uncorr_bn(f_uncorr.view(b, 2048)).view(b, 2048)
+        x_uncorr = F.normalize(x_uncorr, p=2, dim=1)
+        return x_uncorr, x_corr
+
+
+def resnet50_grl(*args, **kwargs):
+    return ResNet50_GRL_Model(*args, **kwargs)

@@ -39,7 +39,7 @@ def test_distances_match_oracle(nq, ng, dim):
     g /= np.linalg.norm(g, axis=1, keepdims=True)
     d = ev.cosin_dist(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda()).cpu().numpy()
     ref64 = -(q.astype(np.float64) @ g.astype(np.float64).T)
-    assert np.abs(d - ref64).max() < 2e-6          # fp32 sgemm itself is ~1e-7 here
+    assert np.abs(d - ref64).max() < 5e-6          # split-bf16: ~2^-17 relative per product; well inside the 1e-5 tie window
     assert_same_ranking_up_to_ties(d, eo.cosin_dist(q, g))
     l2 = ev.pairwise_distance_tensor(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda()).cpu().numpy()
     ref_l2 = eo.pairwise_distance(q, g)
@@ -70,7 +70,7 @@ def test_evaluate_matches_reference_golden(golden_dir, name):
 
 def test_evaluate_mars_shape_vs_c_oracle():
     _, ev = _mods()
-    from tests.test_oracle_eval import c_evaluate, load_c_oracle
+    from helpers import c_evaluate, load_c_oracle
     qf, gf, qp, gp, qc, gc = synth.make_eval_set(1980, 7350, 2048, seed=0, noise=4.0)
     d = ev.cosin_dist(torch.from_numpy(qf).cuda(), torch.from_numpy(gf).cuda())
     cmc, mAP = ev.evaluate(d, qp, gp, qc, gc)
@@ -105,7 +105,8 @@ def test_argsort_rows_is_stable_argsort():
     for nq, ng in ((5, 9330), (3, 1), (4, 1000)):
         d = rng.standard_normal((nq, ng)).astype(np.float32)
         d[:, ::5] = np.round(d[:, ::5])        # ties
-        d[0, :3] = [0.0, -0.0, 0.0]
+        if ng >= 3:
+            d[0, :3] = [0.0, -0.0, 0.0]
         order = ev.argsort_rows(torch.from_numpy(d).cuda()).cpu().numpy()
         assert np.array_equal(order, np.argsort(d, axis=1, kind="stable"))
 

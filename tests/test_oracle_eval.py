@@ -1,39 +1,12 @@
 """CPU: pin the evaluator oracle (numpy + C) to the real reference's outputs."""
-import ctypes
 import os
-import subprocess
 
 import numpy as np
 import pytest
 
 from grl_b200 import synth
 from oracle import eval_oracle as eo
-
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-
-
-def load_c_oracle():
-    so = os.path.join(ROOT, "oracle", "_build", "liboracle_eval.so")
-    if not os.path.exists(so):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
-    lib = ctypes.CDLL(so)
-    lib.grl_oracle_evaluate.restype = ctypes.c_int
-    return lib
-
-
-def c_evaluate(lib, d, qp, gp, qc, gc, max_rank=100):
-    d = np.ascontiguousarray(d, np.float32)
-    nq, ng = d.shape
-    mr = min(max_rank, ng)
-    cmc = np.zeros(mr, np.float32)
-    m = ctypes.c_double()
-    ap = np.zeros(nq, np.float64)
-    arr = lambda a: np.ascontiguousarray(a, np.int64).ctypes.data_as(ctypes.c_void_p)
-    nv = lib.grl_oracle_evaluate(d.ctypes.data_as(ctypes.c_void_p), nq, ng, arr(qp), arr(gp), arr(qc), arr(gc),
-                                 max_rank, cmc.ctypes.data_as(ctypes.c_void_p), ctypes.byref(m),
-                                 ap.ctypes.data_as(ctypes.c_void_p))
-    return cmc, m.value, nv, ap
-
+from helpers import c_evaluate, load_c_oracle
 
 def fixture_ids(g):
     return synth.make_eval_set(int(g["nq"]), int(g["ng_extra"]), int(g["dim"]), seed=int(g["seed"]), num_ids=25,
