@@ -118,8 +118,8 @@ static int launch_variant(grl_handle* h, cudaStream_t st, const GemmParams& p, i
 int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, const Operand& A, const Operand& B,
                 GemmEpi epi, int bn) {
     if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return set_error(h, GRL_EINVAL, "gemm: empty problem %dx%dx%d", M, N, K);
-    if (A.mn_major != B.mn_major) return set_error(h, GRL_EINVAL, "gemm: mixed operand majors are not instantiated");
-    if (A.mn_major && (K % GEMM_BK)) return set_error(h, GRL_EINVAL, "gemm: MN-major operands need K %% 64 == 0");
+    if (A.mn_major && !B.mn_major) return set_error(h, GRL_EINVAL, "gemm: MN-major A with K-major B is not instantiated");
+    if ((A.mn_major || B.mn_major) && (K % GEMM_BK)) return set_error(h, GRL_EINVAL, "gemm: MN-major operands need K %% 64 == 0");
     const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
     if (bn == 0) {
         const long long t256 = (long long)m_tiles * ((N + 255) / 256) * batch;
@@ -138,11 +138,15 @@ int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, 
     GRL_TRY(make_tmap(h, &p.tb_lo, B.lo, B.ld, B.bstride, B.mn_major, N, K, batch, bn));
     const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles * batch;
     const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    // K-major/K-major: fprop and the distance GEMM; MN/MN: wgrad; K-major A with MN-major B: dgrad
+    // (weights [Cout][Cin] consumed as B[n = Cin][k = Cout] without a transposed copy).
     if (bn == 256) {
         if (A.mn_major) return launch_variant<256, true, true>(h, st, p, grid);
+        if (B.mn_major) return launch_variant<256, false, true>(h, st, p, grid);
         return launch_variant<256, false, false>(h, st, p, grid);
     }
     if (A.mn_major) return launch_variant<128, true, true>(h, st, p, grid);
+    if (B.mn_major) return launch_variant<128, false, true>(h, st, p, grid);
     return launch_variant<128, false, false>(h, st, p, grid);
 }
 

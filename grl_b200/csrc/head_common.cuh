@@ -55,15 +55,15 @@ constexpr float BN_MOM = 0.1f;
     X(dzc, 4, BW * 2 * R * HC) X(df1_hi, 2, BW * 2 * R * HC) X(df1_lo, 2, BW * 2 * R * HC)         \
     X(df2_hi, 2, BW * P * 2 * HC) X(df2_lo, 2, BW * P * 2 * HC)                                    \
     X(dxu, 4, BW * 2 * P * HC) X(dxc, 4, BW * P * HC) X(dgc, 4, BW * N * HC)                       \
-    X(kcoef, 4, BW * 2 * 3 * HC) X(se_ds, 4, BW * T * 2 * B * HC) X(se_dh, 4, BW * T * 2 * B * HSE) X(se_dq, 4, BW * 2 * B * HC) \
+    X(kcoef, 4, BW * 2 * 3 * HC) X(se_ds, 4, BW * T * 2 * B * HC) X(se_dh, 4, BW * T * 2 * B * HSE) X(se_dq, 4, BW * T * 2 * B * HC) \
     X(dbf1_part, 4, BW * T * 2 * B * HC) X(dbf2_part, 4, BW * T * 2 * B * HC)                      \
     X(gw_f1, 4, BW * 2 * HC * HC) X(gw_f2, 4, BW * 2 * HC * HC) X(gw_c1, 4, BW * 2 * HB * HC)      \
     X(gw_c2, 4, BW * 2 * HB * HB) X(gw_c3, 4, BW * 2 * HC * HB)                                    \
     X(gbn1, 4, BW * 2 * 2 * HB) X(gbn2, 4, BW * 2 * 2 * HB) X(gbn3, 4, BW * 2 * 2 * HC)            \
     X(dm, 4, BW * P) X(dy3, 4, BW * P) X(dy2_hi, 2, BW * P * HMID) X(dy2_lo, 2, BW * P * HMID)     \
-    X(g2, 4, BW * HMID * HG) X(dz1, 4, BW * P * HG) X(dy1_hi, 2, BW * P * HG) X(dy1_lo, 2, BW * P * HG) \
+    X(g2, 4, BW * 16 * HMID * HG) X(dz1, 4, BW * P * HG) X(dy1_hi, 2, BW * P * HG) X(dy1_lo, 2, BW * P * HG) \
     X(dbias1_part, 4, BW * N * HG) X(dbias1, 4, BW * B * HG) X(du, 4, BW * B * HG) X(dg, 4, BW * B * HC) \
-    X(gsmall, 4, BW * 4096)
+    X(gsmall, 4, BW * 8192)
 
 struct HeadWs {
     int B, T, N, P, R, save, SL, SLM, SLZ;

@@ -126,6 +126,10 @@ case("MN-major 128x256x128 bn256", plain(128, 256, 128, 256, 1, 1))
 case("MN-major 512x2048x4096 bn256", plain(512, 2048, 4096, 256, 1, 1))
 case("MN-major 2048x512x4096 bn128", plain(2048, 512, 4096, 128, 1, 1))
 case("MN-major batch2 256x256x256 bn128", plain(256, 256, 256, 128, 1, 1, batch=2))
+case("mixed (A K-major, B MN-major) 128x128x64 bn128", plain(128, 128, 64, 128, 0, 1))
+case("mixed 256x512x512 bn256", plain(256, 512, 512, 256, 0, 1))
+case("mixed 4096x512x2048 bn128", plain(4096, 512, 2048, 128, 0, 1))
+case("mixed batch2 512x2048x512 auto", plain(512, 2048, 512, 0, 0, 1, batch=2))
 
 
 def epilogue_case():
