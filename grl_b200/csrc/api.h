@@ -15,11 +15,16 @@ typedef CUresult (*grl_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+struct grl_prof_rec { cudaEvent_t e0, e1; double flops; };
+struct grl_prof;   // std::vector<grl_prof_rec>, owned by the handle (gemm.cu)
+
 struct grl_handle {
     int device;
     int num_sms;
     long long launches;
     grl_encode_tiled_fn encode;
+    int prof_on;
+    grl_prof* prof;
     char err[512];
 };
 

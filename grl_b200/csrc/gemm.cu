@@ -2,6 +2,10 @@
 // the fp32 -> bf16 hi/lo split kernels, handle lifecycle and the grl_gemm_bf16x3 C entry point.
 #include "api.h"
 
+#include <vector>
+
+struct grl_prof { std::vector<grl_prof_rec> recs; };
+
 namespace grl {
 
 int set_error(grl_handle* h, int code, const char* fmt, ...) {
@@ -110,8 +114,19 @@ static int launch_variant(grl_handle* h, cudaStream_t st, const GemmParams& p, i
         GRL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
         configured = true;
     }
+    grl_prof_rec rec;
+    if (h->prof_on) {    // bench.py roofline: bracket the launch with events on the caller's stream
+        GRL_CUDA(h, cudaEventCreate(&rec.e0));
+        GRL_CUDA(h, cudaEventCreate(&rec.e1));
+        rec.flops = 2.0 * p.M * (double)p.N * p.K * p.batch;
+        GRL_CUDA(h, cudaEventRecord(rec.e0, st));
+    }
     kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(p);
     GRL_LAUNCH_CHECK(h);
+    if (h->prof_on) {
+        GRL_CUDA(h, cudaEventRecord(rec.e1, st));
+        h->prof->recs.push_back(rec);
+    }
     return GRL_OK;
 }
 
@@ -178,11 +193,41 @@ extern "C" int grl_create(int device, grl_handle** out) {
         return set_error(nullptr, GRL_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
     }
     h->encode = reinterpret_cast<grl_encode_tiled_fn>(fn);
+    h->prof = new grl_prof();
     *out = h;
     return GRL_OK;
 }
 
-extern "C" void grl_destroy(grl_handle* h) { delete h; }
+extern "C" void grl_destroy(grl_handle* h) {
+    if (!h) return;
+    if (h->prof) {
+        for (auto& r : h->prof->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        delete h->prof;
+    }
+    delete h;
+}
+
+extern "C" int grl_profile_enable(grl_handle* h, int on) {
+    if (!h) return GRL_EINVAL;
+    h->prof_on = on ? 1 : 0;
+    return GRL_OK;
+}
+
+extern "C" int grl_profile_read(grl_handle* h, double* gemm_ms, double* gemm_flops, long long* gemm_launches) {
+    if (!h || !gemm_ms || !gemm_flops || !gemm_launches) return set_error(h, GRL_EINVAL, "grl_profile_read: NULL argument");
+    double ms = 0.0, fl = 0.0;
+    long long n = 0;
+    for (auto& r : h->prof->recs) {
+        GRL_CUDA(h, cudaEventSynchronize(r.e1));
+        float t = 0.f;
+        GRL_CUDA(h, cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms += t; fl += r.flops; ++n;
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    h->prof->recs.clear();
+    *gemm_ms = ms; *gemm_flops = fl; *gemm_launches = n;
+    return GRL_OK;
+}
 
 extern "C" const char* grl_last_error(const grl_handle* h) {
     if (h) return h->err;

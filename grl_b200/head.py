@@ -138,6 +138,25 @@ def ws_view(ws, B, T, save, name, dtype, shape):
     return ws[off.value:off.value + nbytes.value].view(dtype).view(*shape) if shape else ws[off.value:off.value + nbytes.value].view(dtype)
 
 
+def saved_state(ws, B, T):
+    """Debug/test: every intermediate a train-mode, save_for_backward forward left in the workspace, as fp32 tensors
+    in pixel-major layout (names follow DESIGN.md's forward plan; bf16 hi/lo planes are summed)."""
+    N, P, R = B * T, B * T * 128, B * 128
+    V = lambda name, shape, dt=torch.float32: ws_view(ws, B, T, True, name, dt, shape)
+    PL = lambda name, shape: V(name + "_hi", shape, torch.bfloat16).float() + V(name + "_lo", shape, torch.bfloat16).float()
+    st = lambda name, c: V(name, (4, c))            # rows: a | c | mean | rstd
+    out = dict(X=PL("xp", (P, 2048)), g=V("g", (B, 2048)), u=V("u", (B, 1024)), glo=V("glo", (B, 1024)),
+               glo_stat=st("glo_stat", 1024), Y1=PL("y1", (P, 1024)), bn1_stat=st("bn1_stat", 1024),
+               Y2=V("y2", (P, 256)), bn2_stat=st("bn2_stat", 256), y3=V("y3", (P,)), bn3_stat=V("bn3_stat", (8,)),
+               m=V("m", (P,)), Xc=PL("xc", (P, 2048)), Xu=PL("xu", (P, 2048)), Gc=V("gc", (N, 2048)),
+               F2=V("f2", (P, 4096)), mem=PL("mem", (T + 1, 2, R, 2048)), Z=PL("z", (T, 2, R, 2048)),
+               F1=V("f1", (T, 2, R, 2048)), q=V("se_q", (T, 2, B, 2048)), h=V("se_h", (T, 2, B, 128)),
+               a=V("se_a", (T, 2, B, 2048)), H1=V("h1", (T, 2, R, 512)), H1p=PL("h1p", (T, 2, R, 512)),
+               H2=V("h2", (T, 2, R, 512)), H2p=PL("h2p", (T, 2, R, 512)), H3=V("h3", (T, 2, R, 2048)),
+               sbn1=V("sbn1", (T, 2, 4, 512)), sbn2=V("sbn2", (T, 2, 4, 512)), sbn3=V("sbn3", (T, 2, 4, 2048)))
+    return out
+
+
 def _alloc_ws(nbytes, device):
     # cudaMalloc'd blocks from the caching allocator are 512-byte aligned; over-allocate to get 1024
     raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
@@ -196,10 +215,9 @@ class _HeadFunction(torch.autograd.Function):
     """autograd node for the fused head: (x, *params) -> (f_uncorr, f_corr, corr_map, x_uncorr, x_corr)."""
 
     @staticmethod
-    def forward(ctx, x, B, T, training, want_maps, names, sd_buffers, *params):
+    def forward(ctx, x, B, T, training, want_maps, need_grad, names, sd_buffers, *params):
         sd = dict(zip(names, params))
         sd.update(sd_buffers)
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for t in params))
         if need_grad and not training:
             raise RuntimeError("grl_b200 head: backward with eval-mode BatchNorm is not supported; call .train() "
                                "or wrap inference in torch.no_grad()")
@@ -227,7 +245,7 @@ class _HeadFunction(torch.autograd.Function):
             g_xu = g_xc = None
         dx, grads = head_backward_raw(sd, x.contiguous().float(), B, T, ctx.ws, g_fu, g_fc, g_xu, g_xc, g_map)
         ctx.ws = None
-        return (dx, None, None, None, None, None, None) + tuple(grads[k] for k in ctx.names)
+        return (dx, None, None, None, None, None, None, None) + tuple(grads[k] for k in ctx.names)
 
 
 def _collect(module_sd_items, prefix_map):
@@ -261,7 +279,10 @@ def run_head(backbone, trl, x, b, t, want_maps=False):
     params, buffers = _HeadState.tensors(backbone, trl)
     names = head_param_names()
     training = backbone.training
-    out = _HeadFunction.apply(x, b, t, training, want_maps, names, buffers, *[params[k] for k in names])
+    plist = [params[k] for k in names]
+    # grad mode is off inside Function.forward, so decide here whether activations must be kept for a backward
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or any(t_.requires_grad for t_ in plist))
+    out = _HeadFunction.apply(x, b, t, training, want_maps, need_grad, names, buffers, *plist)
     if training:    # num_batches_tracked bookkeeping (torch/nn/modules/batchnorm.py): +1 per BN call
         with torch.no_grad():
             for prefix in head_buffer_names():

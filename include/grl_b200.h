@@ -193,6 +193,13 @@ int grl_head_ws_lookup(int B, int T, int save_for_backward, const char* name, si
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches).   */
 long long grl_launch_count(const grl_handle* h);
 
+/* Profiling aid for bench.py's roofline: while enabled, every tcgen05 GEMM launch is bracketed by CUDA
+ * events on the caller's stream.  grl_profile_read waits for them and returns, since the last read, the
+ * summed device time of those launches (ms), their algorithmic FLOPs (2*M*N*K*batch; the split-bf16
+ * kernel issues 3x that in MMAs) and their count.  Off by default; not used on the product path.        */
+int grl_profile_enable(grl_handle* h, int on);
+int grl_profile_read(grl_handle* h, double* gemm_ms, double* gemm_flops, long long* gemm_launches);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

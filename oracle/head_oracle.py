@@ -372,6 +372,45 @@ def plan_trl_backward(p, ctx, d_f_uncorr, d_f_corr):
     return dXu, dXc, G
 
 
+def ctx_from_saved(sv, b, t):
+    """Build the (gce_ctx, trl_ctx) of plan_*_backward from a forward's SAVED state (dict of tensors named as in
+    plan_*_forward, e.g. what grl_b200.head.saved_state() reads out of the CUDA workspace), converted to float64.
+
+    This lets a test run the fp64 oracle backward on exactly the activation pattern (ReLU masks, BN statistics) the
+    CUDA forward produced: the backward kernels are then checked in isolation, free of the ReLU-kink sensitivity that
+    makes end-to-end gradients of this head differ by ~1e-3 even between the reference's own fp32 and fp64 runs."""
+    D = {k: v.detach().double().cpu() for k, v in sv.items()}
+    P = b * t * S
+    a2, c2 = D["bn2_stat"][0], D["bn2_stat"][1]
+    g = dict(X=D["X"], g=D["g"], u=D["u"], mug=D["glo_stat"][2], rstdg=D["glo_stat"][3], glo=D["glo"], Y1=D["Y1"],
+             a1=D["bn1_stat"][0], c1=D["bn1_stat"][1], mu1=D["bn1_stat"][2], rstd1=D["bn1_stat"][3], Y2=D["Y2"],
+             mu2=D["bn2_stat"][2], rstd2=D["bn2_stat"][3], Z2=torch.relu(a2 * D["Y2"] + c2), y3=D["y3"].view(P, 1),
+             mu3=D["bn3_stat"][2], rstd3=D["bn3_stat"][3], m=D["m"], b=b, t=t, training=True)
+    F2 = [D["F2"][:, :2048], D["F2"][:, 2048:]]
+    steps = [[], []]
+    for d in range(2):
+        for i in range(t):
+            tau = i if d == 0 else t - 1 - i
+            r = _rows(b, t, tau)
+            steps[d].append(dict(tau=tau, M=D["mem"][i, d], F1=D["F1"][i, d], E=D["F1"][i, d] - F2[d][r], q=D["q"][i, d],
+                                 h=D["h"][i, d], a=D["a"][i, d], Z=D["Z"][i, d], H1=D["H1"][i, d], mu1=D["sbn1"][i, d, 2],
+                                 rs1=D["sbn1"][i, d, 3], H1p=D["H1p"][i, d], H2=D["H2"][i, d], mu2=D["sbn2"][i, d, 2],
+                                 rs2=D["sbn2"][i, d, 3], H2p=D["H2p"][i, d], H3=D["H3"][i, d], mu3=D["sbn3"][i, d, 2],
+                                 rs3=D["sbn3"][i, d, 3], Mn=D["mem"][i + 1, d]))
+    tc = dict(b=b, t=t, training=True, Xu=D["Xu"], Xc=D["Xc"], steps=steps, Gc=D["Gc"].view(b, t, -1), F2=F2)
+    return g, tc
+
+
+def plan_backward_from_ctx(p, gctx, tctx, d_f_uncorr, d_f_corr):
+    """fp64 oracle backward on a given forward context.  Returns (dx NCHW, {name: grad})."""
+    n = gctx["b"] * gctx["t"]
+    with torch.no_grad():
+        dXu, dXc, G = plan_trl_backward(p, tctx, d_f_uncorr, d_f_corr)
+        dX, G2 = plan_gce_backward(p, gctx, dXu, dXc)
+    G.update(G2)
+    return from_pm(dX, n), G
+
+
 def plan_head(p, x, b, t, training=True, grads=None, update=True):
     """Fused head: forward, and backward when grads=(d_f_uncorr, d_f_corr) is given."""
     n = b * t

@@ -1,0 +1,209 @@
+"""GPU parity: GCE + TRL head (forward, backward, BN buffers, module API) through the C ABI vs the oracle.
+
+Truth = the fp64 oracle (oracle/head_oracle.py, pinned to the real reference by tests/golden).  Tolerances:
+  * forward outputs: 1e-3 relative (north-star); the kernels actually sit near 1e-5, asserted at 1e-4;
+  * BN running buffers: 1e-5;
+  * backward, conditioned on the CUDA forward's own saved activations: 1e-3 (actual ~1e-5).  This is the sharp
+    test of the backward kernels;
+  * backward end to end: the head's gradient is a discontinuous function of its inputs (ReLU masks, tiny-batch BN),
+    so even the reference's own fp32 run differs from its fp64 run by 1e-3..6e-3.  Gate per tensor:
+    err(ours, fp64) <= max(1e-3, E2E_FLOOR_MULT * err(reference fp32, fp64)).
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from grl_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+E2E_FLOOR_MULT = 10.0     # see module docstring; tightened as the forward precision is raised
+# parameters whose gradient is analytically zero: a per-channel constant added in front of a train-mode BatchNorm
+# (glo_fc.0.bias -> glo_fc.1;  corr_atte.1.bias -> conv -> corr_atte.3).  Compared against the scale of their layer.
+ZERO_GRADS = {"backbone.glo_fc.0.bias": "backbone.glo_fc.1.bias", "backbone.corr_atte.1.bias": "backbone.corr_atte.1.weight"}
+
+
+def _mods():
+    from grl_b200 import _lib, head
+    from oracle import head_oracle as ho
+    return _lib, head, ho
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu().reshape(-1)
+    b = torch.as_tensor(b).detach().double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+def device_params(seed=0):
+    return {k: v.cuda().contiguous() for k, v in synth.make_head_params(seed).items()}
+
+
+@pytest.mark.parametrize("name", ["head_train_b2t3", "head_train_b4t2", "head_eval_b3t4"])
+def test_forward_matches_oracle_and_reference_golden(golden_dir, name):
+    _, head, ho = _mods()
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    B, T, training = int(g["B"]), int(g["T"]), bool(g["training"])
+    sd = device_params()
+    x = synth.make_head_input(B, T).cuda()
+    f_uncorr, f_corr, corr_map, xu, xc, _ = head.head_forward_raw(sd, x, B, T, training, save=training, want_maps=True)
+    # against outputs of the REAL reference modules (fp64), committed as fixtures
+    for k, v in (("f_uncorr", f_uncorr), ("f_corr", f_corr), ("corr_map", corr_map)):
+        assert rel(v, g[k]) < 1e-4, (k, rel(v, g[k]))
+    # against the oracle plan, including the stand-alone gated maps and the BN buffers
+    p64 = synth.make_head_params(0, dtype=torch.float64)
+    o = ho.plan_head(p64, synth.make_head_input(B, T, dtype=torch.float64), B, T, training)
+    assert rel(xu, o["x_uncorr"]) < 1e-4 and rel(xc, o["x_corr"]) < 1e-4
+    assert corr_map.shape == (B * T, 1, 16, 8) and f_corr.shape == (B, T, 2048) and f_uncorr.shape == (B, 2048)
+    for k in p64:
+        if "running" in k:
+            assert rel(sd[k], p64[k]) < 1e-5, k
+    if training:      # running buffers as left behind by the REAL reference (fixture), entry by entry
+        off = 0
+        for k in g["buf_names"]:
+            k = str(k)
+            n = max(1, int(sd[k].numel()))
+            ref = g["buf_values"][off:off + n]
+            off += n
+            if "num_batches" in k:
+                continue                      # advanced by the nn.Module wrapper (test_module_api_*)
+            assert rel(sd[k], ref) < 2e-5, (k, rel(sd[k], ref))
+
+
+@pytest.mark.parametrize("B,T", [(2, 3), (4, 2), (6, 4)])
+def test_backward_matches_oracle_on_saved_activations(B, T):
+    """Backward kernels in isolation: fp64 oracle backward evaluated on the CUDA forward's saved state."""
+    _, head, ho = _mods()
+    sd = device_params()
+    x = synth.make_head_input(B, T).cuda()
+    gu, gc = synth.make_head_grads(B, T)
+    *_, ws = head.head_forward_raw(sd, x, B, T, True, save=True)
+    sv = head.saved_state(ws, B, T)
+    gctx, tctx = ho.ctx_from_saved(sv, B, T)
+    p64 = synth.make_head_params(0, dtype=torch.float64)
+    dx_ref, G = ho.plan_backward_from_ctx(p64, gctx, tctx, gu.double(), gc.double())
+    dx, grads = head.head_backward_raw(sd, x, B, T, ws, gu.cuda(), gc.cuda())
+    assert rel(dx, dx_ref) < 1e-3, rel(dx, dx_ref)
+    worst = {}
+    for k in head.head_param_names():
+        ref = G[k].reshape(grads[k].shape)
+        if k in ZERO_GRADS:
+            assert float(grads[k].double().norm()) < 1e-3 * float(G[ZERO_GRADS[k]].norm()), k
+            continue
+        if B == 2 and k.startswith("backbone.glo_fc"):
+            continue      # BatchNorm1d over 2 samples: d(u) is identically ~0 (pure cancellation); covered at B >= 4
+        worst[k] = rel(grads[k], ref)
+    bad = {k: v for k, v in worst.items() if v >= 1e-3}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("B,T", [(2, 3), (4, 2)])
+def test_backward_end_to_end_vs_fp64_oracle(B, T):
+    _, head, ho = _mods()
+    sd = device_params()
+    x = synth.make_head_input(B, T).cuda()
+    gu, gc = synth.make_head_grads(B, T)
+    *_, ws = head.head_forward_raw(sd, x, B, T, True, save=True)
+    dx, grads = head.head_backward_raw(sd, x, B, T, ws, gu.cuda(), gc.cuda())
+
+    def ref_run(dtype):
+        p = {k: (v.to(dtype).requires_grad_("running" not in k) if v.is_floating_point() else v.clone())
+             for k, v in synth.make_head_params(0).items()}
+        xx = synth.make_head_input(B, T).to(dtype).requires_grad_(True)
+        out = ho.ref_forward(p, xx, B, T, True)
+        ((out["f_uncorr"] * gu.to(dtype)).sum() + (out["f_corr"] * gc.to(dtype)).sum()).backward()
+        return xx.grad, {k: v.grad for k, v in p.items() if v.requires_grad}
+
+    dx64, g64 = ref_run(torch.float64)
+    dx32, g32 = ref_run(torch.float32)
+    report = {}
+
+    def gate(name, ours, r64, r32):
+        if name in ZERO_GRADS:
+            return
+        floor = rel(r32, r64)
+        err = rel(ours, r64)
+        report[name] = (err, floor)
+        assert err <= max(1e-3, E2E_FLOOR_MULT * floor), (name, err, floor)
+
+    gate("dx", dx, dx64, dx32)
+    for k in head.head_param_names():
+        if B == 2 and k.startswith("backbone.glo_fc"):
+            continue
+        gate(k, grads[k], g64[k].reshape(grads[k].shape), g32[k].reshape(grads[k].shape))
+    print("end-to-end gradient error (ours vs fp64 | reference fp32 vs fp64):")
+    for k, (e, f) in report.items():
+        print("  %-72s %.2e | %.2e" % (k, e, f))
+
+
+def test_module_api_autograd_and_state_dict(golden_dir):
+    """Drop-in surface: same state_dict keys as the reference, autograd through model.head, BN bookkeeping."""
+    _, head, ho = _mods()
+    g = np.load(os.path.join(golden_dir, "head_train_b2t3.npz"))
+    B, T = 2, 3
+    model = head.ResNet50_GRL_Model(base=torch.nn.Identity()).cuda()
+    keys = set(model.state_dict().keys())
+    for k in list(g["buf_names"]) + list(g["grad_names"]):
+        assert str(k) in keys, k                       # names recorded from the real reference model
+    assert "corr_bn.weight" in keys and "uncorr_bn.running_var" in keys
+    sd = model.state_dict()
+    for k, v in synth.make_head_params(0).items():
+        sd[k] = v
+    model.load_state_dict(sd)
+    model.train()
+    x = synth.make_head_input(B, T).cuda().requires_grad_(True)
+    f_uncorr, f_corr, corr_map, _, _ = model.head(x, B, T)
+    assert f_uncorr.requires_grad and f_corr.requires_grad
+    for k, v in (("f_uncorr", f_uncorr), ("f_corr", f_corr), ("corr_map", corr_map)):
+        assert rel(v, g[k]) < 1e-4, k
+    gu, gc = synth.make_head_grads(B, T)
+    torch.autograd.backward([f_uncorr, f_corr], [gu.cuda(), gc.cuda()])
+    assert x.grad is not None and abs(float(x.grad.double().norm()) / float(g["dx_norm"]) - 1) < 2e-2
+    named = dict(model.named_parameters())
+    for k in head.head_param_names():
+        assert named[k].grad is not None and torch.isfinite(named[k].grad).all(), k
+    msd = model.state_dict()
+    assert int(msd["backbone.corr_atte.1.num_batches_tracked"]) == 1
+    assert int(msd["temporal_learning_block.uncorr_memo_forward.bn2.num_batches_tracked"]) == T   # one BN call per step
+    # eval(): running statistics, no autograd state kept, clips independent
+    model.eval()
+    with torch.no_grad():
+        a = model.head(x.detach(), B, T)[1]
+        b = model.head(x.detach()[T:], 1, T)[1]
+    assert rel(b, a[1:]) < 1e-5
+    with pytest.raises(RuntimeError):
+        model.head(x, B, T)                            # eval-mode backward is not a reference use case: refuse loudly
+
+
+def test_full_size_properties_b32_t8():
+    """BASELINE config 2 (B=32, T=8): size-independent properties instead of a CPU oracle run."""
+    _, head, ho = _mods()
+    B, T = 32, 8
+    sd = device_params()
+    x = synth.make_head_input(B, T).cuda()
+    gu, gc = synth.make_head_grads(B, T)
+    fu, fc, cm, _, _, ws = head.head_forward_raw(sd, x, B, T, True, save=True)
+    assert torch.isfinite(fu).all() and torch.isfinite(fc).all() and (cm > 0).all() and (cm < 1).all()
+    dx1, g1 = head.head_backward_raw(sd, x, B, T, ws, gu.cuda(), gc.cuda())
+    dx2, g2 = head.head_backward_raw(sd, x, B, T, ws, (2 * gu).cuda(), (2 * gc).cuda())
+    assert torch.isfinite(dx1).all()
+    assert rel(dx2, 2 * dx1) < 1e-4                    # backward is linear in the upstream gradient
+    for k in ("temporal_learning_block.forward_f1.0.weight", "backbone.corr_atte.0.weight",
+              "temporal_learning_block.uncorr_memo_backward.conv2.weight"):
+        assert rel(g2[k], 2 * g1[k]) < 1e-4, k
+    # the backward conditioned on its own saved activations, spot-checked on the TRL side at full size:
+    # d f2 bias = column sums of dF2 (a checksum of the whole attention path)
+    sv = head.saved_state(ws, B, T)
+    a_sum = sv["a"][:, 0].permute(1, 0, 2) + sv["a"][:, 1].flip(0).permute(1, 0, 2)      # [B,T,C]: fwd step t, bwd step T-1-t
+    dgc_ref = 2 * gc.cuda() * (2 + a_sum)                # the workspace holds the last backward (upstream grads x2)
+    from grl_b200.head import ws_view
+    dgc = ws_view(ws, B, T, True, "dgc", torch.float32, (B, T, 2048))
+    assert rel(dgc, dgc_ref) < 1e-5
+    # eval mode: chunk invariance (attevaluator.py:72-77 feeds 8 clips at a time)
+    with torch.no_grad():
+        full = head.head_forward_raw(sd, x, B, T, False, save=False)[1]
+        part = head.head_forward_raw(sd, x[8 * T:16 * T], 8, T, False, save=False)[1]
+    assert rel(part, full[8:16]) < 1e-5
