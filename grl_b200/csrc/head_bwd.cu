@@ -55,25 +55,6 @@ __global__ void __launch_bounds__(256) small_outer_kernel(const float* __restric
     for (int jj = 0; jj < 8; ++jj) out[(long long)(j0 + ty * 8 + jj) * ldo + k0 + tx] = acc[jj] * scale;
 }
 
-// out[b*ldo + k] = sum_j in[b*ldi + j] * W[j*ldw + k]      (row vectors times a matrix, rows <= a few dozen)
-__global__ void small_linear_t_kernel(const float* __restrict__ in, long long ldi, const float* __restrict__ W, long long ldw,
-                                      float* __restrict__ out, long long ldo, int rows, int J, int K) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= K) return;
-    for (int b0 = 0; b0 < rows; b0 += 8) {
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int j = 0; j < J; ++j) {
-            const float w = __ldg(W + (long long)j * ldw + k);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (b0 + i < rows) acc[i] += w * __ldg(in + (long long)(b0 + i) * ldi + j);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (b0 + i < rows) out[(long long)(b0 + i) * ldo + k] = acc[i];
-    }
-}
-
 // out[y*out_stride + c] = sum_{o<no, n<ni} src[y*grp_stride + o*os + n*is + c]
 __global__ void small_colsum_kernel(const float* __restrict__ src, long long grp_stride, long long os, long long is, int no, int ni,
                                     float* __restrict__ out, long long out_stride, int Cn) {
@@ -233,17 +214,24 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
     tile_colsum(ax, red, pxh + pidx, t);
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ pxh, int nparts, int Cn, double count,
-                                       BnPtrs2 bp, const float* __restrict__ stat, float* __restrict__ kcoef, OutPtrs2 dgamma,
-                                       OutPtrs2 dbeta, int accumulate) {
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ pxh, int nparts, int Cn,
+                                                              double count, BnPtrs2 bp, const float* __restrict__ stat,
+                                                              float* __restrict__ kcoef, OutPtrs2 dgamma, OutPtrs2 dbeta, int accumulate) {
+    __shared__ double sh[2][8][33];
     const int z = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= Cn) return;
+    const int c = blockIdx.x * 32 + threadIdx.x;          // block (32, 8): 8 lanes share the partials of a channel
     double s = 0.0, x = 0.0;
-    for (int i = 0; i < nparts; ++i) {
-        s += psum[((size_t)z * nparts + i) * Cn + c];
-        x += pxh[((size_t)z * nparts + i) * Cn + c];
-    }
+    if (c < Cn)
+        for (int i = threadIdx.y; i < nparts; i += 8) {
+            s += psum[((size_t)z * nparts + i) * Cn + c];
+            x += pxh[((size_t)z * nparts + i) * Cn + c];
+        }
+    sh[0][threadIdx.y][threadIdx.x] = s; sh[1][threadIdx.y][threadIdx.x] = x;
+    __syncthreads();
+    if (threadIdx.y != 0 || c >= Cn) return;
+    s = 0.0; x = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s += sh[0][i][threadIdx.x]; x += sh[1][i][threadIdx.x]; }
     const float rstd = stat[(size_t)z * 4 * Cn + 3 * Cn + c];
     float* kc = kcoef + (size_t)z * 3 * Cn;
     kc[c] = bp.gamma[z][c] * rstd;
@@ -457,13 +445,22 @@ __global__ void __launch_bounds__(256) gce_bwd_y2_reduce_kernel(const float* __r
     }
 }
 
-// one block of HMID threads: finalize d w3, BN(256) grads and the apply coefficients
-__global__ void gce_bwd_y2_finalize_kernel(const float* __restrict__ pw3, const float* __restrict__ psum, const float* __restrict__ pxh, int nparts,
-                                           double count, const float* __restrict__ gamma, const float* __restrict__ stat2,
-                                           float* __restrict__ kcoef, float* __restrict__ dw3, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int c = threadIdx.x;
+// finalize d w3, BN(256) grads and the apply coefficients.   grid (HMID/32), block (32, 8)
+__global__ void __launch_bounds__(256) gce_bwd_y2_finalize_kernel(const float* __restrict__ pw3, const float* __restrict__ psum,
+                                                                  const float* __restrict__ pxh, int nparts, double count,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ stat2,
+                                                                  float* __restrict__ kcoef, float* __restrict__ dw3,
+                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ double sh[3][8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
     double w = 0.0, s = 0.0, x = 0.0;
-    for (int i = 0; i < nparts; ++i) { w += pw3[(size_t)i * HMID + c]; s += psum[(size_t)i * HMID + c]; x += pxh[(size_t)i * HMID + c]; }
+    for (int i = threadIdx.y; i < nparts; i += 8) { w += pw3[(size_t)i * HMID + c]; s += psum[(size_t)i * HMID + c]; x += pxh[(size_t)i * HMID + c]; }
+    sh[0][threadIdx.y][threadIdx.x] = w; sh[1][threadIdx.y][threadIdx.x] = s; sh[2][threadIdx.y][threadIdx.x] = x;
+    __syncthreads();
+    if (threadIdx.y != 0) return;
+    w = s = x = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { w += sh[0][i][threadIdx.x]; s += sh[1][i][threadIdx.x]; x += sh[2][i][threadIdx.x]; }
     dw3[c] = (float)w; dgamma[c] = (float)x; dbeta[c] = (float)s;
     kcoef[c] = gamma[c] * stat2[3 * HMID + c];
     kcoef[HMID + c] = (float)(s / count);
@@ -527,13 +524,20 @@ __global__ void __launch_bounds__(256) gce_bwd_bn1_reduce_kernel(const float* __
     tile_colsum(ax, red, pxh + (size_t)n * HG + c0, t);
 }
 
-__global__ void gce_bwd_bn1_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ pxh, int nparts, double count,
-                                            const float* __restrict__ gamma, const float* __restrict__ stat1, float* __restrict__ kcoef,
-                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= HG) return;
+__global__ void __launch_bounds__(256) gce_bwd_bn1_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ pxh, int nparts,
+                                                                   double count, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ stat1, float* __restrict__ kcoef,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ double sh[2][8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;          // grid (HG/32), block (32, 8)
     double s = 0.0, x = 0.0;
-    for (int i = 0; i < nparts; ++i) { s += psum[(size_t)i * HG + c]; x += pxh[(size_t)i * HG + c]; }
+    for (int i = threadIdx.y; i < nparts; i += 8) { s += psum[(size_t)i * HG + c]; x += pxh[(size_t)i * HG + c]; }
+    sh[0][threadIdx.y][threadIdx.x] = s; sh[1][threadIdx.y][threadIdx.x] = x;
+    __syncthreads();
+    if (threadIdx.y != 0) return;
+    s = x = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s += sh[0][i][threadIdx.x]; x += sh[1][i][threadIdx.x]; }
     dgamma[c] = (float)x; dbeta[c] = (float)s;
     kcoef[c] = gamma[c] * stat1[3 * HG + c];
     kcoef[HG + c] = (float)(s / count);
@@ -630,7 +634,7 @@ static int bn_backward(grl_handle* h, cudaStream_t st, const HeadWs& w, const fl
     GRL_LAUNCH_CHECK(h);
     BnPtrs2 bp; bp.gamma[0] = gamma0; bp.gamma[1] = gamma1;
     OutPtrs2 dg, db; dg.p[0] = dgamma0; dg.p[1] = dgamma1; db.p[0] = dbeta0; db.p[1] = dbeta1;
-    bn_bwd_finalize_kernel<<<dim3((Cn + 127) / 128, 2), 128, 0, st>>>(WS_F32(w, part_a), WS_F32(w, part_b), B, Cn, (double)R, bp, stat,
+    bn_bwd_finalize_kernel<<<dim3((Cn + 31) / 32, 2), dim3(32, 8), 0, st>>>(WS_F32(w, part_a), WS_F32(w, part_b), B, Cn, (double)R, bp, stat,
                                                                       WS_F32(w, kcoef), dg, db, accumulate);
     GRL_LAUNCH_CHECK(h);
     bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(srcA, srcB, mask_hi, hraw, stat, WS_F32(w, kcoef), Cn, R, out_hi, out_lo, g_out);
@@ -821,7 +825,7 @@ extern "C" int grl_head_backward(grl_handle* h, const grl_head_params* p, const 
     gce_bwd_y2_reduce_kernel<<<yblocks, 256, 0, st>>>(WS_F32(w, y2), WS_F32(w, bn2_stat), p->atte5_w, WS_F32(w, dy3), P, WS_F32(w, part_a),
                                                       WS_F32(w, part_b), WS_F32(w, part_c));
     GRL_LAUNCH_CHECK(h);
-    gce_bwd_y2_finalize_kernel<<<1, HMID, 0, st>>>(WS_F32(w, part_a), WS_F32(w, part_b), WS_F32(w, part_c), yblocks, (double)P, p->atte_bn3.weight,
+    gce_bwd_y2_finalize_kernel<<<HMID / 32, dim3(32, 8), 0, st>>>(WS_F32(w, part_a), WS_F32(w, part_b), WS_F32(w, part_c), yblocks, (double)P, p->atte_bn3.weight,
                                                    WS_F32(w, bn2_stat), k2coef, g->atte5_w, g->atte_bn3_w, g->atte_bn3_b);
     GRL_LAUNCH_CHECK(h);
     gce_bwd_y2_apply_kernel<<<yblocks, 256, 0, st>>>(WS_F32(w, y2), WS_F32(w, bn2_stat), p->atte5_w, WS_F32(w, dy3), k2coef, P, WS_BF(w, dy2_hi),
@@ -847,7 +851,7 @@ extern "C" int grl_head_backward(grl_handle* h, const grl_head_params* p, const 
     gce_bwd_bn1_reduce_kernel<<<dim3(HG / 64, N), 256, 0, st>>>(WS_F32(w, dz1), WS_BF(w, y1_hi), WS_BF(w, y1_lo), WS_F32(w, bn1_stat),
                                                                 WS_F32(w, part_a), WS_F32(w, part_b));
     GRL_LAUNCH_CHECK(h);
-    gce_bwd_bn1_finalize_kernel<<<(HG + 127) / 128, 128, 0, st>>>(WS_F32(w, part_a), WS_F32(w, part_b), N, (double)P, p->atte_bn1.weight,
+    gce_bwd_bn1_finalize_kernel<<<HG / 32, dim3(32, 8), 0, st>>>(WS_F32(w, part_a), WS_F32(w, part_b), N, (double)P, p->atte_bn1.weight,
                                                                   WS_F32(w, bn1_stat), k1coef, g->atte_bn1_w, g->atte_bn1_b);
     GRL_LAUNCH_CHECK(h);
     gce_bwd_bn1_apply_kernel<<<dim3(HG / 64, N), 256, 0, st>>>(WS_F32(w, dz1), WS_BF(w, y1_hi), WS_BF(w, y1_lo), WS_F32(w, bn1_stat), k1coef,
@@ -870,14 +874,12 @@ extern "C" int grl_head_backward(grl_handle* h, const grl_head_params* p, const 
     GRL_LAUNCH_CHECK(h);
     GRL_TRY(outer(h, st, WS_F32(w, dbias1), 0, HG, WS_F32(w, glo), 0, HG, 1, B, g->atte0_w + HC, HC + HG, HG, HG));      // d W1[:, 2048:]
     float* dglo = WS_F32(w, part_c);      // [B][HG] scratch (the partial buffers are idle here)
-    small_linear_t_kernel<<<(HG + 127) / 128, 128, 0, st>>>(WS_F32(w, dbias1), HG, p->atte0_w + HC, HC + HG, dglo, HG, B, HG, HG);
-    GRL_LAUNCH_CHECK(h);
+    GRL_TRY(small_matmul(h, st, WS_F32(w, dbias1), HG, p->atte0_w + HC, HC + HG, 1, nullptr, dglo, HG, B, HG, HG));
     gce_bwd_glo_bn_kernel<<<(HG + 127) / 128, 128, 0, st>>>(dglo, WS_F32(w, glo), WS_F32(w, u), WS_F32(w, glo_stat), p->glo_bn.weight, B,
                                                             WS_F32(w, du), g->glo_bn_w, g->glo_bn_b, g->glo_fc_b);
     GRL_LAUNCH_CHECK(h);
     GRL_TRY(outer(h, st, WS_F32(w, du), 0, HG, WS_F32(w, g), 0, HC, 1, B, g->glo_fc_w, HC, HG, HC));
-    small_linear_t_kernel<<<(HC + 127) / 128, 128, 0, st>>>(WS_F32(w, du), HG, p->glo_fc_w, HC, WS_F32(w, dg), HC, B, HG, HC);
-    GRL_LAUNCH_CHECK(h);
+    GRL_TRY(small_matmul(h, st, WS_F32(w, du), HG, p->glo_fc_w, HC, 1, nullptr, WS_F32(w, dg), HC, B, HG, HC));
     pm_to_nchw_bias_kernel<<<dim3(HC / 64, N), 256, 0, st>>>(WS_F32(w, dxc), WS_F32(w, dg), T, 1.f / (float)(T * HS), dx);
     GRL_LAUNCH_CHECK(h);
     return GRL_OK;

@@ -41,8 +41,8 @@ constexpr float BN_MOM = 0.1f;
     /* --- TRL per-step state (SL = T slots when saving for backward, else 1/2) --- */            \
     X(mem_hi, 2, (size_t)SLM * 2 * R * HC) X(mem_lo, 2, (size_t)SLM * 2 * R * HC)                 \
     X(z_hi, 2, (size_t)SLZ * 2 * R * HC) X(z_lo, 2, (size_t)SLZ * 2 * R * HC)                     \
-    X(f1, 4, (size_t)SL * 2 * R * HC) X(qpart, 4, (size_t)SL * 2 * 4 * B * HC)                    \
-    X(se_q, 4, (size_t)SL * 2 * B * HC) X(se_a, 4, (size_t)SL * 2 * B * HC) X(se_h, 4, (size_t)SL * 2 * B * HSE) \
+    X(f1, 4, (size_t)SL * 2 * R * HC) X(qpart, 4, (size_t)T * 2 * 4 * B * HC)                     \
+    X(se_q, 4, (size_t)T * 2 * B * HC) X(se_a, 4, (size_t)T * 2 * B * HC) X(se_h, 4, (size_t)T * 2 * B * HSE) \
     X(h1, 4, (size_t)SL * 2 * R * HB) X(h1p_hi, 2, (size_t)SL * 2 * R * HB) X(h1p_lo, 2, (size_t)SL * 2 * R * HB) \
     X(h2, 4, (size_t)SL * 2 * R * HB) X(h2p_hi, 2, (size_t)SL * 2 * R * HB) X(h2p_lo, 2, (size_t)SL * 2 * R * HB) \
     X(h3, 4, (size_t)SL * 2 * R * HC)                                                             \
@@ -100,6 +100,10 @@ inline HeadWs head_ws_layout(int B, int T, int save) {
 
 #define WS_F32(w, name) ((w).ptr<float>((w).off_##name))
 #define WS_BF(w, name) ((w).ptr<__nv_bfloat16>((w).off_##name))
+
+// host launcher of the small row-vector x matrix kernel (head_fwd.cu), shared with the backward
+int small_matmul(grl_handle* h, cudaStream_t st, const float* in, long long ldi, const float* W, long long w_js, long long w_ks,
+                 const float* bias, float* out, long long ldo, int rows, int J, int K);
 
 // ------------------------------------------------------------------ device helpers
 // Standard elementwise tile: 256 threads cover 128 rows x 64 channels; thread -> channel group

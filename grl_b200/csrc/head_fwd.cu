@@ -73,27 +73,53 @@ __global__ void glo_mean_kernel(const float* __restrict__ gx, float* __restrict_
     g[i] = s / (float)(T * HS);
 }
 
-// out[b][j] = bias[j] + sum_k in[b][k] * W[j*ldw + k]   (rows <= a few dozen; one warp per output column)
-__global__ void small_linear_kernel(const float* __restrict__ in, const float* __restrict__ W, long long ldw,
-                                    const float* __restrict__ bias, float* __restrict__ out, int rows, int K, int J) {
-    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (j >= J) return;
-    const int lane = lane_id();
-    const float* wrow = W + (size_t)j * ldw;
-    for (int b0 = 0; b0 < rows; b0 += 8) {
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int k = lane; k < K; k += 32) {
-            const float w = __ldg(wrow + k);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (b0 + i < rows) acc[i] += w * __ldg(in + (size_t)(b0 + i) * K + k);
+// out[r*ldo + k] = bias[k] + sum_j in[r*ldi + j] * W[j*w_js + k*w_ks]     (a few dozen rows; J % 16 == 0, K % 64 == 0)
+// nn.Linear forward: w_js = 1, w_ks = ldw;  its input gradient (row vectors times W): w_js = ldw, w_ks = 1.
+// grid (K/64, ceil(rows/32)), 256 threads: 32 rows x 64 columns per block, J staged through shared memory in slices of 16.
+__global__ void __launch_bounds__(256) small_matmul_kernel(const float* __restrict__ in, long long ldi, const float* __restrict__ W,
+                                                           long long w_js, long long w_ks, const float* __restrict__ bias,
+                                                           float* __restrict__ out, long long ldo, int rows, int J, int K) {
+    __shared__ float sA[16][33];
+    __shared__ float sB[16][65];
+    const int k0 = blockIdx.x * 64, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j0 = 0; j0 < J; j0 += 16) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 512; e += 256) {
+            const int r = e >> 4, j = e & 15;
+            sA[j][r] = (r0 + r < rows) ? __ldg(in + (long long)(r0 + r) * ldi + j0 + j) : 0.f;
         }
+        if (w_ks == 1) {
+            for (int e = threadIdx.x; e < 1024; e += 256) {
+                const int j = e >> 6, k = e & 63;
+                sB[j][k] = __ldg(W + (long long)(j0 + j) * w_js + k0 + k);
+            }
+        } else {
+            for (int e = threadIdx.x; e < 1024; e += 256) {
+                const int k = e >> 4, j = e & 15;
+                sB[j][k] = __ldg(W + (long long)(j0 + j) * w_js + (long long)(k0 + k) * w_ks);
+            }
+        }
+        __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float s = warp_sum(acc[i]);
-            if (lane == 0 && b0 + i < rows) out[(size_t)(b0 + i) * J + j] = s + (bias ? bias[j] : 0.f);
+        for (int j = 0; j < 16; ++j) {
+            const float b = sB[j][tx];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += sA[j][ty * 8 + i] * b;
         }
     }
+    const float bv = bias ? bias[k0 + tx] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (r0 + ty * 8 + i < rows) out[(long long)(r0 + ty * 8 + i) * ldo + k0 + tx] = acc[i] + bv;
+}
+
+int small_matmul(grl_handle* h, cudaStream_t st, const float* in, long long ldi, const float* W, long long w_js, long long w_ks,
+                 const float* bias, float* out, long long ldo, int rows, int J, int K) {
+    small_matmul_kernel<<<dim3(K / 64, (rows + 31) / 32), 256, 0, st>>>(in, ldi, W, w_js, w_ks, bias, out, ldo, rows, J, K);
+    GRL_LAUNCH_CHECK(h);
+    return GRL_OK;
 }
 
 // BatchNorm1d over `rows` samples + ReLU; stat = [a | c | mean | rstd] per channel
@@ -124,18 +150,30 @@ __global__ void bn1d_relu_kernel(const float* __restrict__ u, float* __restrict_
 // ------------------------------------------------------------------ BN finalisation from GEMM-epilogue partials
 struct BnPtrs { const float* gamma[2]; const float* beta[2]; float* rmean[2]; float* rvar[2]; };
 
-// stat layout per z: [a | c | mean | rstd] x Cn
-__global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int nparts, long long part_bstride,
-                                   int Cn, double count, BnPtrs bp, float* __restrict__ stat, int train) {
+// stat layout per z: [a | c | mean | rstd] x Cn.   grid (Cn/32, nz), block (32, 8): 8 lanes share the partials of a channel
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int nparts,
+                                                          long long part_bstride, int Cn, double count, BnPtrs bp,
+                                                          float* __restrict__ stat, int train) {
+    __shared__ double sh[2][8][33];
     const int z = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= Cn) return;
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const bool ok = c < Cn;
+    if (train) {
+        double s = 0.0, sq = 0.0;
+        if (ok) {
+            const float* ps = psum + z * part_bstride + c;
+            const float* pq = psq + z * part_bstride + c;
+            for (int i = threadIdx.y; i < nparts; i += 8) { s += ps[(size_t)i * Cn]; sq += pq[(size_t)i * Cn]; }
+        }
+        sh[0][threadIdx.y][threadIdx.x] = s; sh[1][threadIdx.y][threadIdx.x] = sq;
+        __syncthreads();
+    }
+    if (threadIdx.y != 0 || !ok) return;
     double mean, var;
     if (train) {
         double s = 0.0, sq = 0.0;
-        const float* ps = psum + z * part_bstride + c;
-        const float* pq = psq + z * part_bstride + c;
-        for (int i = 0; i < nparts; ++i) { s += ps[(size_t)i * Cn]; sq += pq[(size_t)i * Cn]; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s += sh[0][i][threadIdx.x]; sq += sh[1][i][threadIdx.x]; }
         mean = s / count;
         var = sq / count - mean * mean;
         if (var < 0) var = 0;
@@ -329,47 +367,53 @@ __global__ void __launch_bounds__(256) trl_init_kernel(const __nv_bfloat16* __re
 }
 
 // ------------------------------------------------------------------ K11-13: squeeze-excite on the pooled squared difference
-// grid (B, 2).  q = sum of the 4 per-warp partials / S;  h = relu(L1 q);  a = sigmoid(L2 h);
-// out_d[d][b*T + tau_d][c] = (1 + a[c]) * gc[b*T + tau_d][c]      (F4)
+// Nothing in the recurrence depends on it (it only feeds f_corr), so it runs once after the T steps for every
+// (clip, direction, step): grid (B, 2, T), 512 threads.
+//   q = sum of the 4 per-warp partials / S;  h = relu(L1 q);  a = sigmoid(L2 h);
+//   out_d[d][b*T + tau][c] = (1 + a[c]) * gc[b*T + tau][c]      (F4)
 struct SePtrs { const float* l1[2]; const float* l2[2]; };
-__global__ void __launch_bounds__(256) se_fwd_kernel(const float* __restrict__ qpart, SePtrs sp, const float* __restrict__ gc, int B, int T,
-                                                     int tau0, int tau1, float* __restrict__ se_q, float* __restrict__ se_h,
-                                                     float* __restrict__ se_a, float* __restrict__ out_d) {
-    __shared__ float q[HC];
-    __shared__ float h[HSE];
-    const int b = blockIdx.x, d = blockIdx.y;
-    const int tau = d ? tau1 : tau0;
-    const float* qp = qpart + ((size_t)d * 4 * B + (size_t)b * 4) * HC;
-    for (int c = threadIdx.x; c < HC; c += 256) {
+constexpr int SE_THREADS = 512;
+__global__ void __launch_bounds__(SE_THREADS) se_fwd_kernel(const float* __restrict__ qpart, SePtrs sp, const float* __restrict__ gc, int B, int T,
+                                                            float* __restrict__ se_q, float* __restrict__ se_h, float* __restrict__ se_a,
+                                                            float* __restrict__ out_d) {
+    __shared__ __align__(16) float q[HC];
+    __shared__ __align__(16) float h[HSE];
+    const int b = blockIdx.x, d = blockIdx.y, i = blockIdx.z;
+    const int tau = d ? T - 1 - i : i;
+    const size_t slot = ((size_t)i * 2 + d) * B + b;
+    const float* qp = qpart + slot * 4 * HC;
+    for (int c = threadIdx.x; c < HC; c += SE_THREADS) {
         const float v = (qp[c] + qp[HC + c] + qp[2 * HC + c] + qp[3 * HC + c]) * (1.f / HS);
         q[c] = v;
-        se_q[((size_t)d * B + b) * HC + c] = v;
+        se_q[slot * HC + c] = v;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int j = warp; j < HSE; j += 8) {
+    constexpr int NW = SE_THREADS / 32;
+    for (int j = warp; j < HSE; j += NW) {
         const float* w = sp.l1[d] + (size_t)j * HC;
         float acc = 0.f;
+#pragma unroll 4
         for (int k = lane * 4; k < HC; k += 128) {
             const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
-            acc += wv.x * q[k] + wv.y * q[k + 1] + wv.z * q[k + 2] + wv.w * q[k + 3];
+            const float4 qv = *reinterpret_cast<const float4*>(q + k);
+            acc += wv.x * qv.x + wv.y * qv.y + wv.z * qv.z + wv.w * qv.w;
         }
         acc = warp_sum(acc);
-        if (lane == 0) { const float r = fmaxf(acc, 0.f); h[j] = r; se_h[((size_t)d * B + b) * HSE + j] = r; }
+        if (lane == 0) { const float r = fmaxf(acc, 0.f); h[j] = r; se_h[slot * HSE + j] = r; }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < HC; c += 256) {
-        const float* w = sp.l2[d] + (size_t)c * HSE;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int j = 0; j < HSE; j += 4) {
-            const float4 wv = __ldg(reinterpret_cast<const float4*>(w + j));
-            acc += wv.x * h[j] + wv.y * h[j + 1] + wv.z * h[j + 2] + wv.w * h[j + 3];
+    const float4 hv = *reinterpret_cast<const float4*>(h + lane * 4);
+    const size_t n = (size_t)b * T + tau;
+    for (int c = warp; c < HC; c += NW) {                 // one warp per output channel: a 512-byte row of L2, coalesced
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(sp.l2[d] + (size_t)c * HSE + lane * 4));
+        float acc = wv.x * hv.x + wv.y * hv.y + wv.z * hv.z + wv.w * hv.w;
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float a = 1.f / (1.f + expf(-acc));
+            se_a[slot * HC + c] = a;
+            out_d[((size_t)d * B * T + n) * HC + c] = (1.f + a) * gc[n * HC + c];
         }
-        const float a = 1.f / (1.f + expf(-acc));
-        se_a[((size_t)d * B + b) * HC + c] = a;
-        const size_t n = (size_t)b * T + tau;
-        out_d[((size_t)d * B * T + n) * HC + c] = (1.f + a) * gc[n * HC + c];
     }
 }
 
@@ -499,8 +543,8 @@ int head_prepare_weights(grl_handle* h, cudaStream_t st, const grl_head_params* 
 
 static int bn_finalize(grl_handle* h, cudaStream_t st, const float* psum, const float* psq, int nparts, long long bstride, int Cn,
                        double count, const BnPtrs& bp, float* stat, int train, int nz) {
-    dim3 grid((Cn + 127) / 128, nz);
-    bn_finalize_kernel<<<grid, 128, 0, st>>>(psum, psq, nparts, bstride, Cn, count, bp, stat, train);
+    dim3 grid((Cn + 31) / 32, nz);
+    bn_finalize_kernel<<<grid, dim3(32, 8), 0, st>>>(psum, psq, nparts, bstride, Cn, count, bp, stat, train);
     GRL_LAUNCH_CHECK(h);
     return GRL_OK;
 }
@@ -545,13 +589,11 @@ extern "C" int grl_head_forward(grl_handle* h, const grl_head_params* p, const f
     GRL_LAUNCH_CHECK(h);
     glo_mean_kernel<<<(B * HC + 255) / 256, 256, 0, st>>>(WS_F32(w, gx), WS_F32(w, g), B, T);
     GRL_LAUNCH_CHECK(h);
-    small_linear_kernel<<<(HG * 32 + 255) / 256, 256, 0, st>>>(WS_F32(w, g), p->glo_fc_w, HC, p->glo_fc_b, WS_F32(w, u), B, HC, HG);
-    GRL_LAUNCH_CHECK(h);
+    GRL_TRY(small_matmul(h, st, WS_F32(w, g), HC, p->glo_fc_w, 1, HC, p->glo_fc_b, WS_F32(w, u), HG, B, HC, HG));
     bn1d_relu_kernel<<<(HG + 127) / 128, 128, 0, st>>>(WS_F32(w, u), WS_F32(w, glo), B, HG, p->glo_bn.weight, p->glo_bn.bias,
                                                        p->glo_bn.running_mean, p->glo_bn.running_var, WS_F32(w, glo_stat), train);
     GRL_LAUNCH_CHECK(h);
-    small_linear_kernel<<<(HG * 32 + 255) / 256, 256, 0, st>>>(WS_F32(w, glo), p->atte0_w + HC, HC + HG, nullptr, WS_F32(w, bias1), B, HG, HG);
-    GRL_LAUNCH_CHECK(h);
+    GRL_TRY(small_matmul(h, st, WS_F32(w, glo), HG, p->atte0_w + HC, 1, HC + HG, nullptr, WS_F32(w, bias1), HG, B, HG, HG));
     {   // corr_atte.0: Y1 = X W1a^T + bias1[clip]   (planes out + BN statistics)
         GemmEpi e = epi_default();
         e.Phi = WS_BF(w, y1_hi); e.Plo = WS_BF(w, y1_lo); e.ldp = HG;
@@ -610,7 +652,7 @@ extern "C" int grl_head_forward(grl_handle* h, const grl_head_params* p, const f
         const int tau0 = i, tau1 = T - 1 - i;
         const __nv_bfloat16 *mh = WS_BF(w, mem_hi) + ms * slotM, *ml = WS_BF(w, mem_lo) + ms * slotM;
         const __nv_bfloat16 *zh = WS_BF(w, z_hi) + zs * slotM, *zl = WS_BF(w, z_lo) + zs * slotM;
-        float* qpart = WS_F32(w, qpart) + (size_t)sl * 2 * 4 * B * HC;
+        float* qpart = WS_F32(w, qpart) + (size_t)i * 2 * 4 * B * HC;
         {   // f1 on the memory + squared difference against f2[tau], pooled over the 128 pixels of each clip
             GemmEpi e = epi_default();
             if (save) { e.C = WS_F32(w, f1) + (size_t)sl * 2 * R * HC; e.ldc = HC; e.c_bstride = (long long)R * HC; }
@@ -621,13 +663,6 @@ extern "C" int grl_head_forward(grl_handle* h, const grl_head_params* p, const f
             e.col_sq = qpart; e.stat_bstride = (long long)4 * B * HC;
             Operand a{mh, ml, HC, (long long)R * HC, 0}, b{WS_BF(w, wf1_hi), WS_BF(w, wf1_lo), HC, (long long)HC * HC, 0};
             GRL_TRY(gemm_launch(h, st, R, HC, HC, 2, a, b, e, 0));
-        }
-        {
-            SePtrs sp; sp.l1[0] = p->se1_w[0]; sp.l1[1] = p->se1_w[1]; sp.l2[0] = p->se2_w[0]; sp.l2[1] = p->se2_w[1];
-            se_fwd_kernel<<<dim3(B, 2), 256, 0, st>>>(qpart, sp, WS_F32(w, gc), B, T, tau0, tau1, WS_F32(w, se_q) + (size_t)sl * 2 * B * HC,
-                                                      WS_F32(w, se_h) + (size_t)sl * 2 * B * HSE, WS_F32(w, se_a) + (size_t)sl * 2 * B * HC,
-                                                      WS_F32(w, out_d));
-            GRL_LAUNCH_CHECK(h);
         }
         // ---- memory update: BasicBlock(M, Xu[tau]) ----
         float* h1 = WS_F32(w, h1) + (size_t)sl * 2 * R * HB;
@@ -674,6 +709,12 @@ extern "C" int grl_head_forward(grl_handle* h, const grl_head_params* p, const f
                                                                 T - 2 - i, WS_BF(w, mem_hi) + ms_next * slotM, WS_BF(w, mem_lo) + ms_next * slotM,
                                                                 WS_BF(w, z_hi) + (has_next ? zs_next : zs) * slotM,
                                                                 WS_BF(w, z_lo) + (has_next ? zs_next : zs) * slotM);
+        GRL_LAUNCH_CHECK(h);
+    }
+    {   // squeeze-excite + F4 pooled shortcut for all steps at once
+        SePtrs sp; sp.l1[0] = p->se1_w[0]; sp.l1[1] = p->se1_w[1]; sp.l2[0] = p->se2_w[0]; sp.l2[1] = p->se2_w[1];
+        se_fwd_kernel<<<dim3(B, 2, T), SE_THREADS, 0, st>>>(WS_F32(w, qpart), sp, WS_F32(w, gc), B, T, WS_F32(w, se_q), WS_F32(w, se_h),
+                                                            WS_F32(w, se_a), WS_F32(w, out_d));
         GRL_LAUNCH_CHECK(h);
     }
     const int mfin = save ? T : (T & 1);
