@@ -80,6 +80,9 @@ _SIGNATURES = {
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "grl_topk_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    "grl_dist_topk_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "grl_dist_topk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "grl_head_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "grl_head_forward": (C.c_int, [C.c_void_p, C.POINTER(HeadParams), C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

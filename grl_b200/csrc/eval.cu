@@ -312,6 +312,76 @@ extern "C" int grl_distance(grl_handle* h, int metric, const float* q, const flo
     return gemm_launch(h, st, nq, ng, dim, 1, oa, ob, e, 0);
 }
 
+// ------------------------------------------------------------------ gallery-shard search: distance tiles + streaming top-k
+static int topk_chunk_cols(int nq, int ng) {
+    long long c = (1ll << 28) / (4ll * (nq > 0 ? nq : 1));       // ~256 MB distance tile
+    c = c / 256 * 256;
+    if (c < 1024) c = 1024;
+    if (c > 16384) c = 16384;
+    if (c > ng) c = (ng + 7) / 8 * 8;
+    return (int)c;
+}
+
+static void dist_topk_layout(int nq, int ng, int dim, size_t* q_pl, size_t* g_pl, size_t* norms, size_t* tile, int* chunk) {
+    *chunk = topk_chunk_cols(nq, ng);
+    *q_pl = align_up((size_t)nq * dim * 2, 1024);
+    *g_pl = align_up((size_t)*chunk * dim * 2, 1024);
+    *norms = align_up((size_t)(nq + *chunk) * 4, 1024);
+    *tile = align_up((size_t)nq * *chunk * 4, 1024);
+}
+
+extern "C" size_t grl_dist_topk_workspace_bytes(int nq, int ng, int dim) {
+    size_t a, b, c, t; int chunk;
+    dist_topk_layout(nq, ng, dim, &a, &b, &c, &t, &chunk);
+    return 2 * a + 2 * b + c + t;
+}
+
+extern "C" int grl_dist_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k,
+                             int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !q || !g || !top_d || !top_i || !workspace) return set_error(h, GRL_EINVAL, "grl_dist_topk: NULL argument");
+    if (nq <= 0 || ng <= 0 || dim <= 0 || (dim & 7)) return set_error(h, GRL_EINVAL, "grl_dist_topk: need nq,ng > 0 and dim %% 8 == 0 (dim=%d)", dim);
+    if (k <= 0 || k > TOPK_MAXK) return set_error(h, GRL_EINVAL, "grl_dist_topk: need 0 < k <= %d", TOPK_MAXK);
+    if (metric != GRL_METRIC_NEG_DOT && metric != GRL_METRIC_L2) return set_error(h, GRL_EINVAL, "grl_dist_topk: unknown metric %d", metric);
+    if (idx_base < 0 || idx_base + ng > 0xFFFFFFFFll) return set_error(h, GRL_EINVAL, "grl_dist_topk: global index must fit 32 bits");
+    if (workspace_bytes < grl_dist_topk_workspace_bytes(nq, ng, dim)) return set_error(h, GRL_ENOMEM, "grl_dist_topk: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t qb, gb, nb, tb; int chunk;
+    dist_topk_layout(nq, ng, dim, &qb, &gb, &nb, &tb, &chunk);
+    uint8_t* w = (uint8_t*)workspace;
+    __nv_bfloat16* q_hi = (__nv_bfloat16*)w; w += qb;
+    __nv_bfloat16* q_lo = (__nv_bfloat16*)w; w += qb;
+    __nv_bfloat16* g_hi = (__nv_bfloat16*)w; w += gb;
+    __nv_bfloat16* g_lo = (__nv_bfloat16*)w; w += gb;
+    float* qn = (float*)w;
+    float* gn = qn + nq; w += nb;
+    float* tile = (float*)w;
+    GRL_TRY(split_planes(h, st, q, dim, q_hi, q_lo, dim, nq, dim));
+    if (metric == GRL_METRIC_L2) {
+        row_sqnorm_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(q, nq, dim, qn);
+        GRL_LAUNCH_CHECK(h);
+    }
+    GRL_TRY(grl_topk_init(h, top_d, top_i, nq, k, stream));
+    for (int c0 = 0; c0 < ng; c0 += chunk) {
+        const int nc = (ng - c0 < chunk) ? ng - c0 : chunk;
+        const float* gc = g + (size_t)c0 * dim;
+        GRL_TRY(split_planes(h, st, gc, dim, g_hi, g_lo, dim, nc, dim));
+        GemmEpi e = epi_default();
+        e.C = tile; e.ldc = chunk;
+        if (metric == GRL_METRIC_L2) {
+            row_sqnorm_kernel<<<(nc * 32 + 255) / 256, 256, 0, st>>>(gc, nc, dim, gn);
+            GRL_LAUNCH_CHECK(h);
+            e.mode = 1; e.row_norm = qn; e.col_norm = gn;
+        } else {
+            e.alpha = -1.f;
+        }
+        Operand oa{q_hi, q_lo, dim, 0, 0}, ob{g_hi, g_lo, dim, 0, 0};
+        GRL_TRY(gemm_launch(h, st, nq, nc, dim, 1, oa, ob, e, 0));
+        topk_rows_kernel<<<nq, TOPK_THREADS, 0, st>>>(tile, chunk, nc, k, idx_base + c0, top_d, top_i);
+        GRL_LAUNCH_CHECK(h);
+    }
+    return GRL_OK;
+}
+
 extern "C" int grl_cmc_map(grl_handle* h, const float* dist, long long ld_dist, const int64_t* q_pid, const int64_t* g_pid,
                            const int64_t* q_cam, const int64_t* g_cam, int nq, int ng, int max_rank, int32_t* cmc_hits,
                            double* ap, int32_t* first_hit, void* stream) {

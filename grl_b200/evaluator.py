@@ -131,6 +131,76 @@ def argsort_rows(distmat):
     return order
 
 
+# --------------------------------------------------------------------------------------------
+# Gallery-sharded retrieval (BASELINE.json configs[4]).  The reference has no counterpart: it materialises the whole
+# matrix and argsorts it on the CPU (attevaluator.py:150, eva_functions.py:139).  Gallery rows are split contiguously
+# over the ranks, queries are replicated; every rank searches its shard, one all-gather of [nq, k] candidates over
+# NCCL/NVLink follows, and every rank merges them with ties broken by the lower global gallery index, so the result
+# does not depend on the number of shards.
+# --------------------------------------------------------------------------------------------
+def shard_bounds(num_gallery, world_size, rank):
+    """Contiguous split of gallery rows: returns (first row, number of rows) of `rank`."""
+    base, rem = divmod(num_gallery, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, base + (1 if rank < rem else 0)
+
+
+def retrieve_topk(qf, gf, k, idx_base=0, metric=0):
+    """k nearest rows of this gallery shard per query (grl_dist_topk).  Returns CUDA (dist f32 [nq,k], index i64 [nq,k])."""
+    qf = _as_cuda_f32(qf)
+    gf = _as_cuda_f32(gf, qf.device)
+    nq, ng, dim = qf.size(0), gf.size(0), qf.size(1)
+    if gf.size(1) != dim:
+        raise RuntimeError("size mismatch, qf %s vs gf %s" % (tuple(qf.shape), tuple(gf.shape)))
+    if dim % 8:
+        pad = 8 - dim % 8
+        qf = torch.nn.functional.pad(qf, (0, pad))
+        gf = torch.nn.functional.pad(gf, (0, pad))
+        dim += pad
+    lib = _lib.load_library()
+    with torch.cuda.device(qf.device):
+        h = _lib.get_handle(qf.device)
+        top_d = torch.empty((nq, k), dtype=torch.float32, device=qf.device)
+        top_i = torch.empty((nq, k), dtype=torch.int64, device=qf.device)
+        ws_bytes = lib.grl_dist_topk_workspace_bytes(nq, ng, dim)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qf.device)
+        _lib.check(h, lib.grl_dist_topk(h, metric, qf.data_ptr(), gf.data_ptr(), nq, ng, dim, k, idx_base, top_d.data_ptr(),
+                                        top_i.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(qf.device)), "grl_dist_topk")
+    return top_d, top_i
+
+
+def merge_topk(all_d, all_i):
+    """[nshards, nq, k] candidate lists -> [nq, k] (grl_topk_merge; (distance, global index) order)."""
+    nshards, nq, k = all_d.shape
+    all_d = all_d.contiguous()
+    all_i = all_i.contiguous()
+    lib = _lib.load_library()
+    with torch.cuda.device(all_d.device):
+        h = _lib.get_handle(all_d.device)
+        out_d = torch.empty((nq, k), dtype=torch.float32, device=all_d.device)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=all_d.device)
+        _lib.check(h, lib.grl_topk_merge(h, all_d.data_ptr(), all_i.data_ptr(), nshards, nq, k, out_d.data_ptr(), out_i.data_ptr(),
+                                         _lib.stream_ptr(all_d.device)), "grl_topk_merge")
+    return out_d, out_i
+
+
+def sharded_retrieve(qf, gf_local, k, idx_base, group=None, metric=0, local_search=retrieve_topk, merge=merge_topk):
+    """One search over a gallery sharded across the ranks of `group` (torch.distributed; NCCL on B200).
+
+    `local_search` / `merge` are the per-rank kernels (CUDA by default); they are parameters only so that the
+    rendezvous / gather / merge plumbing can be exercised on CPU with gloo in tests."""
+    import torch.distributed as dist
+    d, i = local_search(qf, gf_local, k, idx_base=idx_base, metric=metric)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return d, i
+    world = dist.get_world_size(group)
+    all_d = [torch.empty_like(d) for _ in range(world)]
+    all_i = [torch.empty_like(i) for _ in range(world)]
+    dist.all_gather(all_d, d.contiguous(), group=group)
+    dist.all_gather(all_i, i.contiguous(), group=group)
+    return merge(torch.stack(all_d), torch.stack(all_i))
+
+
 class ATTEvaluator(object):
     """attevaluator.py:49-163 with the hot calls replaced; loaders/models are the caller's (PyTorch/cuDNN backbone)."""
 

@@ -106,6 +106,13 @@ int grl_topk_rows(grl_handle* h, const float* dist, long long ld_dist, int nq, i
                   float* top_d, int64_t* top_i, void* stream);
 int grl_topk_merge(grl_handle* h, const float* all_d, const int64_t* all_i, int nshards, int nq, int k,
                    float* out_d, int64_t* out_i, void* stream);
+/* One gallery shard, end to end: k nearest gallery rows of every query without materialising the nq x ng matrix
+ * (it is 40 GB at 10k x 1M).  The shard is streamed in column chunks: split-bf16 planes -> tcgen05 distance tile
+ * (<= 256 MB) -> streaming top-k.  g [ng][dim] is this rank's shard, idx_base the global index of its first row.
+ * top_d/top_i [nq][k] are overwritten (sorted by (distance, global index)).  metric as in grl_distance.       */
+size_t grl_dist_topk_workspace_bytes(int nq, int ng, int dim);
+int grl_dist_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k,
+                  int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- GCE + TRL head ------------------------------------------------------------------ */
 /* Parameter block: device pointers to the reference's own state_dict tensors (fp32), in the

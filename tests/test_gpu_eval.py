@@ -142,3 +142,33 @@ def test_topk_stream_and_merge_shard_invariant():
         od = torch.empty((nq, k), device="cuda"); oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
         _lib.check(h, lib.grl_topk_merge(h, all_d.data_ptr(), all_i.data_ptr(), shards, nq, k, od.data_ptr(), oi.data_ptr(), st), "merge")
         assert np.array_equal(od.cpu().numpy(), v_ref) and np.array_equal(oi.cpu().numpy(), i_ref)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_dist_topk_shard_invariant_vs_oracle(metric):
+    """grl_dist_topk per shard + grl_topk_merge == stable top-k of the full distance matrix, for 1/2/4/8 shards."""
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    rng = np.random.default_rng(11)
+    nq, ng, dim, k = 41, 20011, 128, 100
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    g = rng.standard_normal((ng, dim)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)               # unit-norm descriptors like the reference's features
+    g /= np.linalg.norm(g, axis=1, keepdims=True)
+    g[::13] = g[5]                                              # exact ties, also across shard boundaries
+    qd, gd = torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda()
+    full = (ev.cosin_dist(qd, gd) if metric == 0 else ev.pairwise_distance_tensor(qd, gd)).cpu().numpy()
+    v_ref, i_ref = eo.topk_stable(full, k)                      # same device distances: index-exact comparison
+    for shards in (1, 2, 4, 8):
+        parts = []
+        for r in range(shards):
+            lo, n = ev.shard_bounds(ng, shards, r)
+            parts.append(ev.retrieve_topk(qd, gd[lo:lo + n], k, idx_base=lo, metric=metric))
+        od, oi = ev.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+        assert np.array_equal(oi.cpu().numpy(), i_ref), shards
+        assert np.array_equal(od.cpu().numpy(), v_ref), shards
+    # and against the CPU fp32 arithmetic of the reference: identical ranking except at ties within 1e-5
+    ref = eo.cosin_dist(q, g) if metric == 0 else eo.pairwise_distance(q, g)
+    got_d = np.take_along_axis(ref, oi.cpu().numpy(), 1)
+    best = np.sort(ref, axis=1)[:, :k]
+    assert np.abs(got_d - best).max() <= 2e-5

@@ -7,8 +7,12 @@ Truth = the fp64 oracle (oracle/head_oracle.py, pinned to the real reference by 
     test of the backward kernels;
   * backward end to end: the head's gradient is a discontinuous function of its inputs (ReLU masks, tiny-batch BN),
     so even the reference's own fp32 run differs from its fp64 run by 1e-3..6e-3 (a forward
-    perturbation of 1e-6 relative already moves dx by 2e-3..5e-3, DESIGN.md "Numerics").  Gate per tensor:
-    err(ours, fp64) <= max(1e-3, E2E_FLOOR_MULT * err(reference fp32, fp64)).  The two scalar gradients of
+    perturbation of 1e-6 relative already moves dx by 2e-3..5e-3, DESIGN.md "Numerics"); whether a given run flips a
+    mask is a coin toss, so the reference's floor itself jumps between 1e-7 and 5e-3 from tensor to tensor.  Gates:
+      - gradients no kink feeds (f1 / f2 / channel attention weights): 1e-3, the north-star figure;
+      - gradients downstream of the memory-update ReLUs and the GCE gate (everything else, incl. dx):
+        err(ours, fp64) <= max(KINK_TOL, E2E_FLOOR_MULT * err(reference fp32, fp64)).
+    The two scalar gradients of
     corr_atte.6 (BatchNorm2d(1): sums of >= 1024 signed terms that cancel to ~1e-3 of their absolute mass) get an
     absolute allowance instead; their kernels are pinned by the conditioned test above.
 """
@@ -24,6 +28,7 @@ from grl_b200 import synth
 pytestmark = pytest.mark.gpu
 
 E2E_FLOOR_MULT = 10.0     # the tensor-core forward sits at ~1e-5 vs the CPU fp32 reference's ~1e-6: ~3x more mask flips
+KINK_TOL = 1e-2           # a handful of flipped ReLU masks among ~1e6 activations
 SCALAR_BN_TOL = 1e-1      # corr_atte.6.weight / .bias, see module docstring
 # parameters whose gradient is analytically zero: a per-channel constant added in front of a train-mode BatchNorm
 # (glo_fc.0.bias -> glo_fc.1;  corr_atte.1.bias -> conv -> corr_atte.3).  Compared against the scale of their layer.
@@ -131,7 +136,12 @@ def test_backward_end_to_end_vs_fp64_oracle(B, T):
         floor = rel(r32, r64)
         err = rel(ours, r64)
         report[name] = (err, floor)
-        tol = SCALAR_BN_TOL if name.startswith("backbone.corr_atte.6") else max(1e-3, E2E_FLOOR_MULT * floor)
+        if name.startswith("backbone.corr_atte.6"):
+            tol = SCALAR_BN_TOL
+        elif "_f1.0" in name or "_f2.0" in name or "channel_atte" in name:
+            tol = 1e-3
+        else:
+            tol = max(KINK_TOL, E2E_FLOOR_MULT * floor)
         assert err <= tol, (name, err, floor)
 
     gate("dx", dx, dx64, dx32)
