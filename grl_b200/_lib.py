@@ -90,6 +90,14 @@ _SIGNATURES = {
     "grl_head_backward": (C.c_int, [C.c_void_p, C.POINTER(HeadParams), C.c_void_p, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(HeadGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "grl_gce_forward": (C.c_int, [C.c_void_p, C.POINTER(HeadParams), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "grl_gce_backward": (C.c_int, [C.c_void_p, C.POINTER(HeadParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.POINTER(HeadGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "grl_trl_forward": (C.c_int, [C.c_void_p, C.POINTER(HeadParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "grl_trl_backward": (C.c_int, [C.c_void_p, C.POINTER(HeadParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.POINTER(HeadGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
     "grl_head_ws_lookup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
 }
 

@@ -10,6 +10,8 @@
 //   wgrad  = same GEMM with both operands MN-major (K = pixels), accumulated over the T steps
 //   BN     = reduce (sum g, sum g*xhat) -> finalize -> apply, HBM-bound, 128-bit accesses
 // Buffers live in the caller's workspace (head_common.cuh); `dxu` is used as dZ[T][2][R][C].
+#include <stddef.h>
+
 #include "head_common.cuh"
 
 namespace grl {
@@ -310,14 +312,14 @@ __global__ void __launch_bounds__(256) nchw_to_pm_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) gce_bwd_gate_kernel(const float* __restrict__ dz, const float* __restrict__ dmem, float* __restrict__ dxc,
                                                            const float* __restrict__ dgc, const __nv_bfloat16* __restrict__ xh,
                                                            const __nv_bfloat16* __restrict__ xl, const float* __restrict__ m, int B, int T,
-                                                           const float* __restrict__ dxu_extra, float* __restrict__ dm_part) {
+                                                           const float* __restrict__ dxu_extra, int use_trl, float* __restrict__ dm_part) {
     const int n = blockIdx.y, c0 = blockIdx.x * 64;
     const int b = n / T, tt = n - b * T;
     const int R = B * HS;
     const size_t P = (size_t)B * T * HS;
     const Tile t;
-    float gcv[8];
-    load8(dgc + (size_t)n * HC + c0 + t.cg * 8, gcv);
+    float gcv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (use_trl) load8(dgc + (size_t)n * HC + c0 + t.cg * 8, gcv);
     const float invT = 1.f / (float)T;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -325,21 +327,28 @@ __global__ void __launch_bounds__(256) gce_bwd_gate_kernel(const float* __restri
         const size_t col = c0 + t.cg * 8;
         const size_t rrow = (size_t)b * HS + s;
         const size_t p = (size_t)n * HS + s;
-        float u[8], v[8], a[8];
-        load8(dz + (((size_t)tt * 2 + 0) * R + rrow) * HC + col, u);
-        load8(dz + (((size_t)(T - 1 - tt) * 2 + 1) * R + rrow) * HC + col, v);
+        float u[8] = {0, 0, 0, 0, 0, 0, 0, 0}, v[8], a[8];
+        if (use_trl) {
+            load8(dz + (((size_t)tt * 2 + 0) * R + rrow) * HC + col, u);
+            load8(dz + (((size_t)(T - 1 - tt) * 2 + 1) * R + rrow) * HC + col, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) u[i] += v[i];
-        load8(dz + ((size_t)0 * R + rrow) * HC + col, v);
-        load8(dz + ((size_t)1 * R + rrow) * HC + col, a);
+            for (int i = 0; i < 8; ++i) u[i] += v[i];
+            load8(dz + ((size_t)0 * R + rrow) * HC + col, v);
+            load8(dz + ((size_t)1 * R + rrow) * HC + col, a);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += a[i];
-        load8(dmem + ((size_t)0 * R + rrow) * HC + col, a);
+            for (int i = 0; i < 8; ++i) v[i] += a[i];
+            load8(dmem + ((size_t)0 * R + rrow) * HC + col, a);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += a[i];
-        load8(dmem + ((size_t)1 * R + rrow) * HC + col, a);
+            for (int i = 0; i < 8; ++i) v[i] += a[i];
+            load8(dmem + ((size_t)1 * R + rrow) * HC + col, a);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) u[i] += (v[i] + a[i]) * invT;       // u = dXu
+            for (int i = 0; i < 8; ++i) u[i] += (v[i] + a[i]) * invT;   // u = dXu
+        }
+        if (dxu_extra) {                                                 // upstream gradient on the stand-alone x_uncorr
+            load8(dxu_extra + p * HC + col, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[i] += a[i];
+        }
         float c[8], x[8], o[8];
         load8(dxc + p * HC + col, c);
         load8_planes(xh + p * HC + col, xl + p * HC + col, x);
@@ -596,6 +605,46 @@ __global__ void gce_bwd_glo_bn_kernel(const float* __restrict__ dglo, const floa
     dfc_bias[k] = bsum;
 }
 
+// Stand-alone TRL backward: d x_uncorr / d x_corr in pixel-major form (same sums as the gate kernel).  grid (C/64, N)
+//   dxu_out = dZ[t][fwd] + dZ[T-1-t][bwd] + (dM0_fwd + dM0_bwd)/T ;   dxc (in place) += dgc/S
+__global__ void __launch_bounds__(256) trl_bwd_collect_kernel(const float* __restrict__ dz, const float* __restrict__ dmem, float* __restrict__ dxc,
+                                                              const float* __restrict__ dgc, int B, int T, float* __restrict__ dxu_out) {
+    const int n = blockIdx.y, c0 = blockIdx.x * 64;
+    const int b = n / T, tt = n - b * T;
+    const int R = B * HS;
+    const Tile t;
+    float gcv[8];
+    load8(dgc + (size_t)n * HC + c0 + t.cg * 8, gcv);
+    const float invT = 1.f / (float)T;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int s = t.r0 + 32 * k;
+        const size_t col = c0 + t.cg * 8;
+        const size_t rrow = (size_t)b * HS + s;
+        const size_t p = (size_t)n * HS + s;
+        float u[8], v[8], a[8];
+        load8(dz + (((size_t)tt * 2 + 0) * R + rrow) * HC + col, u);
+        load8(dz + (((size_t)(T - 1 - tt) * 2 + 1) * R + rrow) * HC + col, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] += v[i];
+        load8(dz + ((size_t)0 * R + rrow) * HC + col, v);
+        load8(dz + ((size_t)1 * R + rrow) * HC + col, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += a[i];
+        load8(dmem + ((size_t)0 * R + rrow) * HC + col, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += a[i];
+        load8(dmem + ((size_t)1 * R + rrow) * HC + col, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] += (v[i] + a[i]) * invT;
+        store8(dxu_out + p * HC + col, u);
+        load8(dxc + p * HC + col, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += gcv[i] * (1.f / HS);
+        store8(dxc + p * HC + col, v);
+    }
+}
+
 // dx (NCHW) = transpose(dX1 pixel-major) + dg[b][c] / (T*S)      grid (C/64, N)
 __global__ void __launch_bounds__(256) pm_to_nchw_bias_kernel(const float* __restrict__ src, const float* __restrict__ dg, int T, float scale,
                                                               float* __restrict__ out) {
@@ -603,8 +652,8 @@ __global__ void __launch_bounds__(256) pm_to_nchw_bias_kernel(const float* __res
     const int n = blockIdx.y, c0 = blockIdx.x * 64;
     const int b = n / T;
     const Tile t;
-    float add[8];
-    load8(dg + (size_t)b * HC + c0 + t.cg * 8, add);
+    float add[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (dg) load8(dg + (size_t)b * HC + c0 + t.cg * 8, add);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int s = t.r0 + 32 * k;
@@ -653,26 +702,15 @@ static int outer(grl_handle* h, cudaStream_t st, const float* A, long long a_os,
 
 using namespace grl;
 
-extern "C" int grl_head_backward(grl_handle* h, const grl_head_params* p, const float* x, int B, int T, const float* d_f_uncorr,
-                                 const float* d_f_corr, const float* d_x_uncorr, const float* d_x_corr, const float* d_corr_map,
-                                 float* dx, const grl_head_grads* g, void* workspace, size_t workspace_bytes, void* stream) {
-    if (!h || !p || !x || !d_f_uncorr || !d_f_corr || !dx || !g || !workspace) return set_error(h, GRL_EINVAL, "grl_head_backward: NULL argument");
-    if (B < 2 || T <= 0) return set_error(h, GRL_EINVAL, "grl_head_backward: need B >= 2, T > 0");
-    {
-        const float* const* gp = reinterpret_cast<const float* const*>(g);
-        for (size_t i = 0; i < sizeof(grl_head_grads) / sizeof(float*); ++i)
-            if (!gp[i]) return set_error(h, GRL_EINVAL, "grl_head_backward: NULL gradient pointer (slot %zu)", i);
-    }
-    HeadWs w = head_ws_layout(B, T, 1);
-    if (workspace_bytes < w.total) return set_error(h, GRL_ENOMEM, "grl_head_backward: workspace %zu < %zu bytes", workspace_bytes, w.total);
-    if (reinterpret_cast<uintptr_t>(workspace) & 1023) return set_error(h, GRL_EINVAL, "grl_head_backward: workspace must be 1024-byte aligned");
-    w.base = (uint8_t*)workspace;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int N = w.N, P = w.P, R = w.R;
+namespace grl {
+
+// TRL backward: leaves dZ[T][2][R][C] (in `dxu`), dmem (= dF1_0 Wf1), dxc (= dF2cat Wf2cat) and dgc in the workspace
+static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_params* p, const HeadWs& w, const float* d_f_uncorr,
+                             const float* d_f_corr, const grl_head_grads* g) {
+    const int B = w.B, T = w.T, N = w.N, P = w.P, R = w.R;
     const size_t slotM = (size_t)2 * R * HC, slotB = (size_t)2 * R * HB;
     float* dz_all = WS_F32(w, dxu);                 // dZ[T][2][R][HC]
     float* dmem = WS_F32(w, dmem);
-
     // ---------------- squeeze-excite backward for every step (independent of the recurrence) ----------------
     {
         SePtrsB sp; sp.l1[0] = p->se1_w[0]; sp.l1[1] = p->se1_w[1]; sp.l2[0] = p->se2_w[0]; sp.l2[1] = p->se2_w[1];
@@ -799,20 +837,21 @@ extern "C" int grl_head_backward(grl_handle* h, const grl_head_params* p, const 
         Operand a{WS_BF(w, df2_hi), WS_BF(w, df2_lo), 2 * HC, 0, 0}, b{WS_BF(w, wf2_hi), WS_BF(w, wf2_lo), HC, 0, 1};
         GRL_TRY(gemm_launch(h, st, P, HC, 2 * HC, 1, a, b, e, 0));
     }
-    if (d_x_corr) { nchw_to_pm_kernel<<<dim3(HC / 64, N), 256, 0, st>>>(d_x_corr, WS_F32(w, dxc), 1); GRL_LAUNCH_CHECK(h); }
-    float* dxu_extra = nullptr;       // the saved H3 activations are dead after the BPTT loop: reuse as [P][C] scratch
-    if (d_x_uncorr) {
-        dxu_extra = WS_F32(w, h3);
-        nchw_to_pm_kernel<<<dim3(HC / 64, N), 256, 0, st>>>(d_x_uncorr, dxu_extra, 0);
-        GRL_LAUNCH_CHECK(h);
-    }
+    return GRL_OK;
+}
 
+// GCE backward.  use_trl: take d x_uncorr / d x_corr from the TRL backward state; dxu_extra: extra [P][C] gradient on x_uncorr
+static int gce_backward_part(grl_handle* h, cudaStream_t st, const grl_head_params* p, const HeadWs& w, int use_trl,
+                             const float* d_corr_map, const float* dxu_extra, float* dx, const grl_head_grads* g) {
+    const int B = w.B, T = w.T, N = w.N, P = w.P;
+    float* dz_all = WS_F32(w, dxu);
+    float* dmem = WS_F32(w, dmem);
     // ---------------- GCE backward ----------------
     float* gs = WS_F32(w, gsmall);
     float* k2coef = gs;                 // [3][HMID]
     float* k1coef = gs + 1024;          // [3][HG]
     gce_bwd_gate_kernel<<<dim3(HC / 64, N), 256, 0, st>>>(dz_all, dmem, WS_F32(w, dxc), WS_F32(w, dgc), WS_BF(w, xp_hi), WS_BF(w, xp_lo),
-                                                          WS_F32(w, m), B, T, dxu_extra, WS_F32(w, part_c));
+                                                          WS_F32(w, m), B, T, dxu_extra, use_trl, WS_F32(w, part_c));
     GRL_LAUNCH_CHECK(h);
     const int pblocks = (P + 255) / 256;
     gce_bwd_dm_kernel<<<pblocks, 256, 0, st>>>(WS_F32(w, part_c), HC / 64, d_corr_map, WS_F32(w, m), WS_F32(w, y3), WS_F32(w, bn3_stat), P,
@@ -883,4 +922,80 @@ extern "C" int grl_head_backward(grl_handle* h, const grl_head_params* p, const 
     pm_to_nchw_bias_kernel<<<dim3(HC / 64, N), 256, 0, st>>>(WS_F32(w, dxc), WS_F32(w, dg), T, 1.f / (float)(T * HS), dx);
     GRL_LAUNCH_CHECK(h);
     return GRL_OK;
+}
+
+static int check_grads(grl_handle* h, const grl_head_grads* g, int which) {
+    const float* const* gp = reinterpret_cast<const float* const*>(g);
+    const size_t n_gce = offsetof(grl_head_grads, f1_w) / sizeof(float*), n_all = sizeof(grl_head_grads) / sizeof(float*);
+    for (size_t i = (which & 1) ? 0 : n_gce; i < ((which & 2) ? n_all : n_gce); ++i)
+        if (!gp[i]) return set_error(h, GRL_EINVAL, "grl_head backward: NULL gradient pointer (slot %zu)", i);
+    return GRL_OK;
+}
+
+static int bwd_setup(grl_handle* h, const char* who, const grl_head_params* p, int B, int T, const grl_head_grads* g, void* workspace,
+                     size_t workspace_bytes, int which, HeadWs* w) {
+    if (!h || !p || !g || !workspace) return set_error(h, GRL_EINVAL, "%s: NULL argument", who);
+    if (B < ((which & 1) ? 2 : 1) || T <= 0) return set_error(h, GRL_EINVAL, "%s: bad B / T", who);
+    GRL_TRY(check_grads(h, g, which));
+    *w = head_ws_layout(B, T, 1);
+    if (workspace_bytes < w->total) return set_error(h, GRL_ENOMEM, "%s: workspace %zu < %zu bytes", who, workspace_bytes, w->total);
+    if (reinterpret_cast<uintptr_t>(workspace) & 1023) return set_error(h, GRL_EINVAL, "%s: workspace must be 1024-byte aligned", who);
+    w->base = (uint8_t*)workspace;
+    return GRL_OK;
+}
+
+}  // namespace grl
+
+extern "C" int grl_head_backward(grl_handle* h, const grl_head_params* p, const float* x, int B, int T, const float* d_f_uncorr,
+                                 const float* d_f_corr, const float* d_x_uncorr, const float* d_x_corr, const float* d_corr_map,
+                                 float* dx, const grl_head_grads* g, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!x || !d_f_uncorr || !d_f_corr || !dx) return set_error(h, GRL_EINVAL, "grl_head_backward: NULL argument");
+    HeadWs w;
+    GRL_TRY(bwd_setup(h, "grl_head_backward", p, B, T, g, workspace, workspace_bytes, 3, &w));
+    cudaStream_t st = (cudaStream_t)stream;
+    GRL_TRY(trl_backward_part(h, st, p, w, d_f_uncorr, d_f_corr, g));
+    if (d_x_corr) { nchw_to_pm_kernel<<<dim3(HC / 64, w.N), 256, 0, st>>>(d_x_corr, WS_F32(w, dxc), 1); GRL_LAUNCH_CHECK(h); }
+    float* dxu_extra = nullptr;       // the saved H3 activations are dead after the BPTT loop: reuse as [P][C] scratch
+    if (d_x_uncorr) {
+        dxu_extra = WS_F32(w, h3);
+        nchw_to_pm_kernel<<<dim3(HC / 64, w.N), 256, 0, st>>>(d_x_uncorr, dxu_extra, 0);
+        GRL_LAUNCH_CHECK(h);
+    }
+    return gce_backward_part(h, st, p, w, 1, d_corr_map, dxu_extra, dx, g);
+}
+
+extern "C" int grl_trl_backward(grl_handle* h, const grl_head_params* p, int B, int T, const float* d_f_uncorr, const float* d_f_corr,
+                                float* d_x_uncorr, float* d_x_corr, const grl_head_grads* g, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    if (!d_f_uncorr || !d_f_corr || !d_x_uncorr || !d_x_corr) return set_error(h, GRL_EINVAL, "grl_trl_backward: NULL argument");
+    HeadWs w;
+    GRL_TRY(bwd_setup(h, "grl_trl_backward", p, B, T, g, workspace, workspace_bytes, 2, &w));
+    cudaStream_t st = (cudaStream_t)stream;
+    GRL_TRY(trl_backward_part(h, st, p, w, d_f_uncorr, d_f_corr, g));
+    float* dxu_pm = WS_F32(w, h3);    // dead after the BPTT loop
+    trl_bwd_collect_kernel<<<dim3(HC / 64, w.N), 256, 0, st>>>(WS_F32(w, dxu), WS_F32(w, dmem), WS_F32(w, dxc), WS_F32(w, dgc), B, T, dxu_pm);
+    GRL_LAUNCH_CHECK(h);
+    pm_to_nchw_bias_kernel<<<dim3(HC / 64, w.N), 256, 0, st>>>(dxu_pm, nullptr, T, 0.f, d_x_uncorr);
+    GRL_LAUNCH_CHECK(h);
+    pm_to_nchw_bias_kernel<<<dim3(HC / 64, w.N), 256, 0, st>>>(WS_F32(w, dxc), nullptr, T, 0.f, d_x_corr);
+    GRL_LAUNCH_CHECK(h);
+    return GRL_OK;
+}
+
+extern "C" int grl_gce_backward(grl_handle* h, const grl_head_params* p, int B, int T, const float* d_x_uncorr, const float* d_x_corr,
+                                const float* d_corr_map, float* dx, const grl_head_grads* g, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    if (!dx) return set_error(h, GRL_EINVAL, "grl_gce_backward: NULL argument");
+    HeadWs w;
+    GRL_TRY(bwd_setup(h, "grl_gce_backward", p, B, T, g, workspace, workspace_bytes, 1, &w));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_x_corr) { nchw_to_pm_kernel<<<dim3(HC / 64, w.N), 256, 0, st>>>(d_x_corr, WS_F32(w, dxc), 0); GRL_LAUNCH_CHECK(h); }
+    else GRL_CUDA(h, cudaMemsetAsync(WS_F32(w, dxc), 0, (size_t)w.P * HC * 4, st));
+    float* dxu_extra = nullptr;
+    if (d_x_uncorr) {
+        dxu_extra = WS_F32(w, h3);
+        nchw_to_pm_kernel<<<dim3(HC / 64, w.N), 256, 0, st>>>(d_x_uncorr, dxu_extra, 0);
+        GRL_LAUNCH_CHECK(h);
+    }
+    return gce_backward_part(h, st, p, w, 0, d_corr_map, dxu_extra, dx, g);
 }

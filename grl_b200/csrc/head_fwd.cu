@@ -13,7 +13,7 @@ namespace grl {
 
 // ------------------------------------------------------------------ K1: NCHW -> pixel-major planes + per-frame sums
 __global__ void __launch_bounds__(256) nchw_to_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
-                                                             __nv_bfloat16* __restrict__ lo, float* __restrict__ gx) {
+                                                             __nv_bfloat16* __restrict__ lo, float* __restrict__ gx, float gx_scale) {
     __shared__ float tile[64][129];
     const int n = blockIdx.y, c0 = blockIdx.x * 64;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) nchw_to_planes_kernel(const float* __rest
         const float4 v = *reinterpret_cast<const float4*>(x + ((size_t)n * HC + c0 + c) * HS + lane * 4);
         tile[c][lane * 4 + 0] = v.x; tile[c][lane * 4 + 1] = v.y; tile[c][lane * 4 + 2] = v.z; tile[c][lane * 4 + 3] = v.w;
         const float s = warp_sum(v.x + v.y + v.z + v.w);
-        if (lane == 0 && gx) gx[(size_t)n * HC + c0 + c] = s;
+        if (lane == 0 && gx) gx[(size_t)n * HC + c0 + c] = s * gx_scale;
     }
     __syncthreads();
     const Tile t;
@@ -500,14 +500,16 @@ __global__ void add2_kernel(const float* __restrict__ a, const float* __restrict
 }
 
 // ------------------------------------------------------------------ host orchestration
-static int check_params(grl_handle* h, const grl_head_params* p) {
+static int check_params(grl_handle* h, const grl_head_params* p, int which) {      // which: 1 = GCE, 2 = TRL, 3 = both
+    if (which & 1) {
     const void* req[] = {p->glo_fc_w, p->glo_fc_b, p->glo_bn.weight, p->glo_bn.bias, p->glo_bn.running_mean, p->glo_bn.running_var,
                          p->atte0_w, p->atte_bn1.weight, p->atte_bn1.bias, p->atte_bn1.running_mean, p->atte_bn1.running_var,
                          p->atte2_w, p->atte_bn3.weight, p->atte_bn3.bias, p->atte_bn3.running_mean, p->atte_bn3.running_var,
                          p->atte5_w, p->atte_bn6.weight, p->atte_bn6.bias, p->atte_bn6.running_mean, p->atte_bn6.running_var};
     for (const void* q : req)
         if (!q) return set_error(h, GRL_EINVAL, "grl_head: NULL GCE parameter pointer");
-    for (int d = 0; d < 2; ++d) {
+    }
+    for (int d = 0; d < 2 && (which & 2); ++d) {
         const void* r2[] = {p->f1_w[d], p->f1_b[d], p->f2_w[d], p->f2_b[d], p->se1_w[d], p->se2_w[d], p->memo_conv1_w[d],
                             p->memo_conv2_w[d], p->memo_conv3_w[d], p->memo_bn1[d].weight, p->memo_bn1[d].bias,
                             p->memo_bn1[d].running_mean, p->memo_bn1[d].running_var, p->memo_bn2[d].weight, p->memo_bn2[d].bias,
@@ -526,10 +528,12 @@ static BnPtrs bn_ptrs(const grl_bn_params& a, const grl_bn_params& b) {
     return r;
 }
 
-int head_prepare_weights(grl_handle* h, cudaStream_t st, const grl_head_params* p, const HeadWs& w) {
-    GRL_TRY(split_planes(h, st, p->atte0_w, HC + HG, WS_BF(w, w1a_hi), WS_BF(w, w1a_lo), HC, HG, HC));
-    GRL_TRY(split_planes(h, st, p->atte2_w, HG, WS_BF(w, w2_hi), WS_BF(w, w2_lo), HG, HMID, HG));
-    for (int d = 0; d < 2; ++d) {
+int head_prepare_weights(grl_handle* h, cudaStream_t st, const grl_head_params* p, const HeadWs& w, int which) {
+    if (which & 1) {
+        GRL_TRY(split_planes(h, st, p->atte0_w, HC + HG, WS_BF(w, w1a_hi), WS_BF(w, w1a_lo), HC, HG, HC));
+        GRL_TRY(split_planes(h, st, p->atte2_w, HG, WS_BF(w, w2_hi), WS_BF(w, w2_lo), HG, HMID, HG));
+    }
+    for (int d = 0; d < 2 && (which & 2); ++d) {
         GRL_TRY(split_planes(h, st, p->f2_w[d], HC, WS_BF(w, wf2_hi) + (size_t)d * HC * HC, WS_BF(w, wf2_lo) + (size_t)d * HC * HC, HC, HC, HC));
         GRL_TRY(split_planes(h, st, p->f1_w[d], HC, WS_BF(w, wf1_hi) + (size_t)d * HC * HC, WS_BF(w, wf1_lo) + (size_t)d * HC * HC, HC, HC, HC));
         GRL_TRY(split_planes(h, st, p->memo_conv1_w[d], HC, WS_BF(w, wc1_hi) + (size_t)d * HB * HC, WS_BF(w, wc1_lo) + (size_t)d * HB * HC, HC, HB, HC));
@@ -568,24 +572,14 @@ extern "C" int grl_head_ws_lookup(int B, int T, int save_for_backward, const cha
     return GRL_EINVAL;
 }
 
-extern "C" int grl_head_forward(grl_handle* h, const grl_head_params* p, const float* x, int B, int T, int train, float* f_uncorr,
-                                float* f_corr, float* corr_map, float* x_uncorr, float* x_corr, void* workspace,
-                                size_t workspace_bytes, int save_for_backward, void* stream) {
-    if (!h || !p || !x || !f_uncorr || !f_corr || !workspace) return set_error(h, GRL_EINVAL, "grl_head_forward: NULL argument");
-    if (B <= 0 || T <= 0) return set_error(h, GRL_EINVAL, "grl_head_forward: need B, T > 0");
-    if (train && B < 2) return set_error(h, GRL_EINVAL, "grl_head_forward: train-mode BatchNorm1d needs B >= 2 (got %d)", B);
-    GRL_TRY(check_params(h, p));
-    HeadWs w = head_ws_layout(B, T, save_for_backward ? 1 : 0);
-    if (workspace_bytes < w.total) return set_error(h, GRL_ENOMEM, "grl_head_forward: workspace %zu < %zu bytes", workspace_bytes, w.total);
-    if (reinterpret_cast<uintptr_t>(workspace) & 1023) return set_error(h, GRL_EINVAL, "grl_head_forward: workspace must be 1024-byte aligned");
-    w.base = (uint8_t*)workspace;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int N = w.N, P = w.P, R = w.R;
+namespace grl {
 
-    GRL_TRY(head_prepare_weights(h, st, p, w));
-
+// GCE: layer4 maps -> corr_map m, gated planes Xc / Xu, GAP(x_corr)      (basebranch.py:56-68)
+static int gce_forward_part(grl_handle* h, cudaStream_t st, const grl_head_params* p, const HeadWs& w, const float* x, int train,
+                            float* corr_map, float* x_uncorr, float* x_corr) {
+    const int B = w.B, T = w.T, N = w.N, P = w.P;
     // ---------------- GCE ----------------
-    nchw_to_planes_kernel<<<dim3(HC / 64, N), 256, 0, st>>>(x, WS_BF(w, xp_hi), WS_BF(w, xp_lo), WS_F32(w, gx));
+    nchw_to_planes_kernel<<<dim3(HC / 64, N), 256, 0, st>>>(x, WS_BF(w, xp_hi), WS_BF(w, xp_lo), WS_F32(w, gx), 1.f);
     GRL_LAUNCH_CHECK(h);
     glo_mean_kernel<<<(B * HC + 255) / 256, 256, 0, st>>>(WS_F32(w, gx), WS_F32(w, g), B, T);
     GRL_LAUNCH_CHECK(h);
@@ -632,6 +626,13 @@ extern "C" int grl_head_forward(grl_handle* h, const grl_head_params* p, const f
     if (x_corr) { planes_to_nchw_kernel<<<dim3(HC / 64, N), 256, 0, st>>>(WS_BF(w, xc_hi), WS_BF(w, xc_lo), x_corr); GRL_LAUNCH_CHECK(h); }
     if (x_uncorr) { planes_to_nchw_kernel<<<dim3(HC / 64, N), 256, 0, st>>>(WS_BF(w, xu_hi), WS_BF(w, xu_lo), x_uncorr); GRL_LAUNCH_CHECK(h); }
 
+    return GRL_OK;
+}
+
+// TRL: from the Xc / Xu planes and gc = GAP(x_corr)      (grl_model.py:131-180)
+static int trl_forward_part(grl_handle* h, cudaStream_t st, const grl_head_params* p, const HeadWs& w, int train, float* f_uncorr,
+                            float* f_corr) {
+    const int B = w.B, T = w.T, N = w.N, P = w.P, R = w.R;
     // ---------------- TRL ----------------
     {   // f2 for every frame and both directions at once (F2): [P][4096]
         GemmEpi e = epi_default();
@@ -724,4 +725,58 @@ extern "C" int grl_head_forward(grl_handle* h, const grl_head_params* p, const f
     add2_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(WS_F32(w, out_d), WS_F32(w, out_d) + (size_t)N * HC, f_corr, n4);
     GRL_LAUNCH_CHECK(h);
     return GRL_OK;
+}
+
+static int head_setup(grl_handle* h, const char* who, const grl_head_params* p, int B, int T, int train, void* workspace,
+                      size_t workspace_bytes, int save, int which, HeadWs* w) {
+    if (!h || !p || !workspace) return set_error(h, GRL_EINVAL, "%s: NULL argument", who);
+    if (B <= 0 || T <= 0) return set_error(h, GRL_EINVAL, "%s: need B, T > 0", who);
+    if (train && (which & 1) && B < 2) return set_error(h, GRL_EINVAL, "%s: train-mode BatchNorm1d needs B >= 2 (got %d)", who, B);
+    GRL_TRY(check_params(h, p, which));
+    *w = head_ws_layout(B, T, save ? 1 : 0);
+    if (workspace_bytes < w->total) return set_error(h, GRL_ENOMEM, "%s: workspace %zu < %zu bytes", who, workspace_bytes, w->total);
+    if (reinterpret_cast<uintptr_t>(workspace) & 1023) return set_error(h, GRL_EINVAL, "%s: workspace must be 1024-byte aligned", who);
+    w->base = (uint8_t*)workspace;
+    return GRL_OK;
+}
+
+}  // namespace grl
+
+extern "C" int grl_head_forward(grl_handle* h, const grl_head_params* p, const float* x, int B, int T, int train, float* f_uncorr,
+                                float* f_corr, float* corr_map, float* x_uncorr, float* x_corr, void* workspace,
+                                size_t workspace_bytes, int save_for_backward, void* stream) {
+    if (!x || !f_uncorr || !f_corr) return set_error(h, GRL_EINVAL, "grl_head_forward: NULL argument");
+    HeadWs w;
+    GRL_TRY(head_setup(h, "grl_head_forward", p, B, T, train, workspace, workspace_bytes, save_for_backward, 3, &w));
+    cudaStream_t st = (cudaStream_t)stream;
+    GRL_TRY(head_prepare_weights(h, st, p, w, 3));
+    GRL_TRY(gce_forward_part(h, st, p, w, x, train, corr_map, x_uncorr, x_corr));
+    return trl_forward_part(h, st, p, w, train, f_uncorr, f_corr);
+}
+
+extern "C" int grl_gce_forward(grl_handle* h, const grl_head_params* p, const float* x, int B, int T, int train, float* x_uncorr,
+                               float* x_corr, float* corr_map, void* workspace, size_t workspace_bytes, int save_for_backward,
+                               void* stream) {
+    if (!x || !x_uncorr || !x_corr || !corr_map) return set_error(h, GRL_EINVAL, "grl_gce_forward: NULL argument");
+    HeadWs w;
+    GRL_TRY(head_setup(h, "grl_gce_forward", p, B, T, train, workspace, workspace_bytes, save_for_backward, 1, &w));
+    cudaStream_t st = (cudaStream_t)stream;
+    GRL_TRY(head_prepare_weights(h, st, p, w, 1));
+    return gce_forward_part(h, st, p, w, x, train, corr_map, x_uncorr, x_corr);
+}
+
+extern "C" int grl_trl_forward(grl_handle* h, const grl_head_params* p, const float* x_uncorr, const float* x_corr, int B, int T,
+                               int train, float* f_uncorr, float* f_corr, void* workspace, size_t workspace_bytes,
+                               int save_for_backward, void* stream) {
+    if (!x_uncorr || !x_corr || !f_uncorr || !f_corr) return set_error(h, GRL_EINVAL, "grl_trl_forward: NULL argument");
+    HeadWs w;
+    GRL_TRY(head_setup(h, "grl_trl_forward", p, B, T, train, workspace, workspace_bytes, save_for_backward, 2, &w));
+    cudaStream_t st = (cudaStream_t)stream;
+    GRL_TRY(head_prepare_weights(h, st, p, w, 2));
+    // the caller's maps -> pixel-major planes; gc = GAP(x_corr) per frame rides along
+    nchw_to_planes_kernel<<<dim3(HC / 64, w.N), 256, 0, st>>>(x_corr, WS_BF(w, xc_hi), WS_BF(w, xc_lo), WS_F32(w, gc), 1.f / HS);
+    GRL_LAUNCH_CHECK(h);
+    nchw_to_planes_kernel<<<dim3(HC / 64, w.N), 256, 0, st>>>(x_uncorr, WS_BF(w, xu_hi), WS_BF(w, xu_lo), nullptr, 1.f);
+    GRL_LAUNCH_CHECK(h);
+    return trl_forward_part(h, st, p, w, train, f_uncorr, f_corr);
 }

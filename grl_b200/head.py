@@ -41,6 +41,14 @@ def head_param_names():
     return names
 
 
+def gce_param_names():
+    return [k for k in head_param_names() if k.startswith("backbone.")]
+
+
+def trl_param_names():
+    return [k for k in head_param_names() if k.startswith(TP)]
+
+
 def head_buffer_names():
     bn = ["backbone.glo_fc.1", "backbone.corr_atte.1", "backbone.corr_atte.3", "backbone.corr_atte.6"]
     for direction, _ in _DIRS:
@@ -57,13 +65,23 @@ def _bn(sd, prefix):
     return r
 
 
-def pack_params(sd) -> _lib.HeadParams:
-    """Fill the C parameter block with device pointers of fp32, contiguous CUDA tensors."""
-    for k in head_param_names():
+def pack_params(sd, which=3) -> _lib.HeadParams:
+    """Fill the C parameter block with device pointers of fp32, contiguous CUDA tensors.
+    which: 1 = GCE members only, 2 = TRL members only, 3 = both (the other members stay NULL)."""
+    names = (gce_param_names() if which & 1 else []) + (trl_param_names() if which & 2 else [])
+    for k in names:
         t = sd[k]
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise RuntimeError("grl_b200 head: parameter %s must be a contiguous float32 CUDA tensor" % k)
     p = _lib.HeadParams()
+    if which & 1:
+        _pack_gce_params(p, sd)
+    if which & 2:
+        _pack_trl_params(p, sd)
+    return p
+
+
+def _pack_gce_params(p, sd):
     p.glo_fc_w = sd["backbone.glo_fc.0.weight"].data_ptr()
     p.glo_fc_b = sd["backbone.glo_fc.0.bias"].data_ptr()
     p.glo_bn = _bn(sd, "backbone.glo_fc.1")
@@ -73,6 +91,9 @@ def pack_params(sd) -> _lib.HeadParams:
     p.atte_bn3 = _bn(sd, "backbone.corr_atte.3")
     p.atte5_w = sd["backbone.corr_atte.5.weight"].data_ptr()
     p.atte_bn6 = _bn(sd, "backbone.corr_atte.6")
+
+
+def _pack_trl_params(p, sd):
     for d, (direction, atte) in enumerate(_DIRS):
         m = TP + "uncorr_memo_" + direction
         p.f1_w[d] = sd[TP + direction + "_f1.0.weight"].data_ptr()
@@ -87,11 +108,18 @@ def pack_params(sd) -> _lib.HeadParams:
         p.memo_bn2[d] = _bn(sd, m + ".bn2")
         p.memo_conv3_w[d] = sd[m + ".conv3.weight"].data_ptr()
         p.memo_bn3[d] = _bn(sd, m + ".bn3")
-    return p
 
 
-def pack_grads(gd) -> _lib.HeadGrads:
+def pack_grads(gd, which=3) -> _lib.HeadGrads:
     g = _lib.HeadGrads()
+    if which & 1:
+        _pack_gce_grads(g, gd)
+    if which & 2:
+        _pack_trl_grads(g, gd)
+    return g
+
+
+def _pack_gce_grads(g, gd):
     g.glo_fc_w = gd["backbone.glo_fc.0.weight"].data_ptr()
     g.glo_fc_b = gd["backbone.glo_fc.0.bias"].data_ptr()
     g.glo_bn_w = gd["backbone.glo_fc.1.weight"].data_ptr()
@@ -105,6 +133,9 @@ def pack_grads(gd) -> _lib.HeadGrads:
     g.atte5_w = gd["backbone.corr_atte.5.weight"].data_ptr()
     g.atte_bn6_w = gd["backbone.corr_atte.6.weight"].data_ptr()
     g.atte_bn6_b = gd["backbone.corr_atte.6.bias"].data_ptr()
+
+
+def _pack_trl_grads(g, gd):
     for d, (direction, atte) in enumerate(_DIRS):
         m = TP + "uncorr_memo_" + direction
         g.f1_w[d] = gd[TP + direction + "_f1.0.weight"].data_ptr()
@@ -122,7 +153,6 @@ def pack_grads(gd) -> _lib.HeadGrads:
         g.memo_conv3_w[d] = gd[m + ".conv3.weight"].data_ptr()
         g.memo_bn3_w[d] = gd[m + ".bn3.weight"].data_ptr()
         g.memo_bn3_b[d] = gd[m + ".bn3.bias"].data_ptr()
-    return g
 
 
 def workspace_bytes(B, T, save):
@@ -209,6 +239,148 @@ def head_backward_raw(sd, x, B, T, ws, d_f_uncorr, d_f_corr, d_x_uncorr=None, d_
                                    ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
         _lib.check(h, rc, "grl_head_backward")
     return dx, grads
+
+
+def _check_maps(t, B, T, what):
+    if not t.is_cuda:
+        raise RuntimeError("grl_b200 head needs CUDA tensors (no CPU path exists)")
+    t = t.contiguous().float()
+    if t.numel() != B * T * 2048 * 128 or tuple(t.shape[-3:]) != (2048, 16, 8):
+        raise RuntimeError("%s must be [b*t, 2048, 16, 8], got %s (b=%d, t=%d)" % (what, tuple(t.shape), B, T))
+    return t
+
+
+def gce_forward_raw(sd, x, B, T, training, save, ws=None):
+    """grl_gce_forward: (x_uncorr, x_corr, corr_map, workspace)."""
+    x = _check_maps(x, B, T, "GCE input")
+    lib = _lib.load_library()
+    dev = x.device
+    with torch.cuda.device(dev):
+        h = _lib.get_handle(dev)
+        p = pack_params(sd, 1)
+        nbytes = workspace_bytes(B, T, save)
+        if ws is None or ws.numel() < nbytes:
+            ws = _alloc_ws(nbytes, dev)
+        xu, xc = torch.empty_like(x), torch.empty_like(x)
+        corr_map = torch.empty((B * T, 1, 16, 8), device=dev)
+        rc = lib.grl_gce_forward(h, C.byref(p), x.data_ptr(), B, T, 1 if training else 0, xu.data_ptr(), xc.data_ptr(),
+                                 corr_map.data_ptr(), ws.data_ptr(), ws.numel(), 1 if save else 0, _lib.stream_ptr(dev))
+        _lib.check(h, rc, "grl_gce_forward")
+    return xu, xc, corr_map, ws
+
+
+def gce_backward_raw(sd, B, T, ws, d_x_uncorr, d_x_corr, d_corr_map):
+    """grl_gce_backward: (dx, {GCE param name: grad})."""
+    lib = _lib.load_library()
+    dev = ws.device
+    with torch.cuda.device(dev):
+        h = _lib.get_handle(dev)
+        p = pack_params(sd, 1)
+        grads = {k: torch.empty_like(sd[k]) for k in gce_param_names()}
+        g = pack_grads(grads, 1)
+        dx = torch.empty((B * T, 2048, 16, 8), device=dev)
+        cont = lambda t: None if t is None else t.contiguous().float()
+        d_x_uncorr, d_x_corr, d_corr_map = cont(d_x_uncorr), cont(d_x_corr), cont(d_corr_map)
+        rc = lib.grl_gce_backward(h, C.byref(p), B, T, _lib.ptr(d_x_uncorr), _lib.ptr(d_x_corr), _lib.ptr(d_corr_map),
+                                  dx.data_ptr(), C.byref(g), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(h, rc, "grl_gce_backward")
+    return dx, grads
+
+
+def trl_forward_raw(sd, x_uncorr, x_corr, B, T, training, save, ws=None):
+    """grl_trl_forward: (f_uncorr, f_corr, workspace)."""
+    x_uncorr = _check_maps(x_uncorr, B, T, "x_uncorr")
+    x_corr = _check_maps(x_corr, B, T, "x_corr")
+    lib = _lib.load_library()
+    dev = x_corr.device
+    with torch.cuda.device(dev):
+        h = _lib.get_handle(dev)
+        p = pack_params(sd, 2)
+        nbytes = workspace_bytes(B, T, save)
+        if ws is None or ws.numel() < nbytes:
+            ws = _alloc_ws(nbytes, dev)
+        f_uncorr = torch.empty((B, 2048), device=dev)
+        f_corr = torch.empty((B, T, 2048), device=dev)
+        rc = lib.grl_trl_forward(h, C.byref(p), x_uncorr.data_ptr(), x_corr.data_ptr(), B, T, 1 if training else 0,
+                                 f_uncorr.data_ptr(), f_corr.data_ptr(), ws.data_ptr(), ws.numel(), 1 if save else 0,
+                                 _lib.stream_ptr(dev))
+        _lib.check(h, rc, "grl_trl_forward")
+    return f_uncorr, f_corr, ws
+
+
+def trl_backward_raw(sd, B, T, ws, d_f_uncorr, d_f_corr):
+    """grl_trl_backward: (d_x_uncorr, d_x_corr [b*t,2048,16,8], {TRL param name: grad})."""
+    lib = _lib.load_library()
+    dev = ws.device
+    with torch.cuda.device(dev):
+        h = _lib.get_handle(dev)
+        p = pack_params(sd, 2)
+        grads = {k: torch.empty_like(sd[k]) for k in trl_param_names()}
+        g = pack_grads(grads, 2)
+        dxu = torch.empty((B * T, 2048, 16, 8), device=dev)
+        dxc = torch.empty((B * T, 2048, 16, 8), device=dev)
+        d_f_uncorr, d_f_corr = d_f_uncorr.contiguous().float(), d_f_corr.contiguous().float()
+        rc = lib.grl_trl_backward(h, C.byref(p), B, T, d_f_uncorr.data_ptr(), d_f_corr.data_ptr(), dxu.data_ptr(), dxc.data_ptr(),
+                                  C.byref(g), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(h, rc, "grl_trl_backward")
+    return dxu, dxc, grads
+
+
+class _GceFunction(torch.autograd.Function):
+    """Stand-alone GCE: (x, *gce params) -> (x_uncorr, x_corr, corr_map)."""
+
+    @staticmethod
+    def forward(ctx, x, B, T, training, need_grad, names, sd_buffers, *params):
+        sd = dict(zip(names, params))
+        sd.update(sd_buffers)
+        if need_grad and not training:
+            raise RuntimeError("grl_b200 GCE: backward with eval-mode BatchNorm is not supported")
+        xu, xc, corr_map, ws = gce_forward_raw(sd, x, B, T, training, save=need_grad)
+        ctx.B, ctx.T, ctx.names, ctx.sd_buffers = B, T, names, sd_buffers
+        ctx.ws = ws if need_grad else None
+        ctx.save_for_backward(*params)
+        return xu, xc, corr_map
+
+    @staticmethod
+    def backward(ctx, g_xu, g_xc, g_map):
+        sd = dict(zip(ctx.names, ctx.saved_tensors))
+        sd.update(ctx.sd_buffers)
+        dx, grads = gce_backward_raw(sd, ctx.B, ctx.T, ctx.ws, g_xu, g_xc, g_map)
+        ctx.ws = None
+        return (dx, None, None, None, None, None, None) + tuple(grads[k] for k in ctx.names)
+
+
+class _TrlFunction(torch.autograd.Function):
+    """Stand-alone TRL: (x_uncorr, x_corr, *trl params) -> (f_uncorr, f_corr)."""
+
+    @staticmethod
+    def forward(ctx, x_uncorr, x_corr, B, T, training, need_grad, names, sd_buffers, *params):
+        sd = dict(zip(names, params))
+        sd.update(sd_buffers)
+        if need_grad and not training:
+            raise RuntimeError("grl_b200 TRL: backward with eval-mode BatchNorm is not supported")
+        f_uncorr, f_corr, ws = trl_forward_raw(sd, x_uncorr, x_corr, B, T, training, save=need_grad)
+        ctx.B, ctx.T, ctx.names, ctx.sd_buffers, ctx.shape = B, T, names, sd_buffers, x_corr.shape
+        ctx.ws = ws if need_grad else None
+        ctx.save_for_backward(*params)
+        return f_uncorr, f_corr
+
+    @staticmethod
+    def backward(ctx, g_fu, g_fc):
+        sd = dict(zip(ctx.names, ctx.saved_tensors))
+        sd.update(ctx.sd_buffers)
+        dev = ctx.ws.device
+        g_fu = torch.zeros((ctx.B, 2048), device=dev) if g_fu is None else g_fu
+        g_fc = torch.zeros((ctx.B, ctx.T, 2048), device=dev) if g_fc is None else g_fc
+        dxu, dxc, grads = trl_backward_raw(sd, ctx.B, ctx.T, ctx.ws, g_fu, g_fc)
+        ctx.ws = None
+        return (dxu.view(ctx.shape), dxc.view(ctx.shape), None, None, None, None, None, None) + tuple(grads[k] for k in ctx.names)
+
+
+def _bump_bn(buffers, prefixes, steps_of):
+    with torch.no_grad():
+        for prefix in prefixes:
+            buffers[prefix + ".num_batches_tracked"] += steps_of(prefix)
 
 
 class _HeadFunction(torch.autograd.Function):
@@ -317,10 +489,22 @@ class Backbone(nn.Module):
             nn.Conv2d(256, 1, 1, 1, bias=False), nn.BatchNorm2d(1))
         self._trl_for_fused = None      # set by ResNet50_GRL_Model (not a submodule: no state_dict change)
 
+    def gce(self, x, b, t):
+        """GCE on layer4 maps x [b*t, 2048, 16, 8] (grl_gce_forward / grl_gce_backward)."""
+        params = {"backbone." + n: p for n, p in self.named_parameters() if not n.startswith("base.")}
+        buffers = {"backbone." + n: p for n, p in self.named_buffers() if not n.startswith("base.")}
+        names = gce_param_names()
+        plist = [params[k] for k in names]
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in plist))
+        out = _GceFunction.apply(x, b, t, self.training, need_grad, names, buffers, *plist)
+        if self.training:
+            _bump_bn(buffers, [k for k in head_buffer_names() if k.startswith("backbone.")], lambda _: 1)
+        return out
+
     def forward(self, x, b, t):
-        """Stand-alone call (returns the gated maps like the reference)."""
-        raise RuntimeError("Backbone.forward stand-alone needs a TRLBlock partner in this build; use "
-                           "ResNet50_GRL_Model (fused head) or grl_b200.head.run_head(..., want_maps=True)")
+        """reid/models/basebranch.py:52-68: returns (x_uncorr, x_corr, corr_map)."""
+        x = self.base(x)
+        return self.gce(x, b, t)
 
 
 class BasicBlock(nn.Module):
@@ -354,6 +538,19 @@ class TRLBlock(nn.Module):
         self.backward_f2 = nn.Sequential(nn.Conv2d(2048, 2048, 1, 1), nn.ReLU())
         self.channel_atte_backward_corr = nn.Sequential(nn.Linear(2048, 2048 // 16, bias=False), nn.ReLU(inplace=True),
                                                         nn.Linear(2048 // 16, 2048, bias=False), nn.Sigmoid())
+
+    def forward(self, x_uncorr, x_corr):
+        """reid/models/grl_model.py:131-180: x_* [b, t, 2048, 16, 8] -> (f_uncorr [b,2048], f_corr [b,t,2048])."""
+        b, t = x_corr.size(0), x_corr.size(1)
+        params = {TP + n: p for n, p in self.named_parameters()}
+        buffers = {TP + n: p for n, p in self.named_buffers()}
+        names = trl_param_names()
+        plist = [params[k] for k in names]
+        need_grad = torch.is_grad_enabled() and (x_uncorr.requires_grad or x_corr.requires_grad or any(p.requires_grad for p in plist))
+        out = _TrlFunction.apply(x_uncorr, x_corr, b, t, self.training, need_grad, names, buffers, *plist)
+        if self.training:
+            _bump_bn(buffers, [k for k in head_buffer_names() if k.startswith(TP)], lambda _: t)
+        return out
 
 
 class ResNet50_GRL_Model(nn.Module):

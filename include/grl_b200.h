@@ -193,6 +193,24 @@ int grl_head_backward(grl_handle* h, const grl_head_params* p, const float* x, i
                       float* dx, const grl_head_grads* grads,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* The two halves as stand-alone operators (the reference's modules can be called separately):
+ *   grl_gce_forward  = Backbone.forward after self.base (basebranch.py:56-68): x -> x_uncorr, x_corr, corr_map (all written)
+ *   grl_trl_forward  = TRLBlock.forward (grl_model.py:131-180): x_uncorr, x_corr [B*T][2048][16][8] -> f_uncorr, f_corr
+ * and their backwards (same workspace contract as the fused pair; grads: only the GCE resp. TRL members are read
+ * and written).  d_x_uncorr / d_x_corr / d_corr_map of grl_gce_backward may be NULL (= zero).                      */
+int grl_gce_forward(grl_handle* h, const grl_head_params* p, const float* x, int B, int T, int train,
+                    float* x_uncorr, float* x_corr, float* corr_map,
+                    void* workspace, size_t workspace_bytes, int save_for_backward, void* stream);
+int grl_gce_backward(grl_handle* h, const grl_head_params* p, int B, int T,
+                     const float* d_x_uncorr, const float* d_x_corr, const float* d_corr_map,
+                     float* dx, const grl_head_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
+int grl_trl_forward(grl_handle* h, const grl_head_params* p, const float* x_uncorr, const float* x_corr, int B, int T,
+                    int train, float* f_uncorr, float* f_corr,
+                    void* workspace, size_t workspace_bytes, int save_for_backward, void* stream);
+int grl_trl_backward(grl_handle* h, const grl_head_params* p, int B, int T, const float* d_f_uncorr, const float* d_f_corr,
+                     float* d_x_uncorr, float* d_x_corr, const grl_head_grads* grads,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* Debug/test: byte offset and size of a named intermediate inside the head workspace
  * (e.g. "xp_hi", "y1", "m", "f2", "memo_h1").  Returns GRL_EINVAL for unknown names.         */
 int grl_head_ws_lookup(int B, int T, int save_for_backward, const char* name, size_t* offset, size_t* bytes);

@@ -222,3 +222,120 @@ def test_full_size_properties_b32_t8():
         full = head.head_forward_raw(sd, x, B, T, False, save=False)[1]
         part = head.head_forward_raw(sd, x[8 * T:16 * T], 8, T, False, save=False)[1]
     assert rel(part, full[8:16]) < 1e-5
+
+
+def test_config1_b2_t8_forward_vs_oracle():
+    """BASELINE configs[0]: head forward, B=2, T=8, train-mode BN (the reference's CPU-runnable case)."""
+    _, head, ho = _mods()
+    B, T = 2, 8
+    sd = device_params()
+    x = synth.make_head_input(B, T).cuda()
+    fu, fc, cm, _, _, _ = head.head_forward_raw(sd, x, B, T, True, save=False)
+    p64 = synth.make_head_params(0, dtype=torch.float64)
+    o = ho.ref_forward(p64, synth.make_head_input(B, T, dtype=torch.float64), B, T, True)
+    for k, v in (("f_uncorr", fu), ("f_corr", fc), ("corr_map", cm)):
+        assert rel(v, o[k]) < 1e-4, (k, rel(v, o[k]))
+    for k in p64:
+        if "running" in k:
+            assert rel(sd[k], p64[k]) < 2e-5, k
+
+
+def test_config4_long_tracklet_t16_dense_eval():
+    """BASELINE configs[3]: T=16, eval-mode BN, clips of one tracklet fed in chunks of 8 and averaged
+    (attevaluator.py:72-95).  Forward vs the fp64 oracle, and chunk invariance of the aggregation."""
+    _, head, ho = _mods()
+    T, n_clips = 16, 11
+    sd = device_params()
+    x = synth.make_head_input(n_clips, T, seed=9).cuda()
+    feats = []
+    with torch.no_grad():
+        for y in range(0, n_clips, 8):                         # chunks of 8 clips like the reference
+            nb = min(8, n_clips - y)
+            fu, fc, *_ = head.head_forward_raw(sd, x[y * T:(y + nb) * T], nb, T, False, save=False)
+            feats.append(torch.cat((fu, fc.mean(dim=1)), dim=1))
+        dense = torch.cat(feats, 0).mean(dim=0)
+        fu_all, fc_all, *_ = head.head_forward_raw(sd, x, n_clips, T, False, save=False)
+        whole = torch.cat((fu_all, fc_all.mean(dim=1)), dim=1).mean(dim=0)
+    assert rel(dense, whole) < 1e-5                            # eval-mode BN: clips independent, chunking is free
+    p64 = synth.make_head_params(0, dtype=torch.float64)
+    o = ho.ref_forward(p64, synth.make_head_input(3, T, seed=9, dtype=torch.float64)[: 3 * T], 3, T, False)
+    x3 = synth.make_head_input(3, T, seed=9).cuda()
+    fu3, fc3, cm3, _, _, _ = head.head_forward_raw(sd, x3, 3, T, False, save=False)
+    for k, v in (("f_uncorr", fu3), ("f_corr", fc3), ("corr_map", cm3)):
+        assert rel(v, o[k]) < 1e-4, (k, rel(v, o[k]))
+
+
+def test_standalone_backbone_and_trl_modules_match_fused_head():
+    """Backbone.forward (GCE) and TRLBlock.forward called separately, with autograd between them, reproduce the
+    fused head: same outputs, same dx, same parameter gradients (SURVEY.md section 8 rows a1 + a2 on their own)."""
+    _, head, ho = _mods()
+    B, T = 4, 3
+    gu, gc = synth.make_head_grads(B, T)
+
+    def build():
+        m = head.ResNet50_GRL_Model(base=torch.nn.Identity()).cuda()
+        sd = m.state_dict()
+        for k, v in synth.make_head_params(0).items():
+            sd[k] = v
+        m.load_state_dict(sd)
+        return m.train()
+
+    fused, split = build(), build()
+    x1 = synth.make_head_input(B, T).cuda().requires_grad_(True)
+    f_uncorr, f_corr, corr_map, _, _ = fused.head(x1, B, T)
+    torch.autograd.backward([f_uncorr, f_corr], [gu.cuda(), gc.cuda()])
+
+    x2 = synth.make_head_input(B, T).cuda().requires_grad_(True)
+    x_uncorr, x_corr, cmap2 = split.backbone(x2, B, T)                   # reference signature: (x, b, t)
+    assert x_uncorr.shape == (B * T, 2048, 16, 8) and cmap2.shape == (B * T, 1, 16, 8)
+    fu2, fc2 = split.temporal_learning_block(x_uncorr.view(B, T, 2048, 16, 8), x_corr.view(B, T, 2048, 16, 8))
+    torch.autograd.backward([fu2, fc2], [gu.cuda(), gc.cuda()])
+    assert rel(cmap2, corr_map) < 1e-6 and rel(fu2, f_uncorr) < 1e-5 and rel(fc2, f_corr) < 1e-5
+    assert rel(x_uncorr + x_corr, x2) < 1e-5                             # x*(1-m) + x*m
+    assert rel(x2.grad, x1.grad) < 1e-4
+    pf, ps = dict(fused.named_parameters()), dict(split.named_parameters())
+    for k in head.head_param_names():
+        if k in ZERO_GRADS:
+            continue
+        assert rel(ps[k].grad, pf[k].grad) < 1e-4, (k, rel(ps[k].grad, pf[k].grad))
+    sf, ss = fused.state_dict(), split.state_dict()
+    for k in sf:
+        if "running" in k or "num_batches" in k:
+            assert rel(ss[k], sf[k]) < 1e-6, k
+    # a gradient flowing only into corr_map (stand-alone GCE use)
+    x3 = synth.make_head_input(B, T).cuda().requires_grad_(True)
+    _, _, cm3 = split.backbone(x3, B, T)
+    cm3.sum().backward()
+    assert torch.isfinite(x3.grad).all() and float(x3.grad.abs().sum()) > 0
+
+
+def test_fused_head_with_map_outputs_backward_vs_fp64_reference():
+    """want_maps=True: gradients arriving on the stand-alone x_uncorr / x_corr / corr_map outputs as well as on
+    f_uncorr / f_corr (grl_head_backward's optional d_x_uncorr / d_x_corr / d_corr_map) vs autograd of the fp64 oracle."""
+    _, head, ho = _mods()
+    B, T = 4, 2
+    gu, gc = synth.make_head_grads(B, T)
+    rng = np.random.default_rng(4)
+    r_u = torch.from_numpy(rng.standard_normal((B * T, 2048, 16, 8)).astype(np.float32)) * 1e-2
+    r_c = torch.from_numpy(rng.standard_normal((B * T, 2048, 16, 8)).astype(np.float32)) * 1e-2
+    r_m = torch.from_numpy(rng.standard_normal((B * T, 1, 16, 8)).astype(np.float32))
+    model = head.ResNet50_GRL_Model(base=torch.nn.Identity()).cuda()
+    sd = model.state_dict()
+    for k, v in synth.make_head_params(0).items():
+        sd[k] = v
+    model.load_state_dict(sd)
+    model.train()
+    x = synth.make_head_input(B, T).cuda().requires_grad_(True)
+    fu, fc, cm, xu, xc = model.head(x, B, T, want_maps=True)
+    loss = (fu * gu.cuda()).sum() + (fc * gc.cuda()).sum() + (xu * r_u.cuda()).sum() + (xc * r_c.cuda()).sum() + (cm * r_m.cuda()).sum()
+    loss.backward()
+    p64 = {k: (v.double().requires_grad_("running" not in k) if v.is_floating_point() else v.clone())
+           for k, v in synth.make_head_params(0).items()}
+    x64 = synth.make_head_input(B, T, dtype=torch.float64).requires_grad_(True)
+    o = ho.ref_forward(p64, x64, B, T, True)
+    (((o["f_uncorr"] * gu.double()).sum() + (o["f_corr"] * gc.double()).sum() + (o["x_uncorr"] * r_u.double()).sum()
+      + (o["x_corr"] * r_c.double()).sum() + (o["corr_map"] * r_m.double()).sum())).backward()
+    assert rel(x.grad, x64.grad) < KINK_TOL, rel(x.grad, x64.grad)
+    named = dict(model.named_parameters())
+    for k in ("backbone.corr_atte.0.weight", "backbone.corr_atte.2.weight", "temporal_learning_block.forward_f1.0.weight"):
+        assert rel(named[k].grad, p64[k].grad.reshape(named[k].shape)) < KINK_TOL, k
