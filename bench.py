@@ -271,33 +271,54 @@ def run_ours(args):
         msd[k_] = v_
     model.load_state_dict(msd)
     model.train()
-    x_dev = torch.empty_like(x)
     out_host = [torch.empty((B, 2048)).pin_memory(), torch.empty((B, T, 2048)).pin_memory()]
     del ws
     ws = None
     torch.cuda.empty_cache()
+    # Every step's maps are copied host -> device; the copy of step s+1 streams in on a side stream while step s computes
+    # (two device buffers, events both ways), the way a training loop would feed the head.
+    copy_stream = torch.cuda.Stream(dev)
+    xbuf = [torch.empty_like(x), torch.empty_like(x)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    free = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step():
-        x_dev.copy_(x_host, non_blocking=True)
-        xin = x_dev.requires_grad_(True)
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[i])
+            xbuf[i].copy_(x_host, non_blocking=True)
+            ready[i].record(copy_stream)
+
+    def e2e_step(i, more):
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ready[i])
+        if more:
+            prefetch(1 - i)
+        xin = xbuf[i].requires_grad_(True)
         f_uncorr, f_corr, _, _, _ = model.head(xin, B, T)
         torch.autograd.backward([f_uncorr, f_corr], [gu, gc])
         out_host[0].copy_(f_uncorr.detach(), non_blocking=True)
         out_host[1].copy_(f_corr.detach(), non_blocking=True)
-        chk = xin.grad.sum().item()                   # d loss / d layer4 maps stays on the device for the backbone; read a checksum
+        chk = xin.grad.sum()                          # d loss / d layer4 maps stays on the device for the backbone; read a checksum
+        free[i].record(cur)
+        chk = chk.item()
         xin.grad = None
-        x_dev.requires_grad_(False)
+        xbuf[i].requires_grad_(False)
         for p_ in model.parameters():
             p_.grad = None
         return chk
 
-    for _ in range(2):
-        e2e_step()
+    def e2e_run(n):
+        for i_ in (0, 1):
+            free[i_].record(torch.cuda.current_stream(dev))
+        prefetch(0)
+        for s_ in range(n):
+            e2e_step(s_ % 2, s_ + 1 < n)
+
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
     KE = max(2, K // 2)
-    for _ in range(KE):
-        e2e_step()
+    e2e_run(KE)
     barrier()
     dt = time.perf_counter() - t0
     if world > 1:
@@ -306,7 +327,8 @@ def run_ours(args):
         dt = float(t.item())
     e2e = {"value": world * B * KE / dt, "unit": "clips/s", "h2d_bytes_per_step": x_host.numel() * 4,
            "d2h_bytes_per_step": (B * 2048 + B * T * 2048) * 4 + 4, "steps": KE,
-           "api": "ResNet50_GRL_Model.head(x, b, t) + torch.autograd.backward (ctypes -> libgrl_b200.so)"}
+           "api": "ResNet50_GRL_Model.head(x, b, t) + torch.autograd.backward (ctypes -> libgrl_b200.so); the H2D copy of step "
+                  "s+1 overlaps step s on a side stream; outputs and a dx checksum are read back every step"}
 
     # ---- MARS-shape evaluation (configs[2]) through the evaluator API, host features in, CMC/mAP out
     eval_line = None

@@ -913,12 +913,12 @@ static int gce_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
     GRL_LAUNCH_CHECK(h);
     GRL_TRY(outer(h, st, WS_F32(w, dbias1), 0, HG, WS_F32(w, glo), 0, HG, 1, B, g->atte0_w + HC, HC + HG, HG, HG));      // d W1[:, 2048:]
     float* dglo = WS_F32(w, part_c);      // [B][HG] scratch (the partial buffers are idle here)
-    GRL_TRY(small_matmul(h, st, WS_F32(w, dbias1), HG, p->atte0_w + HC, HC + HG, 1, nullptr, dglo, HG, B, HG, HG));
+    GRL_TRY(small_gemm(h, st, w, WS_F32(w, dbias1), B, HG, WS_BF(w, w1b_hi), WS_BF(w, w1b_lo), HG, 1, nullptr, dglo, HG));
     gce_bwd_glo_bn_kernel<<<(HG + 127) / 128, 128, 0, st>>>(dglo, WS_F32(w, glo), WS_F32(w, u), WS_F32(w, glo_stat), p->glo_bn.weight, B,
                                                             WS_F32(w, du), g->glo_bn_w, g->glo_bn_b, g->glo_fc_b);
     GRL_LAUNCH_CHECK(h);
     GRL_TRY(outer(h, st, WS_F32(w, du), 0, HG, WS_F32(w, g), 0, HC, 1, B, g->glo_fc_w, HC, HG, HC));
-    GRL_TRY(small_matmul(h, st, WS_F32(w, du), HG, p->glo_fc_w, HC, 1, nullptr, WS_F32(w, dg), HC, B, HG, HC));
+    GRL_TRY(small_gemm(h, st, w, WS_F32(w, du), B, HG, WS_BF(w, wg_hi), WS_BF(w, wg_lo), HC, 1, nullptr, WS_F32(w, dg), HC));
     pm_to_nchw_bias_kernel<<<dim3(HC / 64, N), 256, 0, st>>>(WS_F32(w, dxc), WS_F32(w, dg), T, 1.f / (float)(T * HS), dx);
     GRL_LAUNCH_CHECK(h);
     return GRL_OK;

@@ -38,6 +38,8 @@ constexpr float BN_MOM = 0.1f;
     X(wf2_hi, 2, (size_t)2 * HC * HC) X(wf2_lo, 2, (size_t)2 * HC * HC) X(wf1_hi, 2, (size_t)2 * HC * HC) X(wf1_lo, 2, (size_t)2 * HC * HC) \
     X(wc1_hi, 2, (size_t)2 * HB * HC) X(wc1_lo, 2, (size_t)2 * HB * HC) X(wc2_hi, 2, (size_t)2 * HB * HB) X(wc2_lo, 2, (size_t)2 * HB * HB) \
     X(wc3_hi, 2, (size_t)2 * HC * HB) X(wc3_lo, 2, (size_t)2 * HC * HB) X(bf2cat, 4, (size_t)2 * HC) X(bf1cat, 4, (size_t)2 * HC) \
+    X(wg_hi, 2, (size_t)HG * HC) X(wg_lo, 2, (size_t)HG * HC) X(w1b_hi, 2, (size_t)HG * HG) X(w1b_lo, 2, (size_t)HG * HG) \
+    X(sa_hi, 2, (size_t)B * HC) X(sa_lo, 2, (size_t)B * HC)                                       \
     /* --- TRL per-step state (SL = T slots when saving for backward, else 1/2) --- */            \
     X(mem_hi, 2, (size_t)SLM * 2 * R * HC) X(mem_lo, 2, (size_t)SLM * 2 * R * HC)                 \
     X(z_hi, 2, (size_t)SLZ * 2 * R * HC) X(z_lo, 2, (size_t)SLZ * 2 * R * HC)                     \
@@ -101,9 +103,10 @@ inline HeadWs head_ws_layout(int B, int T, int save) {
 #define WS_F32(w, name) ((w).ptr<float>((w).off_##name))
 #define WS_BF(w, name) ((w).ptr<__nv_bfloat16>((w).off_##name))
 
-// host launcher of the small row-vector x matrix kernel (head_fwd.cu), shared with the backward
-int small_matmul(grl_handle* h, cudaStream_t st, const float* in, long long ldi, const float* W, long long w_js, long long w_ks,
-                 const float* bias, float* out, long long ldo, int rows, int J, int K);
+// out[rows][N] = in[rows][K] . W (+ bias) for the B-row global-descriptor branch, on the tcgen05 GEMM (rows << 128: the TMA
+// box zero-fills the missing rows).  w_mn = 0: W planes stored [N][K] (nn.Linear forward); 1: stored [K][N] (its input gradient).
+int small_gemm(grl_handle* h, cudaStream_t st, const HeadWs& w, const float* in, int rows, int K, const __nv_bfloat16* w_hi,
+               const __nv_bfloat16* w_lo, long long ldw, int w_mn, const float* bias, float* out, int N);
 
 // ------------------------------------------------------------------ device helpers
 // Standard elementwise tile: 256 threads cover 128 rows x 64 channels; thread -> channel group
