@@ -64,6 +64,7 @@ _SIGNATURES = {
     "grl_version": (C.c_char_p, []),
     "grl_num_sms": (C.c_int, [C.c_void_p]),
     "grl_launch_count": (C.c_longlong, [C.c_void_p]),
+    "grl_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
     "grl_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "grl_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "grl_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(GemmDesc)]),

@@ -25,6 +25,9 @@ struct grl_handle {
     grl_encode_tiled_fn encode;
     int prof_on;
     grl_prof* prof;
+    cudaStream_t side;          // low-priority internal stream: work that is off the recurrence's critical path
+    cudaEvent_t* events;        // pool of timing-disabled events for fork/join between the caller's stream and `side`
+    int n_events, overlap;
     char err[512];
 };
 
@@ -74,6 +77,14 @@ int split_planes(grl_handle* h, cudaStream_t st, const float* src, long long ld_
 // fp32 [rows][cols] -> transposed planes [cols][rows] (ld_dst = leading dim of the transposed planes)
 int split_planes_transposed(grl_handle* h, cudaStream_t st, const float* src, long long ld_src, __nv_bfloat16* hi,
                             __nv_bfloat16* lo, long long ld_dst, int rows, int cols);
+
+// Event k of the handle's pool (grown on demand).  Events are only ever recorded/waited by the thread driving the handle.
+cudaEvent_t pool_event(grl_handle* h, int k);
+// `waiter` waits until everything enqueued on `signaler` so far has finished (uses pool event k).
+int stream_wait(grl_handle* h, cudaStream_t signaler, cudaStream_t waiter, int k);
+// record pool event k on `s` / make `s` wait for pool event k
+int ev_record(grl_handle* h, int k, cudaStream_t s);
+int ev_wait(grl_handle* h, int k, cudaStream_t s);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline GemmEpi epi_default() {

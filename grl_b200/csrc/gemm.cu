@@ -18,6 +18,35 @@ int set_error(grl_handle* h, int code, const char* fmt, ...) {
     return code;
 }
 
+// ------------------------------------------------------------------ fork / join helpers
+cudaEvent_t pool_event(grl_handle* h, int k) {
+    if (k >= h->n_events) {
+        int n = h->n_events ? h->n_events : 64;
+        while (n <= k) n *= 2;
+        cudaEvent_t* ev = new cudaEvent_t[n];
+        for (int i = 0; i < n; ++i) {
+            if (i < h->n_events) ev[i] = h->events[i];
+            else cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+        }
+        delete[] h->events;
+        h->events = ev;
+        h->n_events = n;
+    }
+    return h->events[k];
+}
+int ev_record(grl_handle* h, int k, cudaStream_t s) {
+    GRL_CUDA(h, cudaEventRecord(pool_event(h, k), s));
+    return GRL_OK;
+}
+int ev_wait(grl_handle* h, int k, cudaStream_t s) {
+    GRL_CUDA(h, cudaStreamWaitEvent(s, pool_event(h, k), 0));
+    return GRL_OK;
+}
+int stream_wait(grl_handle* h, cudaStream_t signaler, cudaStream_t waiter, int k) {
+    GRL_TRY(ev_record(h, k, signaler));
+    return ev_wait(h, k, waiter);
+}
+
 // ------------------------------------------------------------------ split kernels
 __global__ void split_planes_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ hi,
                                     __nv_bfloat16* __restrict__ lo, long long ld_dst, long long rows, int cols) {
@@ -194,6 +223,14 @@ extern "C" int grl_create(int device, grl_handle** out) {
     }
     h->encode = reinterpret_cast<grl_encode_tiled_fn>(fn);
     h->prof = new grl_prof();
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // numerically: lo >= hi; `lo` is the least urgent
+    e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_lo);
+    if (e != cudaSuccess) {
+        delete h->prof; delete h;
+        return set_error(nullptr, GRL_ECUDA, "cudaStreamCreateWithPriority: %s", cudaGetErrorString(e));
+    }
+    h->overlap = 1;
     *out = h;
     return GRL_OK;
 }
@@ -204,7 +241,16 @@ extern "C" void grl_destroy(grl_handle* h) {
         for (auto& r : h->prof->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
         delete h->prof;
     }
+    for (int i = 0; i < h->n_events; ++i) cudaEventDestroy(h->events[i]);
+    delete[] h->events;
+    if (h->side) cudaStreamDestroy(h->side);
     delete h;
+}
+
+extern "C" int grl_set_overlap(grl_handle* h, int on) {
+    if (!h) return GRL_EINVAL;
+    h->overlap = on ? 1 : 0;
+    return GRL_OK;
 }
 
 extern "C" int grl_profile_enable(grl_handle* h, int on) {

@@ -710,7 +710,19 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
     const int B = w.B, T = w.T, N = w.N, P = w.P, R = w.R;
     const size_t slotM = (size_t)2 * R * HC, slotB = (size_t)2 * R * HB;
     float* dz_all = WS_F32(w, dxu);                 // dZ[T][2][R][HC]
-    float* dmem = WS_F32(w, dmem);
+    float* dmem_all = WS_F32(w, dmem);              // [T+1][2][R][HC]: slot i = dF1_i Wf1, slot T = d f_uncorr / S broadcast
+    // Two streams.  The caller's stream `st` carries only the recurrence's critical path: per step BN3' -> conv3 dgrad -> BN2' ->
+    // conv2 dgrad -> BN1' -> conv1 dgrad (HBM-bound BN passes + three small GEMMs).  Everything else -- the f1 / f2
+    // reciprocal-attention path (its gradients depend on saved activations only) and every weight gradient -- runs on the
+    // low-priority side stream `sd` and fills the tensor pipe while the chain's elementwise kernels stream through HBM.
+    //   EV_DMEM(i): dF1_i Wf1 ready (side -> main);  EV_DH3/2/1(i): dH planes of step i ready (main -> side, for the wgrads)
+    cudaStream_t sd = h->overlap ? h->side : st;
+    const bool two = sd != st;
+    auto EV_DMEM = [&](int i) { return 8 + i; };
+    auto EV_DH3 = [&](int i) { return 8 + (T + 1) + i; };
+    auto EV_DH2 = [&](int i) { return 8 + 2 * (T + 1) + i; };
+    auto EV_DH1 = [&](int i) { return 8 + 3 * (T + 1) + i; };
+
     // ---------------- squeeze-excite backward for every step (independent of the recurrence) ----------------
     {
         SePtrsB sp; sp.l1[0] = p->se1_w[0]; sp.l1[1] = p->se1_w[1]; sp.l2[0] = p->se2_w[0]; sp.l2[1] = p->se2_w[1];
@@ -719,25 +731,54 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
         GRL_LAUNCH_CHECK(h);
         dgc_kernel<<<(unsigned)(((size_t)N * HC + 255) / 256), 256, 0, st>>>(d_f_corr, WS_F32(w, se_a), B, T, WS_F32(w, dgc));
         GRL_LAUNCH_CHECK(h);
-        for (int d = 0; d < 2; ++d) {
-            // d L2[c][j] = sum_{i,b} ds[c] h[j];   d L1[j][c] = sum_{i,b} dh[j] q[c]
-            GRL_TRY(outer(h, st, WS_F32(w, se_ds) + (size_t)d * B * HC, (long long)2 * B * HC, HC, WS_F32(w, se_h) + (size_t)d * B * HSE,
-                          (long long)2 * B * HSE, HSE, T, B, g->se2_w[d], HSE, HC, HSE));
-            GRL_TRY(outer(h, st, WS_F32(w, se_dh) + (size_t)d * B * HSE, (long long)2 * B * HSE, HSE, WS_F32(w, se_q) + (size_t)d * B * HC,
-                          (long long)2 * B * HC, HC, T, B, g->se1_w[d], HC, HSE, HC));
-        }
+    }
+    if (two) GRL_TRY(stream_wait(h, st, sd, 0));
+    for (int d = 0; d < 2; ++d) {
+        // d L2[c][j] = sum_{i,b} ds[c] h[j];   d L1[j][c] = sum_{i,b} dh[j] q[c]
+        GRL_TRY(outer(h, sd, WS_F32(w, se_ds) + (size_t)d * B * HC, (long long)2 * B * HC, HC, WS_F32(w, se_h) + (size_t)d * B * HSE,
+                      (long long)2 * B * HSE, HSE, T, B, g->se2_w[d], HSE, HC, HSE));
+        GRL_TRY(outer(h, sd, WS_F32(w, se_dh) + (size_t)d * B * HSE, (long long)2 * B * HSE, HSE, WS_F32(w, se_q) + (size_t)d * B * HC,
+                      (long long)2 * B * HC, HC, T, B, g->se1_w[d], HC, HSE, HC));
     }
 
+    // reciprocal-attention path of step i: dF1 (planes), dF2[tau] (planes), bias partials, f1 wgrad, f1 dgrad -> dmem[i]
+    auto f1_path = [&](int i) -> int {
+        const int acc = (i == T - 1) ? 0 : 1;
+        const int tau0 = i, tau1 = T - 1 - i;
+        const __nv_bfloat16 *mem_hi = WS_BF(w, mem_hi) + (size_t)i * slotM, *mem_lo = WS_BF(w, mem_lo) + (size_t)i * slotM;
+        trl_bwd_f1_kernel<<<dim3(HC / 64, B, 2), 256, 0, sd>>>(WS_F32(w, f1) + (size_t)i * slotM, WS_F32(w, f2),
+                                                               WS_F32(w, se_dq) + (size_t)i * 2 * B * HC, B, T, R, tau0, tau1, WS_BF(w, df1_hi),
+                                                               WS_BF(w, df1_lo), WS_BF(w, df2_hi), WS_BF(w, df2_lo),
+                                                               WS_F32(w, dbf1_part) + (size_t)i * 2 * B * HC,
+                                                               WS_F32(w, dbf2_part) + (size_t)i * 2 * B * HC);
+        GRL_LAUNCH_CHECK(h);
+        {   // f1 wgrad: gw_f1[z] (+)= dF1^T M
+            GemmEpi e = epi_default();
+            e.C = WS_F32(w, gw_f1); e.ldc = HC; e.c_bstride = (long long)HC * HC; e.accumulate = acc;
+            Operand a{WS_BF(w, df1_hi), WS_BF(w, df1_lo), HC, (long long)R * HC, 1}, b{mem_hi, mem_lo, HC, (long long)R * HC, 1};
+            GRL_TRY(gemm_launch(h, sd, HC, HC, R, 2, a, b, e, 0));
+        }
+        {   // f1 dgrad: dmem[i] = dF1 Wf1   (the other half of dM for step i-1 is dZ of step i)
+            GemmEpi e = epi_default();
+            e.C = dmem_all + (size_t)i * slotM; e.ldc = HC; e.c_bstride = (long long)R * HC;
+            Operand a{WS_BF(w, df1_hi), WS_BF(w, df1_lo), HC, (long long)R * HC, 0}, b{WS_BF(w, wf1_hi), WS_BF(w, wf1_lo), HC, (long long)HC * HC, 1};
+            GRL_TRY(gemm_launch(h, sd, R, HC, HC, 2, a, b, e, 0));
+        }
+        if (two) GRL_TRY(ev_record(h, EV_DMEM(i), sd));
+        return GRL_OK;
+    };
+
     // ---------------- BPTT over the memory updates ----------------
-    bcast_rows_kernel<<<dim3(HC / 64, B, 2), 256, 0, st>>>(d_f_uncorr, 1.f / HS, R, dmem);     // d f_uncorr = mean_s(M_fwd) + mean_s(M_bwd)
+    bcast_rows_kernel<<<dim3(HC / 64, B, 2), 256, 0, st>>>(d_f_uncorr, 1.f / HS, R, dmem_all + (size_t)T * slotM);   // d f_uncorr = mean_s(M_fwd) + mean_s(M_bwd)
     GRL_LAUNCH_CHECK(h);
+    GRL_TRY(f1_path(T - 1));
     for (int i = T - 1; i >= 0; --i) {
         const int first = (i == T - 1) ? 1 : 0;
         const int acc = first ? 0 : 1;
-        const int tau0 = i, tau1 = T - 1 - i;
+        if (i >= 1) GRL_TRY(f1_path(i - 1));        // side stream runs one step ahead of the chain
         float* dz = dz_all + (size_t)i * slotM;
         const float* dz_prev = first ? nullptr : dz_all + (size_t)(i + 1) * slotM;
-        const __nv_bfloat16 *mem_hi = WS_BF(w, mem_hi) + (size_t)i * slotM, *mem_lo = WS_BF(w, mem_lo) + (size_t)i * slotM;
+        const float* dmem_in = dmem_all + (size_t)(i + 1) * slotM;
         const __nv_bfloat16* memn_hi = WS_BF(w, mem_hi) + (size_t)(i + 1) * slotM;
         const __nv_bfloat16 *z_hi = WS_BF(w, z_hi) + (size_t)i * slotM, *z_lo = WS_BF(w, z_lo) + (size_t)i * slotM;
         const float* h1 = WS_F32(w, h1) + (size_t)i * slotB;
@@ -748,95 +789,90 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
         const float* s1 = WS_F32(w, sbn1) + (size_t)i * 2 * 4 * HB;
         const float* s2 = WS_F32(w, sbn2) + (size_t)i * 2 * 4 * HB;
         const float* s3 = WS_F32(w, sbn3) + (size_t)i * 2 * 4 * HC;
+        __nv_bfloat16 *dh3_hi = WS_BF(w, dh3_hi) + (size_t)i * slotM, *dh3_lo = WS_BF(w, dh3_lo) + (size_t)i * slotM;
+        __nv_bfloat16 *dh2_hi = WS_BF(w, dh2_hi) + (size_t)i * slotB, *dh2_lo = WS_BF(w, dh2_lo) + (size_t)i * slotB;
+        __nv_bfloat16 *dh1_hi = WS_BF(w, dh1_hi) + (size_t)i * slotB, *dh1_lo = WS_BF(w, dh1_lo) + (size_t)i * slotB;
 
+        // ---- critical path (caller's stream) ----
+        if (two && !first) GRL_TRY(ev_wait(h, EV_DMEM(i + 1), st));
         // bn3 + residual ReLU:  dPre = dMn [Mn>0] -> dz (fp32);  dH3 planes
-        GRL_TRY(bn_backward(h, st, w, dmem, dz_prev, memn_hi, h3, s3, HC, p->memo_bn3[0].weight, p->memo_bn3[1].weight, g->memo_bn3_w[0],
-                            g->memo_bn3_w[1], g->memo_bn3_b[0], g->memo_bn3_b[1], acc, WS_BF(w, dh3_hi), WS_BF(w, dh3_lo), dz));
-        {   // conv3 wgrad: gw_c3[z] (+)= dH3^T H2p
-            GemmEpi e = epi_default();
-            e.C = WS_F32(w, gw_c3); e.ldc = HB; e.c_bstride = (long long)HC * HB; e.accumulate = acc;
-            Operand a{WS_BF(w, dh3_hi), WS_BF(w, dh3_lo), HC, (long long)R * HC, 1}, b{h2p_hi, h2p_lo, HB, (long long)R * HB, 1};
-            GRL_TRY(gemm_launch(h, st, HC, HB, R, 2, a, b, e, 0));
-        }
+        GRL_TRY(bn_backward(h, st, w, dmem_in, dz_prev, memn_hi, h3, s3, HC, p->memo_bn3[0].weight, p->memo_bn3[1].weight, g->memo_bn3_w[0],
+                            g->memo_bn3_w[1], g->memo_bn3_b[0], g->memo_bn3_b[1], acc, dh3_hi, dh3_lo, dz));
+        if (two) GRL_TRY(ev_record(h, EV_DH3(i), st));
         {   // conv3 dgrad: dH2p = dH3 Wc3
             GemmEpi e = epi_default();
             e.C = WS_F32(w, dh2p); e.ldc = HB; e.c_bstride = (long long)R * HB;
-            Operand a{WS_BF(w, dh3_hi), WS_BF(w, dh3_lo), HC, (long long)R * HC, 0}, b{WS_BF(w, wc3_hi), WS_BF(w, wc3_lo), HB, (long long)HC * HB, 1};
+            Operand a{dh3_hi, dh3_lo, HC, (long long)R * HC, 0}, b{WS_BF(w, wc3_hi), WS_BF(w, wc3_lo), HB, (long long)HC * HB, 1};
             GRL_TRY(gemm_launch(h, st, R, HB, HC, 2, a, b, e, 0));
         }
         GRL_TRY(bn_backward(h, st, w, WS_F32(w, dh2p), nullptr, h2p_hi, h2, s2, HB, p->memo_bn2[0].weight, p->memo_bn2[1].weight,
-                            g->memo_bn2_w[0], g->memo_bn2_w[1], g->memo_bn2_b[0], g->memo_bn2_b[1], acc, WS_BF(w, dh2_hi), WS_BF(w, dh2_lo), nullptr));
-        {   // conv2 wgrad
-            GemmEpi e = epi_default();
-            e.C = WS_F32(w, gw_c2); e.ldc = HB; e.c_bstride = (long long)HB * HB; e.accumulate = acc;
-            Operand a{WS_BF(w, dh2_hi), WS_BF(w, dh2_lo), HB, (long long)R * HB, 1}, b{h1p_hi, h1p_lo, HB, (long long)R * HB, 1};
-            GRL_TRY(gemm_launch(h, st, HB, HB, R, 2, a, b, e, 0));
-        }
+                            g->memo_bn2_w[0], g->memo_bn2_w[1], g->memo_bn2_b[0], g->memo_bn2_b[1], acc, dh2_hi, dh2_lo, nullptr));
+        if (two) GRL_TRY(ev_record(h, EV_DH2(i), st));
         {   // conv2 dgrad
             GemmEpi e = epi_default();
             e.C = WS_F32(w, dh1p); e.ldc = HB; e.c_bstride = (long long)R * HB;
-            Operand a{WS_BF(w, dh2_hi), WS_BF(w, dh2_lo), HB, (long long)R * HB, 0}, b{WS_BF(w, wc2_hi), WS_BF(w, wc2_lo), HB, (long long)HB * HB, 1};
+            Operand a{dh2_hi, dh2_lo, HB, (long long)R * HB, 0}, b{WS_BF(w, wc2_hi), WS_BF(w, wc2_lo), HB, (long long)HB * HB, 1};
             GRL_TRY(gemm_launch(h, st, R, HB, HB, 2, a, b, e, 0));
         }
         GRL_TRY(bn_backward(h, st, w, WS_F32(w, dh1p), nullptr, h1p_hi, h1, s1, HB, p->memo_bn1[0].weight, p->memo_bn1[1].weight,
-                            g->memo_bn1_w[0], g->memo_bn1_w[1], g->memo_bn1_b[0], g->memo_bn1_b[1], acc, WS_BF(w, dh1_hi), WS_BF(w, dh1_lo), nullptr));
-        {   // conv1 wgrad: gw_c1[z] (+)= dH1^T Z
-            GemmEpi e = epi_default();
-            e.C = WS_F32(w, gw_c1); e.ldc = HC; e.c_bstride = (long long)HB * HC; e.accumulate = acc;
-            Operand a{WS_BF(w, dh1_hi), WS_BF(w, dh1_lo), HB, (long long)R * HB, 1}, b{z_hi, z_lo, HC, (long long)R * HC, 1};
-            GRL_TRY(gemm_launch(h, st, HB, HC, R, 2, a, b, e, 0));
-        }
+                            g->memo_bn1_w[0], g->memo_bn1_w[1], g->memo_bn1_b[0], g->memo_bn1_b[1], acc, dh1_hi, dh1_lo, nullptr));
+        if (two) GRL_TRY(ev_record(h, EV_DH1(i), st));
         {   // conv1 dgrad: dZ = dPre + dH1 Wc1   (accumulates onto dPre)
             GemmEpi e = epi_default();
             e.C = dz; e.ldc = HC; e.c_bstride = (long long)R * HC; e.accumulate = 1;
-            Operand a{WS_BF(w, dh1_hi), WS_BF(w, dh1_lo), HB, (long long)R * HB, 0}, b{WS_BF(w, wc1_hi), WS_BF(w, wc1_lo), HC, (long long)HB * HC, 1};
+            Operand a{dh1_hi, dh1_lo, HB, (long long)R * HB, 0}, b{WS_BF(w, wc1_hi), WS_BF(w, wc1_lo), HC, (long long)HB * HC, 1};
             GRL_TRY(gemm_launch(h, st, R, HC, HB, 2, a, b, e, 0));
         }
-        // reciprocal-attention path of this step: dF1 (planes), dF2[tau] (planes), bias partials
-        trl_bwd_f1_kernel<<<dim3(HC / 64, B, 2), 256, 0, st>>>(WS_F32(w, f1) + (size_t)i * slotM, WS_F32(w, f2),
-                                                               WS_F32(w, se_dq) + (size_t)i * 2 * B * HC, B, T, R, tau0, tau1, WS_BF(w, df1_hi),
-                                                               WS_BF(w, df1_lo), WS_BF(w, df2_hi), WS_BF(w, df2_lo),
-                                                               WS_F32(w, dbf1_part) + (size_t)i * 2 * B * HC,
-                                                               WS_F32(w, dbf2_part) + (size_t)i * 2 * B * HC);
-        GRL_LAUNCH_CHECK(h);
-        {   // f1 wgrad: gw_f1[z] (+)= dF1^T M
+
+        // ---- weight gradients of the memory block (side stream) ----
+        if (two) GRL_TRY(ev_wait(h, EV_DH3(i), sd));
+        {   // conv3 wgrad: gw_c3[z] (+)= dH3^T H2p
             GemmEpi e = epi_default();
-            e.C = WS_F32(w, gw_f1); e.ldc = HC; e.c_bstride = (long long)HC * HC; e.accumulate = acc;
-            Operand a{WS_BF(w, df1_hi), WS_BF(w, df1_lo), HC, (long long)R * HC, 1}, b{mem_hi, mem_lo, HC, (long long)R * HC, 1};
-            GRL_TRY(gemm_launch(h, st, HC, HC, R, 2, a, b, e, 0));
+            e.C = WS_F32(w, gw_c3); e.ldc = HB; e.c_bstride = (long long)HC * HB; e.accumulate = acc;
+            Operand a{dh3_hi, dh3_lo, HC, (long long)R * HC, 1}, b{h2p_hi, h2p_lo, HB, (long long)R * HB, 1};
+            GRL_TRY(gemm_launch(h, sd, HC, HB, R, 2, a, b, e, 0));
         }
-        {   // f1 dgrad: dmem = dF1 Wf1   (the other half of dM for the next iteration is dZ of this step)
+        if (two) GRL_TRY(ev_wait(h, EV_DH2(i), sd));
+        {   // conv2 wgrad
             GemmEpi e = epi_default();
-            e.C = dmem; e.ldc = HC; e.c_bstride = (long long)R * HC;
-            Operand a{WS_BF(w, df1_hi), WS_BF(w, df1_lo), HC, (long long)R * HC, 0}, b{WS_BF(w, wf1_hi), WS_BF(w, wf1_lo), HC, (long long)HC * HC, 1};
-            GRL_TRY(gemm_launch(h, st, R, HC, HC, 2, a, b, e, 0));
+            e.C = WS_F32(w, gw_c2); e.ldc = HB; e.c_bstride = (long long)HB * HB; e.accumulate = acc;
+            Operand a{dh2_hi, dh2_lo, HB, (long long)R * HB, 1}, b{h1p_hi, h1p_lo, HB, (long long)R * HB, 1};
+            GRL_TRY(gemm_launch(h, sd, HB, HB, R, 2, a, b, e, 0));
+        }
+        if (two) GRL_TRY(ev_wait(h, EV_DH1(i), sd));
+        {   // conv1 wgrad: gw_c1[z] (+)= dH1^T Z
+            GemmEpi e = epi_default();
+            e.C = WS_F32(w, gw_c1); e.ldc = HC; e.c_bstride = (long long)HB * HC; e.accumulate = acc;
+            Operand a{dh1_hi, dh1_lo, HB, (long long)R * HB, 1}, b{z_hi, z_lo, HC, (long long)R * HC, 1};
+            GRL_TRY(gemm_launch(h, sd, HB, HC, R, 2, a, b, e, 0));
         }
     }
-    // ---------------- parameter gradients accumulated over the steps ----------------
+    // ---------------- parameter gradients accumulated over the steps; f2 over all frames (side stream) ----------------
     for (int d = 0; d < 2; ++d) {
-        GRL_CUDA(h, cudaMemcpyAsync(g->memo_conv3_w[d], WS_F32(w, gw_c3) + (size_t)d * HC * HB, (size_t)HC * HB * 4, cudaMemcpyDeviceToDevice, st));
-        GRL_CUDA(h, cudaMemcpyAsync(g->memo_conv2_w[d], WS_F32(w, gw_c2) + (size_t)d * HB * HB, (size_t)HB * HB * 4, cudaMemcpyDeviceToDevice, st));
-        GRL_CUDA(h, cudaMemcpyAsync(g->memo_conv1_w[d], WS_F32(w, gw_c1) + (size_t)d * HB * HC, (size_t)HB * HC * 4, cudaMemcpyDeviceToDevice, st));
-        GRL_CUDA(h, cudaMemcpyAsync(g->f1_w[d], WS_F32(w, gw_f1) + (size_t)d * HC * HC, (size_t)HC * HC * 4, cudaMemcpyDeviceToDevice, st));
-        small_colsum_kernel<<<dim3(HC / 256, 1), 256, 0, st>>>(WS_F32(w, dbf1_part) + (size_t)d * B * HC, 0, (long long)2 * B * HC, HC, T, B,
+        GRL_CUDA(h, cudaMemcpyAsync(g->memo_conv3_w[d], WS_F32(w, gw_c3) + (size_t)d * HC * HB, (size_t)HC * HB * 4, cudaMemcpyDeviceToDevice, sd));
+        GRL_CUDA(h, cudaMemcpyAsync(g->memo_conv2_w[d], WS_F32(w, gw_c2) + (size_t)d * HB * HB, (size_t)HB * HB * 4, cudaMemcpyDeviceToDevice, sd));
+        GRL_CUDA(h, cudaMemcpyAsync(g->memo_conv1_w[d], WS_F32(w, gw_c1) + (size_t)d * HB * HC, (size_t)HB * HC * 4, cudaMemcpyDeviceToDevice, sd));
+        GRL_CUDA(h, cudaMemcpyAsync(g->f1_w[d], WS_F32(w, gw_f1) + (size_t)d * HC * HC, (size_t)HC * HC * 4, cudaMemcpyDeviceToDevice, sd));
+        small_colsum_kernel<<<dim3(HC / 256, 1), 256, 0, sd>>>(WS_F32(w, dbf1_part) + (size_t)d * B * HC, 0, (long long)2 * B * HC, HC, T, B,
                                                                g->f1_b[d], 0, HC);
         GRL_LAUNCH_CHECK(h);
-        small_colsum_kernel<<<dim3(HC / 256, 1), 256, 0, st>>>(WS_F32(w, dbf2_part) + (size_t)d * B * HC, 0, (long long)2 * B * HC, HC, T, B,
+        small_colsum_kernel<<<dim3(HC / 256, 1), 256, 0, sd>>>(WS_F32(w, dbf2_part) + (size_t)d * B * HC, 0, (long long)2 * B * HC, HC, T, B,
                                                                g->f2_b[d], 0, HC);
         GRL_LAUNCH_CHECK(h);
         {   // f2 wgrad over all frames: d Wf2[d] = dF2[:, d]^T Xc     (K = P)
             GemmEpi e = epi_default();
             e.C = g->f2_w[d]; e.ldc = HC;
             Operand a{WS_BF(w, df2_hi) + (size_t)d * HC, WS_BF(w, df2_lo) + (size_t)d * HC, 2 * HC, 0, 1}, b{WS_BF(w, xc_hi), WS_BF(w, xc_lo), HC, 0, 1};
-            GRL_TRY(gemm_launch(h, st, HC, HC, P, 1, a, b, e, 0));
+            GRL_TRY(gemm_launch(h, sd, HC, HC, P, 1, a, b, e, 0));
         }
     }
     {   // f2 dgrad, both directions in one contraction (K = 4096): dxc = dF2cat Wf2cat
         GemmEpi e = epi_default();
         e.C = WS_F32(w, dxc); e.ldc = HC;
         Operand a{WS_BF(w, df2_hi), WS_BF(w, df2_lo), 2 * HC, 0, 0}, b{WS_BF(w, wf2_hi), WS_BF(w, wf2_lo), HC, 0, 1};
-        GRL_TRY(gemm_launch(h, st, P, HC, 2 * HC, 1, a, b, e, 0));
+        GRL_TRY(gemm_launch(h, sd, P, HC, 2 * HC, 1, a, b, e, 0));
     }
+    if (two) GRL_TRY(stream_wait(h, sd, st, 1));
     return GRL_OK;
 }
 

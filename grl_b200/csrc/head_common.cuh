@@ -51,9 +51,9 @@ constexpr float BN_MOM = 0.1f;
     X(sbn1, 4, (size_t)SL * 2 * 4 * HB) X(sbn2, 4, (size_t)SL * 2 * 4 * HB) X(sbn3, 4, (size_t)SL * 2 * 4 * HC) \
     X(out_d, 4, (size_t)2 * N * HC)                                                               \
     /* --- backward scratch (only when saving for backward) --- */                                \
-    X(dmem, 4, BW * 2 * R * HC) X(dh3_hi, 2, BW * 2 * R * HC) X(dh3_lo, 2, BW * 2 * R * HC)        \
-    X(dh2p, 4, BW * 2 * R * HB) X(dh2_hi, 2, BW * 2 * R * HB) X(dh2_lo, 2, BW * 2 * R * HB)        \
-    X(dh1p, 4, BW * 2 * R * HB) X(dh1_hi, 2, BW * 2 * R * HB) X(dh1_lo, 2, BW * 2 * R * HB)        \
+    X(dmem, 4, BW * (T + 1) * 2 * R * HC) X(dh3_hi, 2, BW * T * 2 * R * HC) X(dh3_lo, 2, BW * T * 2 * R * HC) \
+    X(dh2p, 4, BW * 2 * R * HB) X(dh2_hi, 2, BW * T * 2 * R * HB) X(dh2_lo, 2, BW * T * 2 * R * HB) \
+    X(dh1p, 4, BW * 2 * R * HB) X(dh1_hi, 2, BW * T * 2 * R * HB) X(dh1_lo, 2, BW * T * 2 * R * HB) \
     X(dzc, 4, BW * 2 * R * HC) X(df1_hi, 2, BW * 2 * R * HC) X(df1_lo, 2, BW * 2 * R * HC)         \
     X(df2_hi, 2, BW * P * 2 * HC) X(df2_lo, 2, BW * P * 2 * HC)                                    \
     X(dxu, 4, BW * 2 * P * HC) X(dxc, 4, BW * P * HC) X(dgc, 4, BW * N * HC)                       \

@@ -632,17 +632,27 @@ static int trl_forward_part(grl_handle* h, cudaStream_t st, const grl_head_param
                             float* f_corr) {
     const int B = w.B, T = w.T, N = w.N, P = w.P, R = w.R;
     // ---------------- TRL ----------------
+    // Two streams: the caller's stream `st` carries the recurrence (memory update: conv1 -> BN -> conv2 -> BN -> conv3 -> BN ->
+    // ReLU, 8 dependent steps); the f2 convolution of all frames, the per-step f1 convolution (+ pooled squared difference) and
+    // the squeeze-excite MLP only feed f_corr, so they run on the handle's low-priority side stream `sd` and overlap the
+    // HBM-bound BN / update kernels of the chain.  Events: EV_M(i) = memory M_i ready, EV_F1(i) = f1 of step i done.
+    cudaStream_t sd = h->overlap ? h->side : st;
+    const bool two = sd != st;
+    auto EV_M = [&](int i) { return 8 + i; };
+    auto EV_F1 = [&](int i) { return 8 + (T + 1) + i; };
+    if (two) GRL_TRY(stream_wait(h, st, sd, 0));
     {   // f2 for every frame and both directions at once (F2): [P][4096]
         GemmEpi e = epi_default();
         e.C = WS_F32(w, f2); e.ldc = 2 * HC;
         e.col_bias = WS_F32(w, bf2cat); e.relu = 1;
         Operand a{WS_BF(w, xc_hi), WS_BF(w, xc_lo), HC, 0, 0}, b{WS_BF(w, wf2_hi), WS_BF(w, wf2_lo), HC, 0, 0};
-        GRL_TRY(gemm_launch(h, st, P, 2 * HC, HC, 1, a, b, e, 0));
+        GRL_TRY(gemm_launch(h, sd, P, 2 * HC, HC, 1, a, b, e, 0));
     }
     const size_t slotM = (size_t)2 * R * HC;     // elements per mem / z slot (both directions)
     trl_init_kernel<<<dim3(HC / 64, B), 256, 0, st>>>(WS_BF(w, xu_hi), WS_BF(w, xu_lo), T, R, WS_BF(w, mem_hi), WS_BF(w, mem_lo),
                                                       WS_BF(w, z_hi), WS_BF(w, z_lo));
     GRL_LAUNCH_CHECK(h);
+    if (two) GRL_TRY(ev_record(h, EV_M(0), st));
     const int save = w.save;
     for (int i = 0; i < T; ++i) {
         const int sl = save ? i : 0;                         // per-step slot
@@ -661,7 +671,9 @@ static int trl_forward_part(grl_handle* h, cudaStream_t st, const grl_head_param
             e.sub_col_off[0] = 0; e.sub_col_off[1] = HC;
             e.col_sq = qpart; e.stat_bstride = (long long)4 * B * HC;
             Operand a{mh, ml, HC, (long long)R * HC, 0}, b{WS_BF(w, wf1_hi), WS_BF(w, wf1_lo), HC, (long long)HC * HC, 0};
-            GRL_TRY(gemm_launch(h, st, R, HC, HC, 2, a, b, e, 0));
+            if (two) GRL_TRY(ev_wait(h, EV_M(i), sd));
+            GRL_TRY(gemm_launch(h, sd, R, HC, HC, 2, a, b, e, 0));
+            if (two) GRL_TRY(ev_record(h, EV_F1(i), sd));
         }
         // ---- memory update: BasicBlock(M, Xu[tau]) ----
         float* h1 = WS_F32(w, h1) + (size_t)sl * 2 * R * HB;
@@ -704,18 +716,22 @@ static int trl_forward_part(grl_handle* h, cudaStream_t st, const grl_head_param
                                 bn_ptrs(p->memo_bn3[0], p->memo_bn3[1]), s3, train, 2));
         }
         const int has_next = (i + 1 < T) ? 1 : 0;
+        // inference ping-pongs two memory slots: this update overwrites the slot M_{i-1} lives in, which f1(i-1) may still read
+        if (two && !save && i >= 1) GRL_TRY(ev_wait(h, EV_F1(i - 1), st));
         memo_update_kernel<<<dim3(HC / 64, B, 2), 256, 0, st>>>(h3, s3, zh, zl, WS_BF(w, xu_hi), WS_BF(w, xu_lo), T, R, has_next, i + 1,
                                                                 T - 2 - i, WS_BF(w, mem_hi) + ms_next * slotM, WS_BF(w, mem_lo) + ms_next * slotM,
                                                                 WS_BF(w, z_hi) + (has_next ? zs_next : zs) * slotM,
                                                                 WS_BF(w, z_lo) + (has_next ? zs_next : zs) * slotM);
         GRL_LAUNCH_CHECK(h);
+        if (two) GRL_TRY(ev_record(h, EV_M(i + 1), st));
     }
-    {   // squeeze-excite + F4 pooled shortcut for all steps at once
+    {   // squeeze-excite + F4 pooled shortcut for all steps at once (after the last f1, in order on the side stream)
         SePtrs sp; sp.l1[0] = p->se1_w[0]; sp.l1[1] = p->se1_w[1]; sp.l2[0] = p->se2_w[0]; sp.l2[1] = p->se2_w[1];
-        se_fwd_kernel<<<dim3(B, 2, T), SE_THREADS, 0, st>>>(WS_F32(w, qpart), sp, WS_F32(w, gc), B, T, WS_F32(w, se_q), WS_F32(w, se_h),
+        se_fwd_kernel<<<dim3(B, 2, T), SE_THREADS, 0, sd>>>(WS_F32(w, qpart), sp, WS_F32(w, gc), B, T, WS_F32(w, se_q), WS_F32(w, se_h),
                                                             WS_F32(w, se_a), WS_F32(w, out_d));
         GRL_LAUNCH_CHECK(h);
     }
+    if (two) GRL_TRY(stream_wait(h, sd, st, 1));
     const int mfin = save ? T : (T & 1);
     trl_final_kernel<<<dim3(HC / 64, B), 256, 0, st>>>(WS_BF(w, mem_hi) + mfin * slotM, WS_BF(w, mem_lo) + mfin * slotM, R, f_uncorr);
     GRL_LAUNCH_CHECK(h);

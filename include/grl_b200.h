@@ -218,6 +218,11 @@ int grl_head_ws_lookup(int B, int T, int save_for_backward, const char* name, si
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches).   */
 long long grl_launch_count(const grl_handle* h);
 
+/* The head entry points fork work that is off the recurrence's critical path (f1 / f2 convolutions, weight
+ * gradients) onto an internal low-priority stream and join it back into the caller's stream before returning, so
+ * HBM-bound glue overlaps tensor-core work.  On by default; 0 runs everything on the caller's stream (debugging).   */
+int grl_set_overlap(grl_handle* h, int on);
+
 /* Profiling aid for bench.py's roofline: while enabled, every tcgen05 GEMM launch is bracketed by CUDA
  * events on the caller's stream.  grl_profile_read waits for them and returns, since the last read, the
  * summed device time of those launches (ms), their algorithmic FLOPs (2*M*N*K*batch; the split-bf16
