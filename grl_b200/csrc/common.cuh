@@ -146,6 +146,22 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 __device__ __forceinline__ float bf16_lo_f(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi_f(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
 
+// ---------------------------------------------------------------- (distance, index) sort keys
+// float -> uint32 whose unsigned order equals the float order (-0 == +0, NaN last).
+__device__ __forceinline__ uint32_t orderable(float d) {
+    if (d == 0.f) d = 0.f;                       // canonicalise -0
+    uint32_t u = __float_as_uint(d);
+    if (d != d) u = 0x7FC00000u;                 // canonical +NaN: sorts after +inf, like numpy
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable(uint32_t o) {
+    const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ uint64_t make_key(float d, uint32_t idx) {
+    return (static_cast<uint64_t>(orderable(d)) << 32) | idx;
+}
+
 // Reduce-scatter of v[32] across the 32 lanes of a warp with 31 shuffles:
 // afterwards v[0] of lane l holds sum over lanes of (their) v[l].
 __device__ __forceinline__ float warp_transpose_sum32(float* v) {

@@ -10,22 +10,7 @@
 
 namespace grl {
 
-// ------------------------------------------------------------------ helpers
-// float -> uint32 whose unsigned order equals the float order (-0 == +0, NaN last).
-__device__ __forceinline__ uint32_t orderable(float d) {
-    if (d == 0.f) d = 0.f;                       // canonicalise -0
-    uint32_t u = __float_as_uint(d);
-    if (d != d) u = 0x7FC00000u;                 // canonical +NaN: sorts after +inf, like numpy
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float from_orderable(uint32_t o) {
-    const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
-    return __uint_as_float(u);
-}
-__device__ __forceinline__ uint64_t make_key(float d, uint32_t idx) {
-    return (static_cast<uint64_t>(orderable(d)) << 32) | idx;
-}
-
+// ------------------------------------------------------------------ helpers (sort keys live in common.cuh)
 // In-place ascending bitonic sort of n (power of two) keys in shared memory by the whole block.
 __device__ void block_bitonic_sort(uint64_t* keys, int n) {
     for (int size = 2; size <= n; size <<= 1) {
@@ -235,6 +220,89 @@ __global__ void topk_init_kernel(float* top_d, int64_t* top_i, long long n) {
     if (i < n) { top_d[i] = CUDART_INF_F; top_i[i] = -1; }
 }
 
+// One column chunk folded into the running lists, fed by the distance GEMM's candidate filter.  One block per query row:
+//   cnt == 0          : nothing in this chunk beats the row's k-th best -> exit
+//   cnt <= cap        : sort (list U candidates) with a bitonic network sized next_pow2(k + cnt) -- typically 128 keys
+//   cnt  > cap        : the candidate list overflowed (first chunk, adversarial order): rescan the row of the distance tile
+// and publish the new k-th best distance as the row's filter threshold.
+__global__ void __launch_bounds__(TOPK_THREADS) topk_update_kernel(const float* __restrict__ dist, long long ld, int ncols, int k,
+                                                                   int64_t idx_base, float* __restrict__ top_d, int64_t* __restrict__ top_i,
+                                                                   float* __restrict__ thresh_out, const unsigned long long* __restrict__ cand,
+                                                                   int* __restrict__ cand_cnt, int cap) {
+    __shared__ uint64_t keys[TOPK_BUF];
+    __shared__ int count;
+    __shared__ uint64_t thresh;
+    const int row = blockIdx.x;
+    const int cnt = cand_cnt[row];
+    if (cnt == 0) return;
+    float* td = top_d + (long long)row * k;
+    int64_t* ti = top_i + (long long)row * k;
+    int nsort;
+    if (cnt <= cap) {
+        int npad = 2;
+        while (npad < k + cnt) npad <<= 1;
+        for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+            uint64_t key = ~0ull;
+            if (i < k) { if (ti[i] >= 0) key = make_key(td[i], (uint32_t)ti[i]); }
+            else if (i < k + cnt) key = cand[(long long)row * cap + (i - k)];
+            keys[i] = key;
+        }
+        block_bitonic_sort(keys, npad);
+        nsort = npad;
+    } else {
+        const float* drow = dist + (long long)row * ld;
+        for (int i = threadIdx.x; i < TOPK_BUF; i += blockDim.x) {
+            uint64_t key = ~0ull;
+            if (i < k && ti[i] >= 0) key = make_key(td[i], (uint32_t)ti[i]);
+            keys[i] = key;
+        }
+        if (threadIdx.x == 0) count = k;
+        __syncthreads();
+        if (threadIdx.x == 0) thresh = keys[k - 1];
+        __syncthreads();
+        const int stage_cap = TOPK_BUF - TOPK_WAVE;
+        for (int c0 = 0; c0 < ncols; c0 += TOPK_WAVE) {
+            const uint64_t th = thresh;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + u * TOPK_THREADS + threadIdx.x;
+                if (c < ncols) {
+                    const uint64_t key = make_key(drow[c], (uint32_t)(idx_base + c));
+                    if (key < th) keys[atomicAdd(&count, 1)] = key;
+                }
+            }
+            __syncthreads();
+            const bool last = c0 + TOPK_WAVE >= ncols;
+            if (count > stage_cap || (last && count > k)) {
+                const int n = count;
+                for (int i = n + threadIdx.x; i < TOPK_BUF; i += blockDim.x) keys[i] = ~0ull;
+                block_bitonic_sort(keys, TOPK_BUF);
+                if (threadIdx.x == 0) { count = k; thresh = keys[k - 1]; }
+                __syncthreads();
+            }
+        }
+        nsort = TOPK_BUF;
+    }
+    (void)nsort;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const uint64_t key = keys[i];
+        if (key == ~0ull) { td[i] = CUDART_INF_F; ti[i] = -1; }
+        else { td[i] = from_orderable((uint32_t)(key >> 32)); ti[i] = (int64_t)(key & 0xFFFFFFFFu); }
+    }
+    if (threadIdx.x == 0) {
+        const uint64_t kth = keys[k - 1];
+        thresh_out[row] = kth == ~0ull ? CUDART_INF_F : from_orderable((uint32_t)(kth >> 32));
+        cand_cnt[row] = 0;
+    }
+}
+
+// Before the first chunk no threshold exists: mark every row "overflowed" (cnt = cap + 1, threshold -inf) so the first
+// update rescans its tile row and the epilogue of the first GEMM appends nothing.
+__global__ void topk_filter_init_kernel(float* thresh, int* cnt, int nq, int cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) { thresh[i] = -CUDART_INF_F; cnt[i] = cap + 1; }
+}
+
 // merge nshards sorted lists [nshards][nq][k] -> [nq][k]; (distance, global index) order
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ all_d, const int64_t* __restrict__ all_i,
                                                          int nshards, int nq, int k, int npad, float* __restrict__ out_d,
@@ -322,6 +390,8 @@ static int topk_chunk_cols(int nq, int ng) {
     return (int)c;
 }
 
+constexpr int TOPK_CAND_CAP = 256;      // candidates per query row per column chunk before the rescan path takes over
+
 static void dist_topk_layout(int nq, int ng, int dim, size_t* q_pl, size_t* g_pl, size_t* norms, size_t* tile, int* chunk) {
     *chunk = topk_chunk_cols(nq, ng);
     *q_pl = align_up((size_t)nq * dim * 2, 1024);
@@ -329,11 +399,14 @@ static void dist_topk_layout(int nq, int ng, int dim, size_t* q_pl, size_t* g_pl
     *norms = align_up((size_t)(nq + *chunk) * 4, 1024);
     *tile = align_up((size_t)nq * *chunk * 4, 1024);
 }
+static size_t dist_topk_filter_bytes(int nq) {   // thresh f32[nq] | cnt i32[nq] | cand u64[nq][cap]
+    return align_up((size_t)nq * 4, 1024) * 2 + align_up((size_t)nq * TOPK_CAND_CAP * 8, 1024);
+}
 
 extern "C" size_t grl_dist_topk_workspace_bytes(int nq, int ng, int dim) {
     size_t a, b, c, t; int chunk;
     dist_topk_layout(nq, ng, dim, &a, &b, &c, &t, &chunk);
-    return 2 * a + 2 * b + c + t;
+    return 2 * a + 2 * b + c + t + dist_topk_filter_bytes(nq);
 }
 
 extern "C" int grl_dist_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k,
@@ -354,7 +427,12 @@ extern "C" int grl_dist_topk(grl_handle* h, int metric, const float* q, const fl
     __nv_bfloat16* g_lo = (__nv_bfloat16*)w; w += gb;
     float* qn = (float*)w;
     float* gn = qn + nq; w += nb;
-    float* tile = (float*)w;
+    float* tile = (float*)w; w += tb;
+    float* thresh = (float*)w; w += align_up((size_t)nq * 4, 1024);
+    int* cand_cnt = (int*)w; w += align_up((size_t)nq * 4, 1024);
+    unsigned long long* cand = (unsigned long long*)w;
+    topk_filter_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(thresh, cand_cnt, nq, TOPK_CAND_CAP);
+    GRL_LAUNCH_CHECK(h);
     GRL_TRY(split_planes(h, st, q, dim, q_hi, q_lo, dim, nq, dim));
     if (metric == GRL_METRIC_L2) {
         row_sqnorm_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(q, nq, dim, qn);
@@ -374,9 +452,12 @@ extern "C" int grl_dist_topk(grl_handle* h, int metric, const float* q, const fl
         } else {
             e.alpha = -1.f;
         }
+        // the epilogue keeps only distances that can still enter a row's list (v <= current k-th best) as candidates
+        e.tk_cand = cand; e.tk_cnt = cand_cnt; e.tk_thresh = thresh; e.tk_cap = TOPK_CAND_CAP; e.tk_idx_base = idx_base + c0;
         Operand oa{q_hi, q_lo, dim, 0, 0}, ob{g_hi, g_lo, dim, 0, 0};
         GRL_TRY(gemm_launch(h, st, nq, nc, dim, 1, oa, ob, e, 0));
-        topk_rows_kernel<<<nq, TOPK_THREADS, 0, st>>>(tile, chunk, nc, k, idx_base + c0, top_d, top_i);
+        topk_update_kernel<<<nq, TOPK_THREADS, 0, st>>>(tile, chunk, nc, k, idx_base + c0, top_d, top_i, thresh, cand, cand_cnt,
+                                                        TOPK_CAND_CAP);
         GRL_LAUNCH_CHECK(h);
     }
     return GRL_OK;

@@ -175,6 +175,7 @@ int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, 
     p.M = M; p.N = N; p.K = K; p.batch = batch;
     p.num_m_tiles = m_tiles;
     p.num_n_tiles = (N + bn - 1) / bn;
+    p.group_m = p.num_m_tiles > 32 ? 16 : p.num_m_tiles;
     p.epi = epi;
     GRL_TRY(make_tmap(h, &p.ta_hi, A.hi, A.ld, A.bstride, A.mn_major, M, K, batch, GEMM_BM));
     GRL_TRY(make_tmap(h, &p.ta_lo, A.lo, A.ld, A.bstride, A.mn_major, M, K, batch, GEMM_BM));
@@ -230,7 +231,7 @@ extern "C" int grl_create(int device, grl_handle** out) {
         delete h->prof; delete h;
         return set_error(nullptr, GRL_ECUDA, "cudaStreamCreateWithPriority: %s", cudaGetErrorString(e));
     }
-    h->overlap = 1;
+    h->overlap = 3;
     *out = h;
     return GRL_OK;
 }
@@ -249,7 +250,7 @@ extern "C" void grl_destroy(grl_handle* h) {
 
 extern "C" int grl_set_overlap(grl_handle* h, int on) {
     if (!h) return GRL_EINVAL;
-    h->overlap = on ? 1 : 0;
+    h->overlap = on & 3;
     return GRL_OK;
 }
 

@@ -54,6 +54,13 @@ struct GemmEpi {
     int mode;                 // 0 plain, 1 L2: v = sqrt(max(row_norm[m] + col_norm[n] - 2*acc, 1e-12))
     const float* row_norm;
     const float* col_norm;
+    // ---- top-k candidate filter (retrieval): every stored value v <= tk_thresh[m] is appended, as a (distance, global column)
+    //      key, to row m's candidate list (capacity tk_cap; tk_cnt keeps counting past it so the consumer sees the overflow) ----
+    unsigned long long* tk_cand;
+    int* tk_cnt;
+    const float* tk_thresh;
+    int tk_cap;
+    long long tk_idx_base;
     // ---- "sub" mode (TRL f1): e = v - sub[sub_row][sub_col]; stat value = e (else v) ----
     const float* sub;
     long long ld_sub;
@@ -66,8 +73,23 @@ struct GemmParams {
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     int M, N, K, batch;
     int num_m_tiles, num_n_tiles;
+    int group_m;              // tile rasterisation: groups of `group_m` m-tiles sweep all n-tiles before the next group
     GemmEpi epi;
 };
+
+// Tile index -> (batch z, m tile, n tile).  Within a batch, groups of group_m m-tiles are swept across all n-tiles
+// (m fastest inside a group) before moving on, so the CTAs running at any time share a slab of A rows and a band of B
+// rows that fit L2: each operand is read from HBM about once even when M*K does not fit L2 (P = B*T*128 pixel rows).
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int tiles_per_batch, int& z, int& m_tile, int& n_tile) {
+    z = tile / tiles_per_batch;
+    const int r = tile - z * tiles_per_batch;
+    const int per_group = p.group_m * p.num_n_tiles;
+    const int mg = r / per_group;
+    const int rr = r - mg * per_group;
+    const int gsize = min(p.group_m, p.num_m_tiles - mg * p.group_m);
+    n_tile = rr / gsize;
+    m_tile = mg * p.group_m + (rr - n_tile * gsize);
+}
 
 template <int BN>
 struct GemmCfg {
@@ -118,10 +140,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int z = tile / tiles_per_batch;
-                const int r = tile - z * tiles_per_batch;
-                const int m0 = (r % p.num_m_tiles) * GEMM_BM;
-                const int n0 = (r / p.num_m_tiles) * BN;
+                int z, m_tile, n_tile;
+                tile_coords(p, tile, tiles_per_batch, z, m_tile, n_tile);
+                const int m0 = m_tile * GEMM_BM;
+                const int n0 = n_tile * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const int k0 = kb * GEMM_BK;
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -207,19 +229,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
         const int row_in_tile = quad * 32 + lane;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int z = tile / tiles_per_batch;
-            const int r = tile - z * tiles_per_batch;
-            const int m_tile = r % p.num_m_tiles;
+            int z, m_tile, n_tile;
+            tile_coords(p, tile, tiles_per_batch, z, m_tile, n_tile);
             const int m0 = m_tile * GEMM_BM;
-            const int n0 = (r / p.num_m_tiles) * BN;
+            const int n0 = n_tile * BN;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int grow = m0 + row_in_tile;
             const bool row_ok = grow < p.M;
-            float rscale = 1.f, rnorm = 0.f;
+            float rscale = 1.f, rnorm = 0.f, rthresh = 0.f;
             if (row_ok) {
                 if (e.row_scale) rscale = e.row_scale[z * e.rs_bstride + grow];
                 if (e.mode == 1) rnorm = e.row_norm[grow];
+                if (e.tk_cand)      // a row whose list already overflowed is rescanned by the consumer anyway: stop appending
+                    rthresh = (e.tk_cnt[grow] > e.tk_cap) ? -__int_as_float(0x7f800000) : e.tk_thresh[grow];
             }
             const float* gb_row = e.grp_bias ? e.grp_bias + (long long)(grow / e.grp_rows) * e.ld_gb : nullptr;
             const float* sub_row = nullptr;
@@ -257,6 +280,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
                     if (e.relu) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                }
+                // ---- top-k candidates: almost every distance fails this one compare once the lists have warmed up ----
+                if (e.tk_cand && row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (v[j] <= rthresh && (full_chunk || col0 + j < p.N)) {
+                            const int pos = atomicAdd(e.tk_cnt + grow, 1);
+                            if (pos < e.tk_cap)
+                                e.tk_cand[(long long)grow * e.tk_cap + pos] = make_key(v[j], (uint32_t)(e.tk_idx_base + col0 + j));
+                        }
                     }
                 }
                 // ---- stores of v ----

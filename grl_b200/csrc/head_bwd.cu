@@ -716,7 +716,7 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
     // reciprocal-attention path (its gradients depend on saved activations only) and every weight gradient -- runs on the
     // low-priority side stream `sd` and fills the tensor pipe while the chain's elementwise kernels stream through HBM.
     //   EV_DMEM(i): dF1_i Wf1 ready (side -> main);  EV_DH3/2/1(i): dH planes of step i ready (main -> side, for the wgrads)
-    cudaStream_t sd = h->overlap ? h->side : st;
+    cudaStream_t sd = (h->overlap & 2) ? h->side : st;
     const bool two = sd != st;
     auto EV_DMEM = [&](int i) { return 8 + i; };
     auto EV_DH3 = [&](int i) { return 8 + (T + 1) + i; };

@@ -636,7 +636,7 @@ static int trl_forward_part(grl_handle* h, cudaStream_t st, const grl_head_param
     // ReLU, 8 dependent steps); the f2 convolution of all frames, the per-step f1 convolution (+ pooled squared difference) and
     // the squeeze-excite MLP only feed f_corr, so they run on the handle's low-priority side stream `sd` and overlap the
     // HBM-bound BN / update kernels of the chain.  Events: EV_M(i) = memory M_i ready, EV_F1(i) = f1 of step i done.
-    cudaStream_t sd = h->overlap ? h->side : st;
+    cudaStream_t sd = (h->overlap & 1) ? h->side : st;
     const bool two = sd != st;
     auto EV_M = [&](int i) { return 8 + i; };
     auto EV_F1 = [&](int i) { return 8 + (T + 1) + i; };

@@ -220,8 +220,9 @@ long long grl_launch_count(const grl_handle* h);
 
 /* The head entry points fork work that is off the recurrence's critical path (f1 / f2 convolutions, weight
  * gradients) onto an internal low-priority stream and join it back into the caller's stream before returning, so
- * HBM-bound glue overlaps tensor-core work.  On by default; 0 runs everything on the caller's stream (debugging).   */
-int grl_set_overlap(grl_handle* h, int on);
+ * HBM-bound glue overlaps tensor-core work.  `mask`: bit 0 = forward, bit 1 = backward; default 3; 0 runs everything
+ * on the caller's stream (debugging, per-kernel profiling).                                                          */
+int grl_set_overlap(grl_handle* h, int mask);
 
 /* Profiling aid for bench.py's roofline: while enabled, every tcgen05 GEMM launch is bracketed by CUDA
  * events on the caller's stream.  grl_profile_read waits for them and returns, since the last read, the

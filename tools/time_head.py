@@ -41,8 +41,14 @@ def bwd():
     head.head_backward_raw(sd, x, B, T, ws, gu, gc)
 
 
-for ov in (0, 1):
-    lib.grl_set_overlap(h, ov)
+def step():
     fwd()
-    print("overlap=%d  fwd(train,save) %.3f ms   bwd %.3f ms   fwd(eval,nosave) %.3f ms" %
-          (ov, timeit(fwd), timeit(bwd), timeit(lambda: fwd(False, False))))
+    bwd()
+
+
+for rep in range(2):
+    for ov in (0, 1, 2, 3):
+        lib.grl_set_overlap(h, ov)
+        fwd()
+        print("overlap mask=%d  fwd(train,save) %.3f ms   bwd %.3f ms   fwd+bwd %.3f ms   fwd(eval,nosave) %.3f ms" %
+              (ov, timeit(fwd, 20), timeit(bwd, 20), timeit(step, 20), timeit(lambda: fwd(False, False), 20)), flush=True)
