@@ -57,6 +57,12 @@ class HeadGrads(C.Structure):
                 ("memo_conv3_w", C.c_void_p * 2), ("memo_bn3_w", C.c_void_p * 2), ("memo_bn3_b", C.c_void_p * 2)]
 
 
+class TailParams(C.Structure):
+    _fields_ = [("corr_bn", BnParams), ("uncorr_bn", BnParams),
+                ("featQ_w", C.c_void_p), ("featQ_b", C.c_void_p), ("featQ_bn", BnParams),
+                ("featK_w", C.c_void_p), ("featK_b", C.c_void_p), ("featK_bn", BnParams)]
+
+
 _SIGNATURES = {
     "grl_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "grl_destroy": (None, [C.c_void_p]),
@@ -99,6 +105,9 @@ _SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "grl_trl_backward": (C.c_int, [C.c_void_p, C.POINTER(HeadParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.POINTER(HeadGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "grl_eval_descriptor_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "grl_eval_descriptor": (C.c_int, [C.c_void_p, C.POINTER(TailParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_longlong, C.c_void_p, C.c_size_t, C.c_void_p]),
     "grl_head_ws_lookup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
 }
 

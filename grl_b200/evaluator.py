@@ -1,5 +1,8 @@
 """Drop-in mirror of the reference's matching / evaluation path on B200.
 
+ATTEvaluator drives the caller's models exactly like the reference (cnn_model(clips) -> siamese_model.self_attention ->
+cat); with grl_b200.head.ResNet50_GRL_Model and grl_b200.siamese.Siamese those calls are the CUDA path end to end.
+
 Same names, argument meaning and return types as
   reid/evaluator/attevaluator.py:15-46   evaluate_seq, pairwise_distance_tensor, cosin_dist
   reid/evaluator/eva_functions.py:134-184 evaluate

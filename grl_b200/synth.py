@@ -166,3 +166,57 @@ def make_eval_set(num_q: int, num_g_extra: int, dim: int, seed: int = 0, num_ids
     g_pid = np.concatenate([q_pid, g_pid_x])
     g_cam = np.concatenate([q_cam, g_cam_x])
     return qf, gf, q_pid.astype(np.int64), g_pid.astype(np.int64), q_cam.astype(np.int64), g_cam.astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------------
+# Eval feature tail: ResNet50_GRL_Model.corr_bn / uncorr_bn (grl_model.py:203-209) and the
+# Siamese temporal self-attention (reid/models/Siamese.py:43-76; input_num=2048, output_num=512, mars_train.py:77)
+# ------------------------------------------------------------------------------------------------
+C_ATT = 512
+
+
+def tail_param_shapes() -> "OrderedDict[str, tuple]":
+    d: "OrderedDict[str, tuple]" = OrderedDict()
+
+    def bn(prefix, n):
+        d[prefix + ".weight"] = (n,)
+        d[prefix + ".bias"] = (n,)
+        d[prefix + ".running_mean"] = (n,)
+        d[prefix + ".running_var"] = (n,)
+
+    bn("corr_bn", C_FEAT)
+    bn("uncorr_bn", C_FEAT)
+    for name in ("featQ", "featK"):
+        d["siamese." + name + ".weight"] = (C_ATT, C_FEAT)
+        d["siamese." + name + ".bias"] = (C_ATT,)
+        bn("siamese." + name + "_bn", C_ATT)
+    return d
+
+
+def make_tail_params(seed: int = 10, dtype=torch.float32):
+    rng = np.random.default_rng(seed)
+    out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for name, shape in tail_param_shapes().items():
+        if name.endswith("running_mean"):
+            v = rng.standard_normal(shape, dtype=np.float32) * 0.05
+        elif name.endswith("running_var"):
+            v = rng.uniform(0.5, 1.5, shape).astype(np.float32)
+        elif "bn" in name and name.endswith(".weight"):
+            v = rng.uniform(0.6, 1.4, shape).astype(np.float32)
+        elif "bn" in name:
+            v = rng.standard_normal(shape, dtype=np.float32) * 0.1
+        elif name.endswith(".weight"):
+            v = (rng.standard_normal(shape, dtype=np.float32) * (2.0 / math.sqrt(C_FEAT))).astype(np.float32)
+        else:
+            v = rng.standard_normal(shape, dtype=np.float32) * 0.1
+        out[name] = torch.from_numpy(np.ascontiguousarray(v)).to(dtype)
+    return out
+
+
+def make_tail_input(n: int, T: int, seed: int = 11, dtype=torch.float32):
+    """Head outputs (f_uncorr [n,2048], f_corr [n,T,2048]): positive, clip- and frame-dependent like pooled ReLU maps."""
+    rng = np.random.default_rng(seed)
+    base = np.abs(rng.standard_normal((n, 1, C_FEAT), dtype=np.float32))
+    fc = np.abs(base + 0.4 * rng.standard_normal((n, T, C_FEAT), dtype=np.float32)).astype(np.float32)
+    fu = np.abs(base[:, 0] + 0.4 * rng.standard_normal((n, C_FEAT), dtype=np.float32)).astype(np.float32)
+    return torch.from_numpy(fu).to(dtype), torch.from_numpy(fc).to(dtype)

@@ -211,6 +211,23 @@ int grl_trl_backward(grl_handle* h, const grl_head_params* p, int B, int T, cons
                      float* d_x_uncorr, float* d_x_corr, const grl_head_grads* grads,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- eval feature tail (what sits between the head and the distance GEMM at evaluation time) --------------- */
+/* Head outputs -> per-clip 6144-d descriptor cat(x_uncorr, self_attention(x_corr), mean_t x_corr), eval-mode BN:
+ *   corr_bn / uncorr_bn + F.normalize            reid/models/grl_model.py:222-226
+ *   Siamese.self_attention                       reid/models/Siamese.py:79-106   (featQ / featK: Linear(2048, 512) + BN1d)
+ *   the concat                                   reid/evaluator/attevaluator.py:79-80
+ * f_uncorr [n][2048], f_corr [n][T][2048] -> out [n][ld_out >= 6144].  apply_tail_bn = 0: the inputs are already the
+ * model's normalised outputs (x_uncorr, x_corr) and corr_bn / uncorr_bn may be NULL; out[:, 2048:4096] is then exactly
+ * Siamese.self_attention(x_corr).                                                                                    */
+typedef struct grl_tail_params {
+    grl_bn_params corr_bn, uncorr_bn;          /* BatchNorm1d(2048) of ResNet50_GRL_Model */
+    const float* featQ_w; const float* featQ_b; grl_bn_params featQ_bn;     /* [512][2048], [512], BatchNorm1d(512) */
+    const float* featK_w; const float* featK_b; grl_bn_params featK_bn;
+} grl_tail_params;
+size_t grl_eval_descriptor_workspace_bytes(int n, int T);
+int grl_eval_descriptor(grl_handle* h, const grl_tail_params* p, const float* f_uncorr, const float* f_corr, int n, int T,
+                        int apply_tail_bn, float* out, long long ld_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Debug/test: byte offset and size of a named intermediate inside the head workspace
  * (e.g. "xp_hi", "y1", "m", "f2", "memo_h1").  Returns GRL_EINVAL for unknown names.         */
 int grl_head_ws_lookup(int B, int T, int save_for_backward, const char* name, size_t* offset, size_t* bytes);

@@ -128,6 +128,38 @@ def eval_fixture(att, eva, name, nq, ng_extra, dim, seed, noise, max_rank=100, q
     print("wrote", name, "mAP %.4f rank1 %.4f" % (mAP, cmc[0]))
 
 
+def tail_fixture(Model, name, n, T):
+    """Eval feature tail on the REAL reference modules: model.corr_bn / uncorr_bn (grl_model.py:222-226) and
+    reid.models.Siamese.Siamese(2048, 512, 2).self_attention (mars_train.py:77), all in eval mode, float64."""
+    from grl_b200 import synth
+    from reid.models.Siamese import Siamese
+    tp = synth.make_tail_params(10)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = Model()
+    sia = Siamese(2048, 512, 2)
+    msd, ssd = model.state_dict(), sia.state_dict()
+    for k, v in tp.items():
+        if k.startswith("siamese."):
+            assert k[8:] in ssd and ssd[k[8:]].shape == v.shape, k
+            ssd[k[8:]] = v.clone()
+        else:
+            assert k in msd and msd[k].shape == v.shape, k
+            msd[k] = v.clone()
+    model.load_state_dict(msd)
+    sia.load_state_dict(ssd)
+    model = model.double().eval()
+    sia = sia.double().eval()
+    fu, fc = synth.make_tail_input(n, T, dtype=torch.float64)
+    with torch.no_grad():
+        x_corr = torch.nn.functional.normalize(model.corr_bn(fc.view(n * T, 2048)).view(n, T, 2048), p=2, dim=2)
+        x_uncorr = torch.nn.functional.normalize(model.uncorr_bn(fu), p=2, dim=1)
+        out_frame = sia.self_attention(x_corr)
+        out_feat = torch.cat((x_uncorr, out_frame, x_corr.mean(dim=1)), dim=1)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), n=n, T=T, out_feat=out_feat.numpy(), out_frame=out_frame.numpy(),
+                        tracklet=out_feat.mean(dim=0).numpy())
+    print("wrote", name, tuple(out_feat.shape))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -135,6 +167,8 @@ def main():
     head_fixture(Model, "head_train_b2t3", 2, 3, True)
     head_fixture(Model, "head_train_b4t2", 4, 2, True)
     head_fixture(Model, "head_eval_b3t4", 3, 4, False, with_grads=False)
+    tail_fixture(Model, "tail_n5t8", 5, 8)
+    tail_fixture(Model, "tail_n3t16", 3, 16)
     eval_fixture(att, eva, "eval_small", 60, 240, 64, seed=3, noise=1.5)
     # NOTE: the reference itself raises (ragged all_cmc, eva_functions.py:164,180) when junk removal leaves
     # fewer than max_rank gallery rows, so "num_g < max_rank" (:136-138) cannot be pinned; use max_rank=10.

@@ -1,0 +1,85 @@
+"""GPU parity: eval feature tail (grl_eval_descriptor) through the C ABI vs the reference golden and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from grl_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu().reshape(-1)
+    b = torch.as_tensor(b).detach().double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+def build_models():
+    from grl_b200 import head, siamese
+    model = head.ResNet50_GRL_Model(base=torch.nn.Identity()).cuda().eval()
+    sia = siamese.Siamese(2048, 512, 2).cuda().eval()
+    tp = synth.make_tail_params(10)
+    msd, ssd = model.state_dict(), sia.state_dict()
+    for k, v in tp.items():
+        if k.startswith("siamese."):
+            ssd[k[8:]] = v
+        else:
+            msd[k] = v
+    model.load_state_dict(msd)
+    sia.load_state_dict(ssd)
+    return model, sia
+
+
+@pytest.mark.parametrize("name", ["tail_n5t8", "tail_n3t16"])
+def test_descriptor_matches_reference_golden(golden_dir, name):
+    from grl_b200 import siamese
+    from oracle import tail_oracle as to
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    n, T = int(g["n"]), int(g["T"])
+    model, sia = build_models()
+    fu, fc = synth.make_tail_input(n, T)
+    out = siamese.eval_descriptor(model, sia, fu.cuda(), fc.cuda())
+    assert out.shape == (n, 6144)
+    # per part: x_uncorr and mean_t x_corr are fp32 row arithmetic; the attention part goes through the split-bf16 GEMM
+    assert rel(out[:, :2048], g["out_feat"][:, :2048]) < 1e-6
+    assert rel(out[:, 4096:], g["out_feat"][:, 4096:]) < 1e-6
+    assert rel(out[:, 2048:4096], g["out_feat"][:, 2048:4096]) < 1e-5
+    assert np.abs(out.cpu().numpy() - g["out_feat"]).max() < 1e-5
+    assert rel(out.mean(0), g["tracklet"]) < 1e-5
+    # reference-signature call: Siamese.self_attention on the model's normalised x_corr
+    p = synth.make_tail_params(10, dtype=torch.float64)
+    xu, xc = to.ref_tail(p, fu.double(), fc.double())
+    att = sia.self_attention(xc.float().cuda())
+    assert att.shape == (n, 2048) and rel(att, g["out_frame"]) < 1e-5
+    sia.train()
+    with pytest.raises(RuntimeError):
+        sia.self_attention(xc.float().cuda())
+    assert set(k for k in sia.state_dict()) >= {"featQ.weight", "featK_bn.running_var", "featV.weight", "classifierlinear.bias"}
+
+
+def test_head_to_descriptor_to_ranking_end_to_end():
+    """layer4 maps -> fused head (eval) -> fused descriptor -> distance -> CMC/mAP, all on the device, vs the oracle chain."""
+    from grl_b200 import evaluator, head, siamese
+    from oracle import eval_oracle as eo
+    from oracle import head_oracle as ho
+    from oracle import tail_oracle as to
+    model, sia = build_models()
+    msd = model.state_dict()
+    for k, v in synth.make_head_params(0).items():
+        msd[k] = v
+    model.load_state_dict(msd)
+    n, T = 6, 4
+    x = synth.make_head_input(n, T, seed=21)
+    with torch.no_grad():
+        fu, fc, *_ = model.head(x.cuda(), n, T)
+        desc = siamese.eval_descriptor(model, sia, fu, fc)
+    p64 = synth.make_head_params(0, dtype=torch.float64)
+    o = ho.ref_forward(p64, x.double(), n, T, False)
+    d64 = to.ref_descriptor(synth.make_tail_params(10, dtype=torch.float64), o["f_uncorr"], o["f_corr"])
+    assert rel(desc, d64) < 1e-4
+    q, g = desc[:2], desc
+    dist = evaluator.cosin_dist(q, g).cpu().numpy()
+    ref = eo.cosin_dist(d64[:2].numpy().astype(np.float32), d64.numpy().astype(np.float32))
+    assert np.abs(dist - ref).max() < 1e-4 * 3.0       # |descriptor|^2 = 3 (three unit-norm parts), descriptors agree to 1e-4 relative
