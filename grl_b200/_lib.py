@@ -90,6 +90,9 @@ _SIGNATURES = {
     "grl_dist_topk_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "grl_dist_topk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "grl_rerank_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "grl_rerank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                             C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "grl_head_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "grl_head_forward": (C.c_int, [C.c_void_p, C.POINTER(HeadParams), C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -244,8 +244,6 @@ class ATTEvaluator(object):
     def evaluate(self, query, gallery, query_loader, gallery_loader, path, visual, rerank):
         if visual:
             raise NotImplementedError("rank visualisation is debug tooling outside the hot path (SURVEY.md §2)")
-        if rerank:
-            raise NotImplementedError("k-reciprocal re-ranking is a 'next' row (SURVEY.md §8(f)-3)")
         qf, q_pids, q_camids = self.extract_feature(query_loader)
         print('Done, obtained {}-by-{} matrix'.format(qf.size(0), qf.size(1)))
         gf, g_pids, g_camids = self.extract_feature(gallery_loader)
@@ -255,4 +253,10 @@ class ATTEvaluator(object):
         print('Done, obtained {}-by-{} matrix'.format(gf.size(0), gf.size(1)))
         print("Computing distance matrix")
         distmat = cosin_dist(qf, gf)                              # stays on the device (no 74 MB D2H, :150)
+        if rerank:                                                # :151-155, all three matrices stay on the device
+            print('Applying person re-ranking ...')
+            from .rerank import re_ranking
+            distmat_qq = pairwise_distance_tensor(qf, qf)
+            distmat_gg = pairwise_distance_tensor(gf, gf)
+            distmat = re_ranking(distmat, distmat_qq, distmat_gg)
         return evaluate_seq(distmat, q_pids, q_camids, g_pids, g_camids, path)

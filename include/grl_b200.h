@@ -114,6 +114,16 @@ size_t grl_dist_topk_workspace_bytes(int nq, int ng, int dim);
 int grl_dist_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k,
                   int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream);
 
+/* k-reciprocal re-ranking: re_ranking(q_g_dist, q_q_dist, g_g_dist, k1, k2, lambda_value)
+ *                                            reid/evaluator/rerank.py:37-104 (called at attevaluator.py:151-155)
+ * q_g [nq][ng], q_q [nq][nq], g_g [ng][ng] fp32 distance matrices -> final_dist [nq][ng] fp32.  Same float32 operation
+ * order as the reference (column-normalised squared distances, k-reciprocal sets with 2/3-overlap expansion, np.sum's
+ * pairwise order, rank-ordered query-expansion mean, ascending-column Jaccard sums); ties in the neighbour ranking go
+ * to the lower index.  Limits: nq + ng <= 65536, 1 <= k1 <= 31, 1 <= k2 <= 32.  Workspace: ~8 bytes x (nq+ng)^2.      */
+size_t grl_rerank_workspace_bytes(int nq, int ng, int k1, int k2);
+int grl_rerank(grl_handle* h, const float* q_g, const float* q_q, const float* g_g, int nq, int ng, int k1, int k2,
+               double lambda_value, float* final_dist, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- GCE + TRL head ------------------------------------------------------------------ */
 /* Parameter block: device pointers to the reference's own state_dict tensors (fp32), in the
  * reference's names (reid/models/basebranch.py:38-50, reid/models/grl_model.py:88-128).

@@ -160,6 +160,25 @@ def tail_fixture(Model, name, n, T):
     print("wrote", name, tuple(out_feat.shape))
 
 
+def rerank_fixture(att, name, nq, ng_extra, dim, seed, k1, k2, lam, noise=0.6):
+    """k-reciprocal re-ranking by the REAL reference (reid/evaluator/rerank.py:37-104) on the three distance matrices
+    ATTEvaluator.evaluate hands it (attevaluator.py:150-155: cosine q-g, L2 q-q and g-g).  The matrices are stored so
+    the restatement and the CUDA path see bit-identical inputs."""
+    from grl_b200 import synth
+    from reid.evaluator.rerank import re_ranking
+    qf, gf, qp, gp, qc, gc = synth.make_eval_set(nq, ng_extra, dim, seed=seed, num_ids=12, noise=noise)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tq, tg = torch.from_numpy(qf), torch.from_numpy(gf)
+        q_g = att.cosin_dist(tq, tg).numpy()
+        q_q = att.pairwise_distance_tensor(tq, tq).numpy()
+        g_g = att.pairwise_distance_tensor(tg, tg).numpy()
+    final = re_ranking(q_g, q_q, g_g, k1=k1, k2=k2, lambda_value=lam)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), nq=nq, ng_extra=ng_extra, dim=dim, seed=seed, k1=k1, k2=k2, lam=lam,
+                        noise=noise, q_g=q_g, q_q=q_q, g_g=g_g, final=final)
+    print("wrote", name, final.shape, final.dtype)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -174,6 +193,9 @@ def main():
     # fewer than max_rank gallery rows, so "num_g < max_rank" (:136-138) cannot be pinned; use max_rank=10.
     eval_fixture(att, eva, "eval_rank10", 20, 100, 32, seed=4, noise=1.0, max_rank=10)
     eval_fixture(att, eva, "eval_ties", 40, 160, 16, seed=5, noise=1.0, quantize=8)  # exact ties
+    rerank_fixture(att, "rerank_k20", 48, 160, 64, seed=11, k1=20, k2=6, lam=0.3)
+    rerank_fixture(att, "rerank_k6", 30, 100, 32, seed=12, k1=6, k2=3, lam=0.5)
+    rerank_fixture(att, "rerank_k5_noqe", 25, 90, 32, seed=13, k1=5, k2=1, lam=0.3)      # k2 == 1 skips :78-83
 
 
 if __name__ == "__main__":
