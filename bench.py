@@ -255,8 +255,16 @@ def run_ours(args):
     lib.grl_set_overlap(h, 3)
     peaks = measured_peaks()
     achieved = g_fl.value / (g_ms.value * 1e-3) / 1e12 if g_ms.value > 0 else 0.0
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01c_gemm_traffic.json")     # written from the committed ncu capture of this command's step
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     roofline = {"bound": "tensor", "kernel": "gemm_bf16x3_kernel (split-bf16 tcgen05/TMEM GEMM, TMA-fed)", "achieved": achieved,
-                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
+                "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's GEMM launches)",
+                "traffic_source": traffic_src,
                 "peak_source": "%s (bf16 dense, sustained)" % peaks["source"],
                 "issued_frac": 3.0 * achieved / peaks["tflops"],
                 "note": "achieved = algorithmic 2*M*N*K per launch / event-timed launch duration, averaged over %d launches of %d "
@@ -351,6 +359,31 @@ def run_ours(args):
         eval_line = {"workload": "MARS-shape eval 1980 x 9330 x 2048: -q.g^T + CMC/mAP (host features in, metrics out)",
                      "queries_per_s": 1980 / dt_e, "ms": dt_e * 1e3, "mAP": float(mAP), "rank1": float(cmc[0])}
 
+    # ---- k-reciprocal re-ranking at MARS shape: host features in, re-ranked distance matrix stays on the device
+    rerank_line = None
+    if not args.no_eval and rank == 0:
+        from grl_b200.rerank import re_ranking
+        qf, gf, qp, gp, qc, gcam = synth.make_eval_set(1980, 7350, 2048, seed=0, noise=4.0)
+        qf_h, gf_h = torch.from_numpy(qf).pin_memory(), torch.from_numpy(gf).pin_memory()
+
+        def rerank_step():
+            q_, g_ = qf_h.to(dev, non_blocking=True), gf_h.to(dev, non_blocking=True)
+            d_ = re_ranking(evaluator.pairwise_distance_tensor(q_, g_), evaluator.pairwise_distance_tensor(q_, q_),
+                            evaluator.pairwise_distance_tensor(g_, g_))
+            return evaluator.evaluate(d_, qp, gp, qc, gcam)
+        rerank_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            cmc_r, mAP_r = rerank_step()
+        torch.cuda.synchronize()
+        dt_r = (time.perf_counter() - t0) / 3
+        rerank_line = {"workload": "MARS-shape re-ranked eval: 3 L2 matrices over 1980 + 9330 rows x 2048-d, k-reciprocal re-ranking "
+                                   "(k1=20, k2=6, lambda=0.3), CMC/mAP (host features in, metrics out)",
+                       "queries_per_s": 1980 / dt_r, "ms": dt_r * 1e3, "mAP": float(mAP_r), "rank1": float(cmc_r[0])}
+        del qf_h, gf_h
+        torch.cuda.empty_cache()
+
     # ---- gallery-sharded retrieval (configs[4]): 10k queries x 1M gallery rows x 2048-d, top-100, gallery split over the ranks,
     #      one NCCL all-gather of the candidates + merge.  Queries come from pinned host memory, results go back to the host.
     retr = None
@@ -389,6 +422,18 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline()
+        if rerank_line is not None:
+            # the reference's re_ranking (oracle restatement, bit-identical to it) on a BOUNDED sample: 200 queries + 1,000 gallery rows;
+            # its dense N x N stages grow with N^2, so the full 11,310-row problem is ~90x this time
+            from oracle import eval_oracle as eo
+            from oracle import rerank_oracle as ro
+            qf_s, gf_s, *_ = synth.make_eval_set(200, 800, 256, seed=0, noise=1.2)
+            mats = (eo.pairwise_distance(qf_s, gf_s), eo.pairwise_distance(qf_s, qf_s), eo.pairwise_distance(gf_s, gf_s))
+            t0 = time.perf_counter()
+            ro.re_ranking(*mats)
+            dt_c = time.perf_counter() - t0
+            rerank_line["cpu_port"] = {"queries_per_s": 200 / dt_c, "cores": 1, "kind": "port",
+                                       "sample": "re_ranking only, 200 queries + 1,000 gallery rows (N=1,200) in %.2f s" % dt_c}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -405,6 +450,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if eval_line is not None:
             line["eval"] = eval_line
+        if rerank_line is not None:
+            line["rerank"] = rerank_line
         if retr is not None:
             line["retrieval"] = retr
         print(json.dumps(line), flush=True)
