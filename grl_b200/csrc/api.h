@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -70,6 +71,14 @@ struct Operand {
 // D[z] = A[z] * B[z]^T with the fused epilogue `epi`; bn = 0 picks the N tile automatically.
 int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, const Operand& A, const Operand& B,
                 GemmEpi epi, int bn);
+
+// D = A * B^T with ONE fp16 plane per operand (K-major, one MMA per k-step): coarse pass of the retrieval search.
+int gemm_launch_f16(grl_handle* h, cudaStream_t st, int M, int N, int K, const __half* A, long long lda, const __half* B,
+                    long long ldb, GemmEpi epi, int bn);
+
+// The same contraction on 256 x 256 tiles (coarse_gemm.cuh) when the problem is large enough, else gemm_launch_f16.
+int coarse_gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, const __half* A, long long lda, const __half* B,
+                       long long ldb, GemmEpi epi);
 
 // fp32 [rows][cols] (ld_src) -> bf16 hi/lo planes [rows][cols] (ld_dst); optional per-row scale.
 int split_planes(grl_handle* h, cudaStream_t st, const float* src, long long ld_src, __nv_bfloat16* hi,

@@ -1,0 +1,251 @@
+// grl_b200 — coarse-pass GEMM of the retrieval search (sm_100a): D = A * B^T, one fp16 plane per operand.
+//
+// With a single MMA per k-step the 128 x 256 tile of gemm.cuh is bound by L2 -> shared-memory traffic (48 KB per 4.2 MFLOP,
+// 85 FLOP/B against ~6300 B/clk of L2), not by the tensor pipe.  This kernel computes a 256 x 256 tile per CTA instead: one
+// 256-row A box and one 256-row B box per k-block (64 KB per 8.4 MFLOP, 128 FLOP/B), two UMMA 128 x 256 x 16 per k-step into
+// the two halves of TMEM (512 columns = the whole tensor memory, so the accumulator is single-buffered and the epilogue is
+// spread over EIGHT warps, two per TMEM lane quadrant, to keep its exposed time short).
+//   warp 0    TMA producer (3 stages of 64 KB)          warp 1    MMA issuer, TMEM owner
+//   warps 2-9 epilogue: scale by the per-row/column power-of-two factors, optional squared-L2 form, top-k candidate filter
+//             (the same contract as GemmEpi::tk_* in gemm.cuh), fp32 tile store
+#pragma once
+#include "gemm.cuh"
+
+namespace grl {
+
+constexpr int CG_BM = 256, CG_BN = 256, CG_BK = 64, CG_STAGES = 3;
+constexpr int CG_THREADS = 320;
+constexpr int CG_A_BYTES = CG_BM * CG_BK * 2, CG_B_BYTES = CG_BN * CG_BK * 2;
+constexpr int CG_STAGE_BYTES = CG_A_BYTES + CG_B_BYTES;
+constexpr int CG_COLBUF_BYTES = 2 * 2 * CG_BN * 4;   // double-buffered column scales and norms of the current tile
+constexpr int CG_SMEM_BYTES = CG_STAGES * CG_STAGE_BYTES + 1024 + 256 + CG_COLBUF_BYTES;
+
+struct CoarseGemmParams {
+    CUtensorMap ta, tb;
+    int M, N, K;
+    int num_m_tiles, num_n_tiles, group_m;
+    GemmEpi epi;            // uses C/ldc, alpha, row_scale, col_scale, mode (0 | 2), row_norm, col_norm, tk_*
+};
+
+__global__ void __launch_bounds__(CG_THREADS, 1) coarse_gemm_kernel(const __grid_constant__ CoarseGemmParams p) {
+    extern __shared__ uint8_t cg_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(cg_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CG_STAGES * CG_STAGE_BYTES);
+    uint64_t* full = bars;                       // [STAGES]
+    uint64_t* empty = bars + CG_STAGES;          // [STAGES]
+    uint64_t* tmem_full = bars + 2 * CG_STAGES;  // [1]
+    uint64_t* tmem_empty = tmem_full + 1;        // [1]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+    float* colbuf = reinterpret_cast<float*>(smem + CG_STAGES * CG_STAGE_BYTES + 256);   // [2][2][CG_BN]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.ta); tma_prefetch_desc(&p.tb);
+        for (int s = 0; s < CG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1); mbar_init(tmem_empty, 8);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int num_kb = (p.K + CG_BK - 1) / CG_BK;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    // same rasterisation as gemm.cuh: groups of group_m row tiles sweep all column tiles
+    auto coords = [&](int tile, int& m_tile, int& n_tile) {
+        const int per_group = p.group_m * p.num_n_tiles;
+        const int mg = tile / per_group;
+        const int rr = tile - mg * per_group;
+        const int gsize = min(p.group_m, p.num_m_tiles - mg * p.group_m);
+        n_tile = rr / gsize;
+        m_tile = mg * p.group_m + (rr - n_tile * gsize);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m_tile, n_tile;
+                coords(tile, m_tile, n_tile);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * CG_STAGE_BYTES;
+                    uint8_t* sB = sA + CG_A_BYTES;
+                    mbar_arrive_expect_tx(&full[stage], CG_STAGE_BYTES);
+                    tma_load_3d(sA, &p.ta, &full[stage], kb * CG_BK, m_tile * CG_BM, 0);
+                    tma_load_3d(sB, &p.tb, &full[stage], kb * CG_BK, n_tile * CG_BN, 0);
+                    if (++stage == CG_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(128, CG_BN, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                mbar_wait(tmem_empty, (it & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const uint32_t sA = smem_u32(smem + stage * CG_STAGE_BYTES);
+                    const uint32_t sB = sA + CG_A_BYTES;
+                    const uint64_t dA0 = make_smem_desc(sA, 16, 1024), dA1 = make_smem_desc(sA + 128 * 128, 16, 1024);
+                    const uint64_t dB = make_smem_desc(sB, 16, 1024);
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < CG_BK / 16; ++k) {
+                        umma_bf16(tmem_base, dA0 + k * 2, dB + k * 2, idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16(tmem_base + 256, dA1 + k * 2, dB + k * 2, idesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (kb == num_kb - 1) umma_commit(tmem_full);
+                    if (++stage == CG_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        const GemmEpi& e = p.epi;
+        const int quad = warp & 3;                       // TMEM lane quadrant of this warp
+        const int half = (warp - 2) >> 2;                // 0: rows 0-127 of the tile (TMEM columns 0-255), 1: rows 128-255
+        const int row_in_tile = half * 128 + quad * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            int m_tile, n_tile;
+            coords(tile, m_tile, n_tile);
+            const int n0 = n_tile * CG_BN;
+            const int grow = m_tile * CG_BM + row_in_tile;
+            const bool row_ok = grow < p.M;
+            float rscale = 1.f, rnorm = 0.f, rthresh = 0.f;
+            if (row_ok) {
+                if (e.row_scale) rscale = e.row_scale[grow];
+                if (e.mode != 0) rnorm = e.row_norm[grow];
+                if (e.tk_cand) rthresh = (e.tk_cnt[grow] > e.tk_cap) ? -__int_as_float(0x7f800000) : e.tk_thresh[grow];
+            }
+            float* c_row = e.C ? e.C + (long long)grow * e.ldc : nullptr;
+            // column scales / norms of this tile -> shared memory while the MMAs of the tile are still running
+            float* cs_s = colbuf + (it & 1) * 2 * CG_BN;
+            float* cn_s = cs_s + CG_BN;
+            {
+                const int t = threadIdx.x - 64, col = n0 + t;     // 256 epilogue threads, one column each
+                cs_s[t] = (e.col_scale && col < p.N) ? __ldg(e.col_scale + col) : 1.f;
+                cn_s[t] = (e.mode != 0 && col < p.N) ? __ldg(e.col_norm + col) : 0.f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(tmem_full, it & 1);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(half * 256);
+            const int nchunks = min(CG_BN / 32, (p.N - n0 + 31) / 32);
+            float nxt[32];
+            tmem_ld_32x32(t_row, nxt);
+            tmem_ld_wait();
+            uint32_t pmask = 0;                           // candidate reservation in flight (issued one chunk earlier)
+            int ppos = 0, pcol0 = 0;
+#pragma unroll 1
+            for (int c = 0; c < nchunks; ++c) {
+                const int col0 = n0 + c * 32;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = nxt[j];
+                if (c + 1 < nchunks) tmem_ld_32x32(t_row + uint32_t((c + 1) * 32), nxt);   // in flight while this chunk is processed
+                if (col0 + 32 <= p.N) {
+                    // ---- full chunk: vectorised uniform loads, no per-element bounds checks
+                    {
+                        const float4* cs4 = reinterpret_cast<const float4*>(cs_s + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 s4 = cs4[j];
+                            v[4 * j] *= s4.x; v[4 * j + 1] *= s4.y; v[4 * j + 2] *= s4.z; v[4 * j + 3] *= s4.w;
+                        }
+                    }
+                    if (e.mode != 0) {
+                        const float4* cn4 = reinterpret_cast<const float4*>(cn_s + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 n4 = cn4[j];
+                            v[4 * j] = fmaxf(rnorm + n4.x - 2.f * (v[4 * j] * rscale), 1e-12f);
+                            v[4 * j + 1] = fmaxf(rnorm + n4.y - 2.f * (v[4 * j + 1] * rscale), 1e-12f);
+                            v[4 * j + 2] = fmaxf(rnorm + n4.z - 2.f * (v[4 * j + 2] * rscale), 1e-12f);
+                            v[4 * j + 3] = fmaxf(rnorm + n4.w - 2.f * (v[4 * j + 3] * rscale), 1e-12f);
+                        }
+                    } else {
+                        const float ar = e.alpha * rscale;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= ar;
+                    }
+                    // the previous chunk's reservation has had a whole chunk to come back: append its column numbers now
+                    while (pmask && ppos < e.tk_cap) {
+                        const int j = __ffs(pmask) - 1;
+                        pmask &= pmask - 1;
+                        e.tk_cand[(long long)grow * e.tk_cap + ppos++] = (uint32_t)(pcol0 + j);
+                    }
+                    // Branch-free pass mask; once the lists have warmed up a lane sees a candidate in a few percent of its chunks.
+                    // One atomic per row and chunk reserves the slots; its latency hides behind the tile stores below, and only
+                    // column numbers are appended (the consumer reads the values back from the tile).
+                    pmask = 0;
+                    if (e.tk_cand) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) pmask |= (v[j] <= rthresh) ? (1u << j) : 0u;
+                        if (!row_ok) pmask = 0;
+                        pcol0 = col0;
+                        if (pmask) ppos = atomicAdd(e.tk_cnt + grow, __popc(pmask));
+                    }
+                    if (row_ok && c_row) {
+                        float4* d4 = reinterpret_cast<float4*>(c_row + col0);     // ldc % 4 == 0 and 16-byte aligned C (checked on the host)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                } else {
+                    while (pmask && ppos < e.tk_cap) {       // pending reservation of the previous (full) chunk
+                        const int j = __ffs(pmask) - 1;
+                        pmask &= pmask - 1;
+                        e.tk_cand[(long long)grow * e.tk_cap + ppos++] = (uint32_t)(pcol0 + j);
+                    }
+                    pmask = 0;
+                    // ---- ragged last chunk of the matrix
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const bool ok = col0 + j < p.N;
+                        float x = v[j] * (ok ? cs_s[c * 32 + j] : 1.f);
+                        if (e.mode != 0) x = fmaxf(rnorm + cn_s[c * 32 + j] - 2.f * (x * rscale), 1e-12f);
+                        else x *= e.alpha * rscale;
+                        v[j] = x;
+                    }
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {        // fully unrolled: v[] must stay in registers
+                            if (col0 + j < p.N) {
+                                if (e.tk_cand && v[j] <= rthresh) {
+                                    const int pos1 = atomicAdd(e.tk_cnt + grow, 1);
+                                    if (pos1 < e.tk_cap) e.tk_cand[(long long)grow * e.tk_cap + pos1] = (uint32_t)(col0 + j);
+                                }
+                                if (c_row) c_row[col0 + j] = v[j];
+                            }
+                        }
+                    }
+                }
+                tmem_ld_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);          // TMEM is drained: the next tile's MMAs may start
+            while (pmask && ppos < e.tk_cap) {
+                const int j = __ffs(pmask) - 1;
+                pmask &= pmask - 1;
+                e.tk_cand[(long long)grow * e.tk_cap + ppos++] = (uint32_t)(pcol0 + j);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace grl

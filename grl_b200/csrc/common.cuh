@@ -134,6 +134,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// the same with A = B = fp16 (format code 0)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |
+           (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
 // ---------------------------------------------------------------- bf16 hi/lo split
 // x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits, fp32 exponent range.
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {

@@ -1,6 +1,7 @@
 // grl_b200 — host side of the split-bf16 tcgen05 GEMM: TMA tensor maps, tile choice, launch,
 // the fp32 -> bf16 hi/lo split kernels, handle lifecycle and the grl_gemm_bf16x3 C entry point.
 #include "api.h"
+#include "coarse_gemm.cuh"
 
 #include <vector>
 
@@ -106,8 +107,9 @@ int split_planes_transposed(grl_handle* h, cudaStream_t st, const float* src, lo
 }
 
 // ------------------------------------------------------------------ tensor maps
-static int make_tmap(grl_handle* h, CUtensorMap* map, const __nv_bfloat16* base, long long ld, long long bstride,
-                     int mn_major, long long rows, long long K, int batch, int tile_rows) {
+static int make_tmap(grl_handle* h, CUtensorMap* map, const void* base, long long ld, long long bstride,
+                     int mn_major, long long rows, long long K, int batch, int tile_rows,
+                     CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 7) || (batch > 1 && (bstride & 7)))
         return set_error(h, GRL_EINVAL, "gemm operand must be 16-byte aligned with ld %% 8 == 0 (ld=%lld)", ld);
     cuuint64_t dims[3];
@@ -126,7 +128,7 @@ static int make_tmap(grl_handle* h, CUtensorMap* map, const __nv_bfloat16* base,
     box[2] = 1;
     strides[0] = (cuuint64_t)ld * 2;
     strides[1] = (cuuint64_t)((batch > 1) ? bstride : outer * ld) * 2;
-    CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(base), dims, strides, box,
+    CUresult r = h->encode(map, dtype, 3, const_cast<void*>(base), dims, strides, box,
                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -135,12 +137,12 @@ static int make_tmap(grl_handle* h, CUtensorMap* map, const __nv_bfloat16* base,
     return GRL_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int PLANES = 3>
 static int launch_variant(grl_handle* h, cudaStream_t st, const GemmParams& p, int grid) {
-    auto kern = gemm_bf16x3_kernel<BN, A_MN, B_MN>;
+    auto kern = gemm_bf16x3_kernel<BN, A_MN, B_MN, PLANES>;
     static bool configured = false;   // per instantiation
     if (!configured) {
-        GRL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
+        GRL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, PLANES>::SMEM_BYTES));
         configured = true;
     }
     grl_prof_rec rec;
@@ -150,7 +152,7 @@ static int launch_variant(grl_handle* h, cudaStream_t st, const GemmParams& p, i
         rec.flops = 2.0 * p.M * (double)p.N * p.K * p.batch;
         GRL_CUDA(h, cudaEventRecord(rec.e0, st));
     }
-    kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(p);
+    kern<<<grid, GEMM_THREADS, GemmCfg<BN, PLANES>::SMEM_BYTES, st>>>(p);
     GRL_LAUNCH_CHECK(h);
     if (h->prof_on) {
         GRL_CUDA(h, cudaEventRecord(rec.e1, st));
@@ -193,6 +195,70 @@ int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, 
     if (A.mn_major) return launch_variant<128, true, true>(h, st, p, grid);
     if (B.mn_major) return launch_variant<128, false, true>(h, st, p, grid);
     return launch_variant<128, false, false>(h, st, p, grid);
+}
+
+// D = A * B^T with ONE fp16 plane per operand (K-major both, no batch): the coarse pass of the retrieval search.
+int gemm_launch_f16(grl_handle* h, cudaStream_t st, int M, int N, int K, const __half* A, long long lda, const __half* B,
+                    long long ldb, GemmEpi epi, int bn) {
+    if (M <= 0 || N <= 0 || K <= 0) return set_error(h, GRL_EINVAL, "gemm_f16: empty problem %dx%dx%d", M, N, K);
+    const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    if (bn == 0) {
+        const long long t256 = (long long)m_tiles * ((N + 255) / 256);
+        bn = (N > 128 && t256 >= (long long)h->num_sms * 3 / 4) ? 256 : 128;
+    }
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K; p.batch = 1;
+    p.num_m_tiles = m_tiles;
+    p.num_n_tiles = (N + bn - 1) / bn;
+    p.group_m = p.num_m_tiles > 32 ? 16 : p.num_m_tiles;
+    p.epi = epi;
+    GRL_TRY(make_tmap(h, &p.ta_hi, A, lda, 0, 0, M, K, 1, GEMM_BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
+    GRL_TRY(make_tmap(h, &p.tb_hi, B, ldb, 0, 0, N, K, 1, bn, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
+    p.ta_lo = p.ta_hi; p.tb_lo = p.tb_hi;
+    const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
+    const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    if (bn == 256) return launch_variant<256, false, false, 1>(h, st, p, grid);
+    return launch_variant<128, false, false, 1>(h, st, p, grid);
+}
+
+// The 256 x 256-tile coarse GEMM (coarse_gemm.cuh); falls back to the 128-row single-plane variant for small problems.
+int coarse_gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, const __half* A, long long lda, const __half* B,
+                       long long ldb, GemmEpi epi) {
+    const bool aligned = !epi.C || ((reinterpret_cast<uintptr_t>(epi.C) & 15) == 0 && (epi.ldc & 3) == 0);
+    const bool aligned_cols = (!epi.col_scale || (reinterpret_cast<uintptr_t>(epi.col_scale) & 15) == 0) &&
+                              (!epi.col_norm || (reinterpret_cast<uintptr_t>(epi.col_norm) & 15) == 0);
+    if (M < 1024 || N < 1024 || !aligned || !aligned_cols) return gemm_launch_f16(h, st, M, N, K, A, lda, B, ldb, epi, 0);
+    CoarseGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K;
+    p.num_m_tiles = (M + CG_BM - 1) / CG_BM;
+    p.num_n_tiles = (N + CG_BN - 1) / CG_BN;
+    p.group_m = p.num_m_tiles > 16 ? 8 : p.num_m_tiles;
+    p.epi = epi;
+    GRL_TRY(make_tmap(h, &p.ta, A, lda, 0, 0, M, K, 1, CG_BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
+    GRL_TRY(make_tmap(h, &p.tb, B, ldb, 0, 0, N, K, 1, CG_BN, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
+    static bool configured = false;
+    if (!configured) {
+        GRL_CUDA(h, cudaFuncSetAttribute(coarse_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_BYTES));
+        configured = true;
+    }
+    const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
+    const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    grl_prof_rec rec;
+    if (h->prof_on) {
+        GRL_CUDA(h, cudaEventCreate(&rec.e0));
+        GRL_CUDA(h, cudaEventCreate(&rec.e1));
+        rec.flops = 2.0 * M * (double)N * K;
+        GRL_CUDA(h, cudaEventRecord(rec.e0, st));
+    }
+    coarse_gemm_kernel<<<grid, CG_THREADS, CG_SMEM_BYTES, st>>>(p);
+    GRL_LAUNCH_CHECK(h);
+    if (h->prof_on) {
+        GRL_CUDA(h, cudaEventRecord(rec.e1, st));
+        h->prof->recs.push_back(rec);
+    }
+    return GRL_OK;
 }
 
 }  // namespace grl

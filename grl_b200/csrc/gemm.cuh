@@ -46,17 +46,19 @@ struct GemmEpi {
     long long rs_bstride;
     const float* col_bias;
     long long cb_bstride;
+    const float* col_scale;   // [N] or NULL: v *= col_scale[n] before everything else (per-row power-of-two scales of fp16 operands)
     const float* grp_bias;
     int grp_rows;
     long long ld_gb;
     int relu;
     int accumulate;           // C += v (read-modify-write)
-    int mode;                 // 0 plain, 1 L2: v = sqrt(max(row_norm[m] + col_norm[n] - 2*acc, 1e-12))
+    int mode;                 // 0 plain, 1 L2: v = sqrt(max(row_norm[m] + col_norm[n] - 2*acc, 1e-12)), 2: the same without the sqrt
     const float* row_norm;
     const float* col_norm;
-    // ---- top-k candidate filter (retrieval): every stored value v <= tk_thresh[m] is appended, as a (distance, global column)
-    //      key, to row m's candidate list (capacity tk_cap; tk_cnt keeps counting past it so the consumer sees the overflow) ----
-    unsigned long long* tk_cand;
+    // ---- top-k candidate filter (retrieval): the column number (within this GEMM's N) of every stored value v <= tk_thresh[m]
+    //      is appended to row m's candidate list (capacity tk_cap; tk_cnt keeps counting past it so the consumer sees the
+    //      overflow); the consumer reads the values back from C ----
+    uint32_t* tk_cand;
     int* tk_cnt;
     const float* tk_thresh;
     int tk_cap;
@@ -91,19 +93,21 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int t
     m_tile = mg * p.group_m + (rr - n_tile * gsize);
 }
 
-template <int BN>
+// PLANES = 3: split-bf16 (hi and lo planes, three MMAs per k-step).  PLANES = 1: one fp16 plane per operand, one MMA per
+// k-step -- the coarse pass of the retrieval search (eval.cu), whose candidates are re-scored exactly afterwards.
+template <int BN, int PLANES = 3>
 struct GemmCfg {
-    static constexpr int STAGES = (BN == 256) ? 2 : 3;
+    static constexpr int STAGES = (PLANES == 1) ? ((BN == 256) ? 4 : 6) : ((BN == 256) ? 2 : 3);
     static constexpr int A_PLANE = GEMM_BM * GEMM_BK * 2;   // bytes per A plane per stage (16 KB)
     static constexpr int B_PLANE = BN * GEMM_BK * 2;        // 16 / 32 KB
-    static constexpr int STAGE_BYTES = 2 * (A_PLANE + B_PLANE);
+    static constexpr int STAGE_BYTES = (PLANES == 1 ? 1 : 2) * (A_PLANE + B_PLANE);
     static constexpr int TMEM_COLS = 2 * BN;                // two accumulator stages
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int PLANES = 3>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, PLANES>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -164,6 +168,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
                     } else {
                         tma_load_3d(sB_hi, &p.tb_hi, &full_hi[stage], k0, n0, z);
                     }
+                    if (PLANES == 1) {
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full_lo[stage], Cfg::A_PLANE + Cfg::B_PLANE);
                     if (A_MN) {
 #pragma unroll
@@ -184,7 +192,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            constexpr uint32_t idesc = (PLANES == 1) ? make_idesc_f16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0)
+                                                     : make_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
             // K-major  SW128: 8-row groups 1024 B apart (SBO); LBO unused.   k-step (16 elems) = +32 B
             // MN-major SW128: 64-element MN atoms BK*128 B apart (LBO), 8-row k groups 1024 B apart (SBO); k-step = 16 rows = +2048 B
             constexpr uint32_t a_lbo = A_MN ? GEMM_BK * 128 : 16, b_lbo = B_MN ? GEMM_BK * 128 : 16;
@@ -209,12 +218,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k)
                         umma_bf16(d_tmem, dA_hi + k * a_kstep, dB_hi + k * b_kstep, idesc, (kb | k) ? 1u : 0u);
-                    mbar_wait(&full_lo[stage], phase);
-                    tc_fence_after();
+                    if (PLANES == 3) {
+                        mbar_wait(&full_lo[stage], phase);
+                        tc_fence_after();
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        umma_bf16(d_tmem, dA_lo + k * a_kstep, dB_hi + k * b_kstep, idesc, 1u);
-                        umma_bf16(d_tmem, dA_hi + k * a_kstep, dB_lo + k * b_kstep, idesc, 1u);
+                        for (int k = 0; k < GEMM_BK / 16; ++k) {
+                            umma_bf16(d_tmem, dA_lo + k * a_kstep, dB_hi + k * b_kstep, idesc, 1u);
+                            umma_bf16(d_tmem, dA_hi + k * a_kstep, dB_lo + k * b_kstep, idesc, 1u);
+                        }
                     }
                     umma_commit(&empty[stage]);                 // smem stage reusable once these MMAs retire
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
             float rscale = 1.f, rnorm = 0.f, rthresh = 0.f;
             if (row_ok) {
                 if (e.row_scale) rscale = e.row_scale[z * e.rs_bstride + grow];
-                if (e.mode == 1) rnorm = e.row_norm[grow];
+                if (e.mode != 0) rnorm = e.row_norm[grow];
                 if (e.tk_cand)      // a row whose list already overflowed is rescanned by the consumer anyway: stop appending
                     rthresh = (e.tk_cnt[grow] > e.tk_cap) ? -__int_as_float(0x7f800000) : e.tk_thresh[grow];
             }
@@ -259,11 +270,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
                 tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN + c * 32), v);
                 tmem_ld_wait();
                 const bool full_chunk = col0 + 32 <= p.N;
-                if (e.mode == 1) {
+                if (e.col_scale) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= (full_chunk || col0 + j < p.N) ? __ldg(e.col_scale + col0 + j) : 0.f;
+                }
+                if (e.mode != 0) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float cn = (col0 + j < p.N) ? e.col_norm[col0 + j] : 0.f;
-                        v[j] = sqrtf(fmaxf(rnorm + cn - 2.f * v[j], 1e-12f));
+                        const float sq = fmaxf(rnorm + cn - 2.f * (v[j] * rscale), 1e-12f);
+                        v[j] = (e.mode == 1) ? sqrtf(sq) : sq;
                     }
                 } else {
 #pragma unroll
@@ -282,14 +298,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
                 }
-                // ---- top-k candidates: almost every distance fails this one compare once the lists have warmed up ----
-                if (e.tk_cand && row_ok) {
+                // ---- top-k candidates: a branch-free pass mask, then ONE atomic per row and chunk reserves the slots ----
+                if (e.tk_cand) {
+                    uint32_t mask = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (v[j] <= rthresh && (full_chunk || col0 + j < p.N)) {
-                            const int pos = atomicAdd(e.tk_cnt + grow, 1);
-                            if (pos < e.tk_cap)
-                                e.tk_cand[(long long)grow * e.tk_cap + pos] = make_key(v[j], (uint32_t)(e.tk_idx_base + col0 + j));
+                    for (int j = 0; j < 32; ++j) mask |= (v[j] <= rthresh && (full_chunk || col0 + j < p.N)) ? (1u << j) : 0u;
+                    if (!row_ok) mask = 0;
+                    if (mask) {
+                        int pos = atomicAdd(e.tk_cnt + grow, __popc(mask));
+                        while (mask && pos < e.tk_cap) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            e.tk_cand[(long long)grow * e.tk_cap + pos++] = (uint32_t)(col0 + j);
                         }
                     }
                 }

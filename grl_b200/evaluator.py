@@ -148,18 +148,23 @@ def shard_bounds(num_gallery, world_size, rank):
     return lo, base + (1 if rank < rem else 0)
 
 
-def retrieve_topk(qf, gf, k, idx_base=0, metric=0):
-    """k nearest rows of this gallery shard per query (grl_dist_topk).  Returns CUDA (dist f32 [nq,k], index i64 [nq,k])."""
+def _padded_features(qf, gf):
     qf = _as_cuda_f32(qf)
     gf = _as_cuda_f32(gf, qf.device)
-    nq, ng, dim = qf.size(0), gf.size(0), qf.size(1)
-    if gf.size(1) != dim:
+    if gf.size(1) != qf.size(1):
         raise RuntimeError("size mismatch, qf %s vs gf %s" % (tuple(qf.shape), tuple(gf.shape)))
-    if dim % 8:
-        pad = 8 - dim % 8
+    if qf.size(1) % 8:      # TMA rows must be 16-byte multiples: zero-pad the feature axis (does not change any distance)
+        pad = 8 - qf.size(1) % 8
         qf = torch.nn.functional.pad(qf, (0, pad))
         gf = torch.nn.functional.pad(gf, (0, pad))
-        dim += pad
+    return qf, gf
+
+
+def retrieve_topk(qf, gf, k, idx_base=0, metric=0):
+    """k nearest rows of this gallery shard per query (grl_dist_topk: coarse fp16 tensor-core pass + exact fp32 re-score).
+    Returns CUDA (dist f32 [nq,k], index i64 [nq,k]), the stable top-k of the fixed-order fp32 distances."""
+    qf, gf = _padded_features(qf, gf)
+    nq, ng, dim = qf.size(0), gf.size(0), qf.size(1)
     lib = _lib.load_library()
     with torch.cuda.device(qf.device):
         h = _lib.get_handle(qf.device)
@@ -187,21 +192,114 @@ def merge_topk(all_d, all_i):
     return out_d, out_i
 
 
-def sharded_retrieve(qf, gf_local, k, idx_base, group=None, metric=0, local_search=retrieve_topk, merge=merge_topk):
-    """One search over a gallery sharded across the ranks of `group` (torch.distributed; NCCL on B200).
+class CudaSearchStages(object):
+    """The per-rank stages of the two-stage exact search (include/grl_b200.h: grl_coarse_topk, grl_rescore, grl_topk_finalize,
+    grl_exact_topk, grl_topk_merge).  sharded_retrieve takes the stages as an object only so that its collectives can be
+    exercised on CPU with gloo in tests (which plug in a numpy restatement)."""
 
-    `local_search` / `merge` are the per-rank kernels (CUDA by default); they are parameters only so that the
-    rendezvous / gather / merge plumbing can be exercised on CPU with gloo in tests."""
+    @staticmethod
+    def kprime(k):
+        return int(_lib.load_library().grl_topk_kprime(k))
+
+    @staticmethod
+    def coarse(qf, gf, kp, idx_base, metric):
+        nq, ng, dim = qf.size(0), gf.size(0), qf.size(1)
+        lib = _lib.load_library()
+        with torch.cuda.device(qf.device):
+            h = _lib.get_handle(qf.device)
+            cd = torch.empty((nq, kp), dtype=torch.float32, device=qf.device)
+            ci = torch.empty((nq, kp), dtype=torch.int64, device=qf.device)
+            gmax2 = torch.zeros(1, dtype=torch.float32, device=qf.device)
+            ws_bytes = lib.grl_coarse_topk_workspace_bytes(nq, ng, dim)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qf.device)
+            _lib.check(h, lib.grl_coarse_topk(h, metric, qf.data_ptr(), gf.data_ptr(), nq, ng, dim, kp, idx_base, cd.data_ptr(),
+                                              ci.data_ptr(), gmax2.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(qf.device)),
+                       "grl_coarse_topk")
+        return cd, ci, gmax2
+
+    merge = staticmethod(merge_topk)
+
+    @staticmethod
+    def rescore(qf, gf, cand_i, idx_base, metric):
+        nq, ng, dim = qf.size(0), gf.size(0), qf.size(1)
+        lib = _lib.load_library()
+        with torch.cuda.device(qf.device):
+            h = _lib.get_handle(qf.device)
+            ed = torch.empty(cand_i.shape, dtype=torch.float32, device=qf.device)
+            _lib.check(h, lib.grl_rescore(h, metric, qf.data_ptr(), gf.data_ptr(), nq, ng, dim, idx_base, cand_i.data_ptr(),
+                                          cand_i.size(1), ed.data_ptr(), _lib.stream_ptr(qf.device)), "grl_rescore")
+        return ed
+
+    @staticmethod
+    def finalize(qf, cd, ci, ed, gmax2, k, metric):
+        nq, dim, kp = qf.size(0), qf.size(1), ci.size(1)
+        lib = _lib.load_library()
+        with torch.cuda.device(qf.device):
+            h = _lib.get_handle(qf.device)
+            top_d = torch.empty((nq, k), dtype=torch.float32, device=qf.device)
+            top_i = torch.empty((nq, k), dtype=torch.int64, device=qf.device)
+            flags = torch.empty(nq, dtype=torch.int32, device=qf.device)
+            nflag = torch.zeros(1, dtype=torch.int32, device=qf.device)
+            _lib.check(h, lib.grl_topk_finalize(h, metric, qf.data_ptr(), nq, dim, cd.data_ptr(), ci.data_ptr(), ed.data_ptr(), kp,
+                                                gmax2.data_ptr(), k, top_d.data_ptr(), top_i.data_ptr(), flags.data_ptr(),
+                                                nflag.data_ptr(), _lib.stream_ptr(qf.device)), "grl_topk_finalize")
+        return top_d, top_i, flags
+
+    @staticmethod
+    def exact(qf, gf, k, idx_base, metric):
+        nq, ng, dim = qf.size(0), gf.size(0), qf.size(1)
+        lib = _lib.load_library()
+        with torch.cuda.device(qf.device):
+            h = _lib.get_handle(qf.device)
+            top_d = torch.empty((nq, k), dtype=torch.float32, device=qf.device)
+            top_i = torch.empty((nq, k), dtype=torch.int64, device=qf.device)
+            ws_bytes = lib.grl_exact_topk_workspace_bytes(nq, ng, dim)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qf.device)
+            _lib.check(h, lib.grl_exact_topk(h, metric, qf.data_ptr(), gf.data_ptr(), nq, ng, dim, k, idx_base, top_d.data_ptr(),
+                                             top_i.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(qf.device)), "grl_exact_topk")
+        return top_d, top_i
+
+
+def sharded_retrieve(qf, gf_local, k, idx_base, group=None, metric=0, stages=None):
+    """One search over a gallery sharded across the ranks of `group` (torch.distributed; NCCL over NVLink on B200).
+
+    Every rank ranks its shard by the coarse tensor-core distance and keeps K' candidates per query; one all-gather + merge
+    gives the global coarse K'; every rank re-scores (fixed-order fp32) the candidates whose gallery rows it owns and an
+    all-reduce (sum of disjoint contributions) assembles them; finalisation sorts by exact distance and proves completeness
+    per query.  Queries without a proof (rare: near-duplicate galleries) are searched by brute force per shard and merged.
+    The result is identical on every rank and for every shard count."""
     import torch.distributed as dist
-    d, i = local_search(qf, gf_local, k, idx_base=idx_base, metric=metric)
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return d, i
-    world = dist.get_world_size(group)
-    all_d = [torch.empty_like(d) for _ in range(world)]
-    all_i = [torch.empty_like(i) for _ in range(world)]
-    dist.all_gather(all_d, d.contiguous(), group=group)
-    dist.all_gather(all_i, i.contiguous(), group=group)
-    return merge(torch.stack(all_d), torch.stack(all_i))
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if stages is None:
+        if world == 1:
+            return retrieve_topk(qf, gf_local, k, idx_base=idx_base, metric=metric)
+        stages = CudaSearchStages
+        qf, gf_local = _padded_features(qf, gf_local)
+    kp = stages.kprime(k)
+    cd, ci, gmax2 = stages.coarse(qf, gf_local, kp, idx_base, metric)
+    if world > 1:
+        all_d = [torch.empty_like(cd) for _ in range(world)]
+        all_i = [torch.empty_like(ci) for _ in range(world)]
+        dist.all_gather(all_d, cd.contiguous(), group=group)
+        dist.all_gather(all_i, ci.contiguous(), group=group)
+        dist.all_reduce(gmax2, op=dist.ReduceOp.MAX, group=group)
+        cd, ci = stages.merge(torch.stack(all_d), torch.stack(all_i))
+    ed = stages.rescore(qf, gf_local, ci, idx_base, metric)
+    if world > 1:
+        dist.all_reduce(ed, op=dist.ReduceOp.SUM, group=group)       # every candidate is owned by exactly one rank
+    top_d, top_i, flags = stages.finalize(qf, cd, ci, ed, gmax2, k, metric)
+    rows = torch.nonzero(flags).flatten()                            # identical on every rank (same inputs to finalize)
+    if rows.numel():
+        d_x, i_x = stages.exact(qf[rows].contiguous(), gf_local, k, idx_base, metric)
+        if world > 1:
+            all_d = [torch.empty_like(d_x) for _ in range(world)]
+            all_i = [torch.empty_like(i_x) for _ in range(world)]
+            dist.all_gather(all_d, d_x.contiguous(), group=group)
+            dist.all_gather(all_i, i_x.contiguous(), group=group)
+            d_x, i_x = stages.merge(torch.stack(all_d), torch.stack(all_i))
+        top_d[rows] = d_x
+        top_i[rows] = i_x
+    return top_d, top_i
 
 
 class ATTEvaluator(object):

@@ -106,10 +106,37 @@ int grl_topk_rows(grl_handle* h, const float* dist, long long ld_dist, int nq, i
                   float* top_d, int64_t* top_i, void* stream);
 int grl_topk_merge(grl_handle* h, const float* all_d, const int64_t* all_i, int nshards, int nq, int k,
                    float* out_d, int64_t* out_i, void* stream);
-/* One gallery shard, end to end: k nearest gallery rows of every query without materialising the nq x ng matrix
- * (it is 40 GB at 10k x 1M).  The shard is streamed in column chunks: split-bf16 planes -> tcgen05 distance tile
- * (<= 256 MB) -> streaming top-k.  g [ng][dim] is this rank's shard, idx_base the global index of its first row.
- * top_d/top_i [nq][k] are overwritten (sorted by (distance, global index)).  metric as in grl_distance.       */
+/* One gallery shard, end to end: the k nearest gallery rows of every query without materialising the nq x ng matrix (40 GB
+ * at 10k x 1M).  Two-stage exact search:
+ *   1. grl_coarse_topk   fp16 operands (per-row power-of-two scaling), ONE tcgen05 MMA per k-step, candidate filter fused
+ *                        into the GEMM epilogue, streaming top-K' (K' = grl_topk_kprime(k)) by COARSE distance;
+ *   2. grl_rescore       fixed-order fp32 inner products of the K' candidates (the distance the result reports);
+ *   3. grl_topk_finalize sort by (exact distance, global index), emit the top k, and PROVE per query that no row outside
+ *                        the K' candidates can belong to them (coarse K'-th value minus the worst-case rounding error of
+ *                        the coarse pass still exceeds the exact k-th value); queries where the proof fails are flagged;
+ *   4. grl_exact_topk    brute force in the same fixed-order arithmetic for the flagged queries (rare).
+ * The result is the exact stable top-k of the fixed-order fp32 distances, independent of chunking and of the number of
+ * gallery shards.  g [ng][dim] is this rank's shard, idx_base the global index of its first row; top_d/top_i [nq][k] are
+ * overwritten.  grl_dist_topk runs 1-4 for one shard and synchronises the stream once (it reads the flag count).
+ * For a sharded gallery the caller interleaves the stages with its collectives (grl_b200/evaluator.py: sharded_retrieve):
+ * all-gather + grl_topk_merge of the coarse lists, each rank re-scores the candidates it owns (grl_rescore writes 0 for
+ * rows of other shards, so the per-rank results combine by a sum), finalize, and the flagged queries go through
+ * grl_exact_topk per shard + grl_topk_merge.
+ * coarse_d holds -q.g (metric 0) or the SQUARED L2 distance (metric 1); gmax2 [1] = max |g|^2 over the shard (combine
+ * shards with a max); flags int32 [nq], nflag int32 [1].                                                                */
+int grl_topk_kprime(int k);
+size_t grl_coarse_topk_workspace_bytes(int nq, int ng, int dim);
+int grl_coarse_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int kprime,
+                    int64_t idx_base, float* coarse_d, int64_t* coarse_i, float* gmax2, void* workspace,
+                    size_t workspace_bytes, void* stream);
+int grl_rescore(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int64_t idx_base,
+                const int64_t* cand_i, int kprime, float* exact_d, void* stream);
+int grl_topk_finalize(grl_handle* h, int metric, const float* q, int nq, int dim, const float* coarse_d, const int64_t* cand_i,
+                      const float* exact_d, int kprime, const float* gmax2, int k, float* top_d, int64_t* top_i,
+                      int32_t* flags, int32_t* nflag, void* stream);
+size_t grl_exact_topk_workspace_bytes(int nq, int ng, int dim);
+int grl_exact_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k, int64_t idx_base,
+                   float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream);
 size_t grl_dist_topk_workspace_bytes(int nq, int ng, int dim);
 int grl_dist_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k,
                   int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream);

@@ -116,3 +116,99 @@ def merge_topk(vals_list, idx_list, k: int):
     i = np.concatenate(idx_list, 1)
     order = np.lexsort((i, v), axis=1)[:, :k]
     return np.take_along_axis(v, order, 1), np.take_along_axis(i, order, 1)
+
+
+# --------------------------------------------------------------------------------------------
+# Two-stage exact search (grl_b200/csrc/eval.cu): numpy restatements used by the tests.
+# The reference has no counterpart beyond `-qf @ gf.T` + argsort (attevaluator.py:44-46, eva_functions.py:139); what is
+# pinned here is the ARITHMETIC the kernels promise: distances are fp32 inner products in one fixed summation order.
+# --------------------------------------------------------------------------------------------
+def _fixed_order_reduce(prod):
+    """prod [..., dim] float32 products -> [...] float32: lane l sums the float4 chunks l, l+32, ... component by component,
+    then an xor-shuffle tree over the 32 lanes (warp_dot_fixed in eval.cu)."""
+    dim = prod.shape[-1]
+    assert dim % 4 == 0
+    nv = dim // 4
+    nt = (nv + 31) // 32
+    lanes = np.zeros(prod.shape[:-1] + (32,), np.float32)
+    for t in range(nt):
+        lo = t * 32
+        n = min(32, nv - lo)
+        blk = prod[..., lo * 4:(lo + n) * 4].reshape(prod.shape[:-1] + (n, 4))
+        for c in range(4):
+            lanes[..., :n] = lanes[..., :n] + blk[..., c]
+    for off in (16, 8, 4, 2, 1):
+        lanes = lanes + lanes[..., np.arange(32) ^ off]
+    return lanes[..., 0]
+
+
+def exact_distance_fixed(qf: np.ndarray, gf: np.ndarray, metric: int = 0, block: int = 2048) -> np.ndarray:
+    """[nq, ng] float32 distances exactly as rescore_kernel / exact_rows_kernel compute them."""
+    qf = np.ascontiguousarray(qf, np.float32)
+    gf = np.ascontiguousarray(gf, np.float32)
+    out = np.empty((qf.shape[0], gf.shape[0]), np.float32)
+    qq = _fixed_order_reduce(qf * qf)
+    for c0 in range(0, gf.shape[0], block):
+        g = gf[c0:c0 + block]
+        dot = _fixed_order_reduce(qf[:, None, :] * g[None, :, :])
+        if metric == 0:
+            out[:, c0:c0 + block] = -dot
+        else:
+            gg = _fixed_order_reduce(g * g)
+            s = (qq[:, None] + gg[None, :]) - np.float32(2.0) * dot
+            out[:, c0:c0 + block] = np.sqrt(np.maximum(s, np.float32(1e-12)))
+    return out
+
+
+def f16_rows(x: np.ndarray):
+    """f16_rows_kernel: per-row power-of-two scale so that max|x| lands in [2^14, 2^15), fp16 rounding.
+    Returns (x16 as float32, inv_scale [rows], sqnorm [rows])."""
+    x = np.ascontiguousarray(x, np.float32)
+    m = np.abs(x).max(axis=1)
+    e = np.where((m > 0) & np.isfinite(m), np.floor(np.log2(np.where(m > 0, m, 1.0))), 0.0).astype(np.int64)
+    e = np.clip(e, -100, 100)
+    s = np.ldexp(np.float32(1.0), (14 - e).astype(np.int32)).astype(np.float32)
+    x16 = (x * s[:, None]).astype(np.float16).astype(np.float32)
+    return x16, np.ldexp(np.float32(1.0), (e - 14).astype(np.int32)).astype(np.float32), _fixed_order_reduce(x * x)
+
+
+def coarse_distance(qf, gf, metric: int = 0) -> np.ndarray:
+    """Stage-1 distances: fp16 operands, exact products, (here) float64 accumulation rounded to float32; metric 1 is the
+    SQUARED L2 distance.  The tensor core's accumulation order differs, which the error bound CE covers."""
+    q16, qi, qn = f16_rows(qf)
+    g16, gi, gn = f16_rows(gf)
+    dot = ((q16.astype(np.float64) @ g16.astype(np.float64).T) * qi[:, None].astype(np.float64) * gi[None, :]).astype(np.float32)
+    if metric == 0:
+        return -dot
+    return np.maximum(qn[:, None] + gn[None, :] - np.float32(2.0) * dot, np.float32(1e-12))
+
+
+def coarse_error_constant(dim: int) -> float:
+    return float(np.float32(2.0 ** -10) + np.float32(2.0 ** -17) + np.float32(2.0) * np.float32(dim) * np.float32(2.0 ** -24))
+
+
+def finalize_topk(qf, coarse_d, cand_i, exact_d, gmax2, k, metric=0):
+    """topk_finalize_kernel: (top_d, top_i, flags).  cand_i < 0 marks empty slots; coarse_d ascending per row."""
+    nq, kp = cand_i.shape
+    top_d = np.full((nq, k), np.inf, np.float32)
+    top_i = np.full((nq, k), -1, np.int64)
+    flags = np.zeros(nq, np.int32)
+    ce = np.float32(coarse_error_constant(qf.shape[1]))
+    for r in range(nq):
+        valid = cand_i[r] >= 0
+        d, i = exact_d[r][valid], cand_i[r][valid]
+        order = np.lexsort((i, d))[:k]
+        top_d[r, :len(order)] = d[order]
+        top_i[r, :len(order)] = i[order]
+        if valid.all() and len(order) == k:
+            u = top_d[r, k - 1]
+            ck = np.float32(coarse_d[r, kp - 1])
+            qq = np.float32((qf[r].astype(np.float64) ** 2).sum())
+            emax = ce * np.sqrt(qq) * np.sqrt(np.float32(gmax2)) * np.float32(1.00001)
+            if metric == 1:
+                lb = ck - np.float32(2.0) * emax - np.float32(1e-5) * (qq + np.float32(gmax2))
+                ok = lb > 1e-12 and np.sqrt(lb) * np.float32(0.999999) > u
+            else:
+                ok = ck - emax - np.float32(1e-6) * abs(ck) > u
+            flags[r] = 0 if ok else 1
+    return top_d, top_i, flags

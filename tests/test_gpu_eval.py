@@ -144,21 +144,27 @@ def test_topk_stream_and_merge_shard_invariant():
         assert np.array_equal(od.cpu().numpy(), v_ref) and np.array_equal(oi.cpu().numpy(), i_ref)
 
 
-@pytest.mark.parametrize("metric", [0, 1])
-def test_dist_topk_shard_invariant_vs_oracle(metric):
-    """grl_dist_topk per shard + grl_topk_merge == stable top-k of the full distance matrix, for 1/2/4/8 shards."""
-    _, ev = _mods()
-    from oracle import eval_oracle as eo
-    rng = np.random.default_rng(11)
-    nq, ng, dim, k = 41, 20011, 128, 100
+def _retrieval_inputs(nq, ng, dim, seed, dup_every=13):
+    rng = np.random.default_rng(seed)
     q = rng.standard_normal((nq, dim)).astype(np.float32)
     g = rng.standard_normal((ng, dim)).astype(np.float32)
     q /= np.linalg.norm(q, axis=1, keepdims=True)               # unit-norm descriptors like the reference's features
     g /= np.linalg.norm(g, axis=1, keepdims=True)
-    g[::13] = g[5]                                              # exact ties, also across shard boundaries
+    if dup_every:
+        g[::dup_every] = g[5]                                   # exact ties, also across shard boundaries
+    return q, g
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_dist_topk_shard_invariant_vs_oracle(metric):
+    """grl_dist_topk per shard (coarse fp16 pass + exact re-score + completeness proof, brute force where the proof fails)
+    + grl_topk_merge == stable top-k of the fixed-order fp32 distance matrix, bit for bit, for 1/2/4/8 shards."""
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    nq, ng, dim, k = 41, 20011, 128, 100
+    q, g = _retrieval_inputs(nq, ng, dim, 11)                   # ~1540 duplicated rows: queries near them fail the proof
     qd, gd = torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda()
-    full = (ev.cosin_dist(qd, gd) if metric == 0 else ev.pairwise_distance_tensor(qd, gd)).cpu().numpy()
-    v_ref, i_ref = eo.topk_stable(full, k)                      # same device distances: index-exact comparison
+    v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q, g, metric), k)
     for shards in (1, 2, 4, 8):
         parts = []
         for r in range(shards):
@@ -172,3 +178,75 @@ def test_dist_topk_shard_invariant_vs_oracle(metric):
     got_d = np.take_along_axis(ref, oi.cpu().numpy(), 1)
     best = np.sort(ref, axis=1)[:, :k]
     assert np.abs(got_d - best).max() <= 2e-5
+
+
+@pytest.mark.parametrize("metric,dup_every,k", [(0, 13, 100), (1, 0, 100), (0, 0, 300), (1, 13, 17)])
+def test_staged_search_over_simulated_shards(metric, dup_every, k):
+    """The stages sharded_retrieve runs on every rank, driven here for 1/3/8 shards on one GPU with the collectives
+    replaced by stack / max / sum: coarse lists -> merge -> owned re-scores summed -> finalize -> brute force of flagged rows."""
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    st = ev.CudaSearchStages
+    nq, ng, dim = 53, 9001, 256
+    q, g = _retrieval_inputs(nq, ng, dim, 21 + k, dup_every)
+    qd, gd = torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda()
+    v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q, g, metric), k)
+    kp = st.kprime(k)
+    n_flagged = []
+    for shards in (1, 3, 8):
+        spans = [ev.shard_bounds(ng, shards, r) for r in range(shards)]
+        coarse = [st.coarse(qd, gd[lo:lo + n].contiguous(), kp, lo, metric) for lo, n in spans]
+        gmax2 = torch.stack([c[2] for c in coarse]).max(dim=0).values
+        cd, ci = st.merge(torch.stack([c[0] for c in coarse]), torch.stack([c[1] for c in coarse]))
+        ed = sum(st.rescore(qd, gd[lo:lo + n].contiguous(), ci, lo, metric) for lo, n in spans)
+        top_d, top_i, flags = st.finalize(qd, cd, ci, ed, gmax2, k, metric)
+        rows = torch.nonzero(flags).flatten()
+        n_flagged.append(int(rows.numel()))
+        if rows.numel():
+            ex = [st.exact(qd[rows].contiguous(), gd[lo:lo + n].contiguous(), k, lo, metric) for lo, n in spans]
+            d_x, i_x = st.merge(torch.stack([e[0] for e in ex]), torch.stack([e[1] for e in ex]))
+            top_d[rows] = d_x
+            top_i[rows] = i_x
+        assert np.array_equal(top_i.cpu().numpy(), i_ref), (shards, n_flagged)
+        assert np.array_equal(top_d.cpu().numpy(), v_ref), (shards, n_flagged)
+        # the coarse ranking must honour its error bound against the exact distances (what the proof relies on)
+        own = ci >= 0
+        c_exact = torch.where(own, ed, torch.zeros_like(ed))
+        c_coarse = torch.where(own, cd, torch.zeros_like(cd))
+        if metric == 1:
+            c_exact = c_exact ** 2
+        bound = eo.coarse_error_constant(dim) * (2.0 if metric == 1 else 1.0) * 1.01 + 1e-5
+        assert float((c_exact - c_coarse).abs().max()) <= bound
+    if dup_every == 0 and k <= 100:
+        assert n_flagged == [0, 0, 0], n_flagged                 # generic data: every proof succeeds, no brute force
+    if dup_every and k == 100:
+        assert n_flagged[0] > 0                                  # duplicated rows straddling K': the brute-force leg ran
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_dist_topk_large_query_block(metric):
+    """nq >= 1024 and shards >= 1024 rows: the 256 x 256-tile coarse GEMM (coarse_gemm.cuh), ragged last tiles included."""
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    nq, ng, dim, k = 1100, 3333, 64, 20
+    q, g = _retrieval_inputs(nq, ng, dim, 31, dup_every=0)
+    qd, gd = torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda()
+    v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q, g, metric), k)
+    for shards in (1, 2):
+        parts = []
+        for r in range(shards):
+            lo, n = ev.shard_bounds(ng, shards, r)
+            parts.append(ev.retrieve_topk(qd, gd[lo:lo + n], k, idx_base=lo, metric=metric))
+        od, oi = ev.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+        assert np.array_equal(oi.cpu().numpy(), i_ref), shards
+        assert np.array_equal(od.cpu().numpy(), v_ref), shards
+
+
+def test_exact_topk_brute_force_matches_oracle():
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    for metric in (0, 1):
+        q, g = _retrieval_inputs(19, 3001, 72, 5 + metric)
+        d, i = ev.CudaSearchStages.exact(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda(), 50, 1000, metric)
+        v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q, g, metric), 50, 1000)
+        assert np.array_equal(i.cpu().numpy(), i_ref) and np.array_equal(d.cpu().numpy(), v_ref)
