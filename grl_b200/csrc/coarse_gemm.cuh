@@ -27,6 +27,20 @@ struct CoarseGemmParams {
     GemmEpi epi;            // uses C/ldc, alpha, row_scale, col_scale, mode (0 | 2), row_norm, col_norm, tk_*
 };
 
+// v[j] for a run-time j without indexing the register array dynamically (31 selects)
+__device__ __forceinline__ float select32(const float (&v)[32], int j) {
+    float a[16], b[8], c[4], d[2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+    return (j & 16) ? d[1] : d[0];
+}
+
 __global__ void __launch_bounds__(CG_THREADS, 1) coarse_gemm_kernel(const __grid_constant__ CoarseGemmParams p) {
     extern __shared__ uint8_t cg_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(cg_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -142,8 +156,18 @@ __global__ void __launch_bounds__(CG_THREADS, 1) coarse_gemm_kernel(const __grid
             float nxt[32];
             tmem_ld_32x32(t_row, nxt);
             tmem_ld_wait();
-            uint32_t pmask = 0;                           // candidate reservation in flight (issued one chunk earlier)
-            int ppos = 0, pcol0 = 0;
+            // candidate reservation in flight: the slot index comes back from an atomic issued one chunk earlier, so its
+            // latency hides behind the next chunk; up to two (value, column) pairs wait in registers
+            int pend_n = 0, ppos = 0;
+            float pv0 = 0.f, pv1 = 0.f;
+            uint32_t pc0 = 0, pc1 = 0;
+            auto flush_pending = [&]() {
+                if (pend_n) {
+                    if (ppos < e.tk_cap) e.tk_cand[(long long)grow * e.tk_cap + ppos] = make_key(pv0, pc0);
+                    if (pend_n > 1 && ppos + 1 < e.tk_cap) e.tk_cand[(long long)grow * e.tk_cap + ppos + 1] = make_key(pv1, pc1);
+                    pend_n = 0;
+                }
+            };
 #pragma unroll 1
             for (int c = 0; c < nchunks; ++c) {
                 const int col0 = n0 + c * 32;
@@ -176,22 +200,33 @@ __global__ void __launch_bounds__(CG_THREADS, 1) coarse_gemm_kernel(const __grid
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] *= ar;
                     }
-                    // the previous chunk's reservation has had a whole chunk to come back: append its column numbers now
-                    while (pmask && ppos < e.tk_cap) {
-                        const int j = __ffs(pmask) - 1;
-                        pmask &= pmask - 1;
-                        e.tk_cand[(long long)grow * e.tk_cap + ppos++] = (uint32_t)(pcol0 + j);
-                    }
+                    flush_pending();
                     // Branch-free pass mask; once the lists have warmed up a lane sees a candidate in a few percent of its chunks.
-                    // One atomic per row and chunk reserves the slots; its latency hides behind the tile stores below, and only
-                    // column numbers are appended (the consumer reads the values back from the tile).
-                    pmask = 0;
                     if (e.tk_cand) {
+                        uint32_t mask = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) pmask |= (v[j] <= rthresh) ? (1u << j) : 0u;
-                        if (!row_ok) pmask = 0;
-                        pcol0 = col0;
-                        if (pmask) ppos = atomicAdd(e.tk_cnt + grow, __popc(pmask));
+                        for (int j = 0; j < 32; ++j) mask |= (v[j] <= rthresh) ? (1u << j) : 0u;
+                        if (!row_ok) mask = 0;
+                        if (mask) {
+                            ppos = atomicAdd(e.tk_cnt + grow, __popc(mask));       // one atomic reserves all slots of this row and chunk
+                            const uint32_t gcol = (uint32_t)(e.tk_idx_base + col0);
+                            int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            pv0 = select32(v, j); pc0 = gcol + j; pend_n = 1;
+                            if (mask) {
+                                j = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                pv1 = select32(v, j); pc1 = gcol + j; pend_n = 2;
+                            }
+                            int extra = 2;
+                            while (mask) {                                          // > 2 candidates in one 32-column chunk: rare
+                                j = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const float val = select32(v, j);
+                                if (ppos + extra < e.tk_cap) e.tk_cand[(long long)grow * e.tk_cap + ppos + extra] = make_key(val, gcol + j);
+                                ++extra;
+                            }
+                        }
                     }
                     if (row_ok && c_row) {
                         float4* d4 = reinterpret_cast<float4*>(c_row + col0);     // ldc % 4 == 0 and 16-byte aligned C (checked on the host)
@@ -199,12 +234,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) coarse_gemm_kernel(const __grid
                         for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
                 } else {
-                    while (pmask && ppos < e.tk_cap) {       // pending reservation of the previous (full) chunk
-                        const int j = __ffs(pmask) - 1;
-                        pmask &= pmask - 1;
-                        e.tk_cand[(long long)grow * e.tk_cap + ppos++] = (uint32_t)(pcol0 + j);
-                    }
-                    pmask = 0;
+                    flush_pending();
                     // ---- ragged last chunk of the matrix
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -220,7 +250,8 @@ __global__ void __launch_bounds__(CG_THREADS, 1) coarse_gemm_kernel(const __grid
                             if (col0 + j < p.N) {
                                 if (e.tk_cand && v[j] <= rthresh) {
                                     const int pos1 = atomicAdd(e.tk_cnt + grow, 1);
-                                    if (pos1 < e.tk_cap) e.tk_cand[(long long)grow * e.tk_cap + pos1] = (uint32_t)(col0 + j);
+                                    if (pos1 < e.tk_cap)
+                                        e.tk_cand[(long long)grow * e.tk_cap + pos1] = make_key(v[j], (uint32_t)(e.tk_idx_base + col0 + j));
                                 }
                                 if (c_row) c_row[col0 + j] = v[j];
                             }
@@ -232,11 +263,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) coarse_gemm_kernel(const __grid
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty);          // TMEM is drained: the next tile's MMAs may start
-            while (pmask && ppos < e.tk_cap) {
-                const int j = __ffs(pmask) - 1;
-                pmask &= pmask - 1;
-                e.tk_cand[(long long)grow * e.tk_cap + ppos++] = (uint32_t)(pcol0 + j);
-            }
+            flush_pending();
         }
     }
 

@@ -231,8 +231,8 @@ __global__ void topk_init_kernel(float* top_d, int64_t* top_i, long long n) {
 // and publish the new k-th best distance as the row's filter threshold.
 __global__ void __launch_bounds__(TOPK_THREADS) topk_update_kernel(const float* __restrict__ dist, long long ld, int ncols, int k,
                                                                    int64_t idx_base, float* __restrict__ top_d, int64_t* __restrict__ top_i,
-                                                                   float* __restrict__ thresh_out, const uint32_t* __restrict__ cand,
-                                                                   int* __restrict__ cand_cnt, int cap) {
+                                                                   float* __restrict__ thresh_out, const unsigned long long* __restrict__ cand,
+                                                                   int* __restrict__ cand_cnt, int cap, int32_t* __restrict__ dirty) {
     __shared__ uint64_t keys[TOPK_BUF];
     __shared__ int count;
     __shared__ uint64_t thresh;
@@ -248,15 +248,18 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_update_kernel(const float* 
         for (int i = threadIdx.x; i < npad; i += blockDim.x) {
             uint64_t key = ~0ull;
             if (i < k) { if (ti[i] >= 0) key = make_key(td[i], (uint32_t)ti[i]); }
-            else if (i < k + cnt) {                  // candidates are column numbers of this tile: the value comes from the tile
-                const uint32_t col = cand[(long long)row * cap + (i - k)];
-                key = make_key(dist[(long long)row * ld + col], (uint32_t)(idx_base + col));
-            }
+            else if (i < k + cnt) key = cand[(long long)row * cap + (i - k)];
             keys[i] = key;
         }
         block_bitonic_sort(keys, npad);
         nsort = npad;
     } else {
+        if (dist == nullptr) {
+            // The candidate list overflowed in a chunk whose tile was not stored (only the first, threshold-less chunk is):
+            // this row's list can no longer be trusted.  Mark it; finalisation sends it to the brute-force search.
+            if (threadIdx.x == 0) { dirty[row] = 1; thresh_out[row] = -CUDART_INF_F; cand_cnt[row] = 0; }
+            return;
+        }
         const float* drow = dist + (long long)row * ld;
         for (int i = threadIdx.x; i < TOPK_BUF; i += blockDim.x) {
             uint64_t key = ~0ull;
@@ -307,9 +310,8 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_update_kernel(const float* 
 // barriers: the candidates are sorted across the lanes with a shuffle network and merged into the (sorted) running list by
 // rank -- every list key moves down by the number of candidates below it, every candidate lands at its own rank plus the
 // number of list keys below it -- so the cost is one pass over the list instead of a 512-key bitonic sort.
-__global__ void __launch_bounds__(256) topk_update_small_kernel(const float* __restrict__ dist, long long ld, int64_t idx_base, int nq, int k,
-                                                                float* __restrict__ top_d, int64_t* __restrict__ top_i,
-                                                                float* __restrict__ thresh_out, const uint32_t* __restrict__ cand,
+__global__ void __launch_bounds__(256) topk_update_small_kernel(int nq, int k, float* __restrict__ top_d, int64_t* __restrict__ top_i,
+                                                                float* __restrict__ thresh_out, const unsigned long long* __restrict__ cand,
                                                                 int* __restrict__ cand_cnt, int cap) {
     extern __shared__ uint64_t small_keys[];          // [8 warps][k]
     const int warp = threadIdx.x >> 5, lane = lane_id();
@@ -321,11 +323,7 @@ __global__ void __launch_bounds__(256) topk_update_small_kernel(const float* __r
     float* td = top_d + (long long)row * k;
     int64_t* ti = top_i + (long long)row * k;
     for (int t = lane; t < k; t += 32) sl[t] = ti[t] >= 0 ? make_key(td[t], (uint32_t)ti[t]) : ~0ull;
-    uint64_t c = ~0ull;
-    if (lane < cnt) {
-        const uint32_t col = cand[(long long)row * cap + lane];
-        c = make_key(dist[(long long)row * ld + col], (uint32_t)(idx_base + col));
-    }
+    uint64_t c = lane < cnt ? cand[(long long)row * cap + lane] : ~0ull;
 #pragma unroll
     for (int size = 2; size <= 32; size <<= 1) {      // bitonic sort across the lanes, ascending
 #pragma unroll
@@ -518,8 +516,9 @@ __global__ void __launch_bounds__(256) rescore_kernel(int metric, const float* _
 __global__ void __launch_bounds__(256) topk_finalize_kernel(int metric, const float* __restrict__ q, int dim, const float* __restrict__ coarse_d,
                                                             const int64_t* __restrict__ cand_i, const float* __restrict__ exact_d, int kp,
                                                             int npad, const float* __restrict__ gmax2, float ce, int k,
-                                                            float* __restrict__ top_d, int64_t* __restrict__ top_i,
-                                                            int32_t* __restrict__ flags, int32_t* __restrict__ nflag) {
+                                                            const int32_t* __restrict__ dirty, float* __restrict__ top_d,
+                                                            int64_t* __restrict__ top_i, int32_t* __restrict__ flags,
+                                                            int32_t* __restrict__ nflag) {
     extern __shared__ uint64_t fkeys[];
     __shared__ float red[8];
     __shared__ int nvalid_s;
@@ -550,9 +549,9 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(int metric, const fl
         else { top_d[(long long)row * k + t] = from_orderable((uint32_t)(key >> 32)); top_i[(long long)row * k + t] = (int64_t)(key & 0xFFFFFFFFu); }
     }
     if (threadIdx.x == 0) {
-        bool ok = true;
+        bool ok = !(dirty && dirty[row]);             // a shard's candidate list overflowed: not provable
         const int nvalid = nvalid_s;
-        if (nvalid == kp && nvalid > k - 1 && fkeys[k - 1] != ~0ull) {   // a full list may have cut off relevant rows
+        if (ok && nvalid == kp && nvalid > k - 1 && fkeys[k - 1] != ~0ull) {   // a full list may have cut off relevant rows
             const float u = from_orderable((uint32_t)(fkeys[k - 1] >> 32));
             const float ck = coarse_d[(long long)row * kp + kp - 1];
             const float g2 = *gmax2;
@@ -658,16 +657,19 @@ extern "C" int grl_distance(grl_handle* h, int metric, const float* q, const flo
 }
 
 // ------------------------------------------------------------------ gallery-shard search: coarse tiles + streaming top-K', exact re-score
-static int topk_chunk_cols(int nq, int ng, int num_sms) {
-    long long c = (1ll << 29) / (4ll * (nq > 0 ? nq : 1));       // <= 512 MB distance tile
-    c = c / 256 * 256;
-    if (c < 1024) c = 1024;
-    if (c > 16384) c = 16384;
+// Column chunks of one search.  The first chunk has no thresholds yet: its tile IS stored and every row is rescanned, so it is
+// kept small (TOPK_FIRST_CHUNK columns).  Afterwards the K'-th best of n_seen columns lets ~K' * nc / n_seen candidates per row
+// through, so chunks grow with n_seen (at most doubling the columns seen) up to the steady-state size, whose 256 x 256 tiles
+// fill whole waves of the persistent grid; their tiles are never stored.
+constexpr int TOPK_FIRST_CHUNK = 2048;
+constexpr int TOPK_CAND_CAP = 512;      // candidates per query row per column chunk (expected <= K' = 256..1024 / growth factor)
+
+static int topk_chunk_max(int nq, int ng, int num_sms) {
+    long long c = 16384;
     if (nq >= 1024 && c < ng) {
-        // 256 x 256 tiles on a persistent grid of num_sms CTAs: pick the column count whose tile count fills whole waves
         const long long mt = (nq + 255) / 256;
         double best = 0.0; long long best_n = c / 256;
-        for (long long n = c / 256; n >= 4 && n >= c / 512; --n) {
+        for (long long n = c / 256; n >= 16; --n) {
             const long long tiles = mt * n, waves = (tiles + num_sms - 1) / num_sms;
             const double eff = (double)tiles / (double)(waves * num_sms);
             if (eff > best + 1e-9) { best = eff; best_n = n; }
@@ -677,8 +679,13 @@ static int topk_chunk_cols(int nq, int ng, int num_sms) {
     if (c > ng) c = (ng + 7) / 8 * 8;
     return (int)c;
 }
-
-constexpr int TOPK_CAND_CAP = 256;      // candidates per query row per column chunk before the rescan path takes over
+static int topk_next_chunk(int c0, int ng, int chunk_max) {
+    long long nc = c0 == 0 ? TOPK_FIRST_CHUNK : (c0 < chunk_max ? c0 : chunk_max);
+    nc = (nc + 255) / 256 * 256;
+    if (nc > chunk_max) nc = chunk_max;
+    if (nc > ng - c0) nc = ng - c0;
+    return (int)nc;
+}
 
 extern "C" int grl_topk_kprime(int k) { return k <= 128 ? 256 : (k <= 256 ? 512 : 1024); }
 
@@ -687,21 +694,22 @@ static float coarse_error_constant(int dim) {   // CE of the comment above f16_r
 }
 
 struct CoarseLayout {
-    int chunk;
+    int chunk, first;
     size_t q16, g16, qf, gf, tile, thresh, cnt, cand, total;
 };
 static void coarse_layout(int nq, int ng, int dim, CoarseLayout* L) {
-    L->chunk = topk_chunk_cols(nq, ng, 148);
+    L->chunk = topk_chunk_max(nq, ng, 148);
+    L->first = ng < TOPK_FIRST_CHUNK ? (ng + 7) / 8 * 8 : TOPK_FIRST_CHUNK;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
     L->q16 = take((size_t)nq * dim * 2);
     L->g16 = take((size_t)L->chunk * dim * 2);
     L->qf = take((size_t)nq * 4 * 2);                 // inv_scale | sqnorm
     L->gf = take((size_t)L->chunk * 4 * 2);
-    L->tile = take((size_t)nq * L->chunk * 4);
+    L->tile = take((size_t)nq * L->first * 4);        // coarse distances of the first chunk only
     L->thresh = take((size_t)nq * 4);
     L->cnt = take((size_t)nq * 4);
-    L->cand = take((size_t)nq * TOPK_CAND_CAP * 4);
+    L->cand = take((size_t)nq * TOPK_CAND_CAP * 8);
     L->total = off;
 }
 
@@ -712,9 +720,9 @@ extern "C" size_t grl_coarse_topk_workspace_bytes(int nq, int ng, int dim) {
 }
 
 extern "C" int grl_coarse_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int kprime,
-                               int64_t idx_base, float* coarse_d, int64_t* coarse_i, float* gmax2, void* workspace,
+                               int64_t idx_base, float* coarse_d, int64_t* coarse_i, float* gmax2, int32_t* dirty, void* workspace,
                                size_t workspace_bytes, void* stream) {
-    if (!h || !q || !g || !coarse_d || !coarse_i || !gmax2 || !workspace) return set_error(h, GRL_EINVAL, "grl_coarse_topk: NULL argument");
+    if (!h || !q || !g || !coarse_d || !coarse_i || !gmax2 || !dirty || !workspace) return set_error(h, GRL_EINVAL, "grl_coarse_topk: NULL argument");
     if (nq <= 0 || ng <= 0 || dim <= 0 || (dim & 7)) return set_error(h, GRL_EINVAL, "grl_coarse_topk: need nq,ng > 0 and dim %% 8 == 0 (dim=%d)", dim);
     if (kprime <= 0 || kprime > TOPK_MAXK) return set_error(h, GRL_EINVAL, "grl_coarse_topk: need 0 < kprime <= %d", TOPK_MAXK);
     if (metric != GRL_METRIC_NEG_DOT && metric != GRL_METRIC_L2) return set_error(h, GRL_EINVAL, "grl_coarse_topk: unknown metric %d", metric);
@@ -733,36 +741,38 @@ extern "C" int grl_coarse_topk(grl_handle* h, int metric, const float* q, const 
     float* tile = (float*)(w + L.tile);
     float* thresh = (float*)(w + L.thresh);
     int* cand_cnt = (int*)(w + L.cnt);
-    uint32_t* cand = (uint32_t*)(w + L.cand);
-    const int chunk = L.chunk;
+    unsigned long long* cand = (unsigned long long*)(w + L.cand);
     GRL_CUDA(h, cudaMemsetAsync(gmax2, 0, 4, st));
+    GRL_CUDA(h, cudaMemsetAsync(dirty, 0, (size_t)nq * 4, st));
     if ((size_t)8 * kprime * 8 > 48 * 1024)
         GRL_CUDA(h, cudaFuncSetAttribute(topk_update_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * TOPK_MAXK * 8));
     topk_filter_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(thresh, cand_cnt, nq, TOPK_CAND_CAP);
     GRL_LAUNCH_CHECK(h);
-    // the query norms go to a scratch max (thresh is free until the first update): only the gallery maximum is reported
+    // the query norms go to a scratch max (cand is free until the first GEMM): only the gallery maximum is reported
     f16_rows_kernel<<<(int)(((long long)nq * 32 + 255) / 256), 256, 0, st>>>(q, nq, dim, q16, q_inv, q_n2, (unsigned int*)cand);
     GRL_LAUNCH_CHECK(h);
     GRL_TRY(grl_topk_init(h, coarse_d, coarse_i, nq, kprime, stream));
-    for (int c0 = 0; c0 < ng; c0 += chunk) {
-        const int nc = (ng - c0 < chunk) ? ng - c0 : chunk;
+    for (int c0 = 0; c0 < ng;) {
+        const int nc = topk_next_chunk(c0, ng, L.chunk);
+        const bool first = c0 == 0;
         const float* gc = g + (size_t)c0 * dim;
         f16_rows_kernel<<<(int)(((long long)nc * 32 + 255) / 256), 256, 0, st>>>(gc, nc, dim, g16, g_inv, g_n2, (unsigned int*)gmax2);
         GRL_LAUNCH_CHECK(h);
         GemmEpi e = epi_default();
-        e.C = tile; e.ldc = chunk;
+        if (first) { e.C = tile; e.ldc = L.first; }   // later chunks never store their tile
         e.row_scale = q_inv; e.col_scale = g_inv;
         if (metric == GRL_METRIC_L2) { e.mode = 2; e.row_norm = q_n2; e.col_norm = g_n2; }
         else e.alpha = -1.f;
         // the epilogue keeps only distances that can still enter a row's list (v <= current K'-th best) as candidates
         e.tk_cand = cand; e.tk_cnt = cand_cnt; e.tk_thresh = thresh; e.tk_cap = TOPK_CAND_CAP; e.tk_idx_base = idx_base + c0;
         GRL_TRY(coarse_gemm_launch(h, st, nq, nc, dim, q16, dim, g16, dim, e));
-        topk_update_small_kernel<<<(nq + 7) / 8, 256, (size_t)8 * kprime * 8, st>>>(tile, chunk, idx_base + c0, nq, kprime, coarse_d, coarse_i,
-                                                                                     thresh, cand, cand_cnt, TOPK_CAND_CAP);
+        topk_update_small_kernel<<<(nq + 7) / 8, 256, (size_t)8 * kprime * 8, st>>>(nq, kprime, coarse_d, coarse_i, thresh, cand, cand_cnt,
+                                                                                     TOPK_CAND_CAP);
         GRL_LAUNCH_CHECK(h);
-        topk_update_kernel<<<nq, TOPK_THREADS, 0, st>>>(tile, chunk, nc, kprime, idx_base + c0, coarse_d, coarse_i, thresh, cand, cand_cnt,
-                                                        TOPK_CAND_CAP);
+        topk_update_kernel<<<nq, TOPK_THREADS, 0, st>>>(first ? tile : nullptr, L.first, nc, kprime, idx_base + c0, coarse_d, coarse_i, thresh,
+                                                        cand, cand_cnt, TOPK_CAND_CAP, dirty);
         GRL_LAUNCH_CHECK(h);
+        c0 += nc;
     }
     return GRL_OK;
 }
@@ -779,8 +789,8 @@ extern "C" int grl_rescore(grl_handle* h, int metric, const float* q, const floa
 }
 
 extern "C" int grl_topk_finalize(grl_handle* h, int metric, const float* q, int nq, int dim, const float* coarse_d, const int64_t* cand_i,
-                                 const float* exact_d, int kprime, const float* gmax2, int k, float* top_d, int64_t* top_i,
-                                 int32_t* flags, int32_t* nflag, void* stream) {
+                                 const float* exact_d, int kprime, const float* gmax2, const int32_t* dirty, int k, float* top_d,
+                                 int64_t* top_i, int32_t* flags, int32_t* nflag, void* stream) {
     if (!h || !q || !coarse_d || !cand_i || !exact_d || !gmax2 || !top_d || !top_i || !flags || !nflag)
         return set_error(h, GRL_EINVAL, "grl_topk_finalize: NULL argument");
     if (nq <= 0 || dim <= 0 || kprime <= 0 || kprime > TOPK_MAXK || k <= 0 || k > kprime) return set_error(h, GRL_EINVAL, "grl_topk_finalize: need 0 < k <= kprime <= %d", TOPK_MAXK);
@@ -788,7 +798,7 @@ extern "C" int grl_topk_finalize(grl_handle* h, int metric, const float* q, int 
     GRL_CUDA(h, cudaMemsetAsync(nflag, 0, 4, st));
     const int npad = next_pow2(kprime < 2 ? 2 : kprime);
     topk_finalize_kernel<<<nq, 256, (size_t)npad * 8, st>>>(metric, q, dim, coarse_d, cand_i, exact_d, kprime, npad, gmax2,
-                                                            coarse_error_constant(dim), k, top_d, top_i, flags, nflag);
+                                                            coarse_error_constant(dim), k, dirty, top_d, top_i, flags, nflag);
     GRL_LAUNCH_CHECK(h);
     return GRL_OK;
 }
@@ -836,7 +846,7 @@ extern "C" int grl_exact_topk(grl_handle* h, int metric, const float* q, const f
 
 // ---- one shard, end to end
 struct DistTopkLayout {
-    size_t coarse, cd, ci, ed, misc, flags, rows, tmp_d, tmp_i, brute, total;
+    size_t coarse, cd, ci, ed, misc, flags, rows, dirty, tmp_d, tmp_i, brute, total;
     int kp;
 };
 static void dist_topk_layout(int nq, int ng, int dim, int k, DistTopkLayout* L) {
@@ -850,6 +860,7 @@ static void dist_topk_layout(int nq, int ng, int dim, int k, DistTopkLayout* L) 
     L->misc = take(64);                               // gmax2 f32 | nflag i32 | nrows i32
     L->flags = take((size_t)nq * 4);
     L->rows = take((size_t)nq * 4);
+    L->dirty = take((size_t)nq * 4);
     L->tmp_d = take((size_t)8 * k * 4);
     L->tmp_i = take((size_t)8 * k * 8);
     L->brute = take(grl_exact_topk_workspace_bytes(nq, ng, dim));
@@ -882,10 +893,11 @@ extern "C" int grl_dist_topk(grl_handle* h, int metric, const float* q, const fl
     int32_t* nrows = (int32_t*)(w + L.misc) + 2;
     int32_t* flags = (int32_t*)(w + L.flags);
     int32_t* rows = (int32_t*)(w + L.rows);
+    int32_t* dirty = (int32_t*)(w + L.dirty);
     GRL_CUDA(h, cudaMemsetAsync(w + L.misc, 0, 64, st));
-    GRL_TRY(grl_coarse_topk(h, metric, q, g, nq, ng, dim, L.kp, idx_base, cd, ci, gmax2, w + L.coarse, L.total - L.coarse, stream));
+    GRL_TRY(grl_coarse_topk(h, metric, q, g, nq, ng, dim, L.kp, idx_base, cd, ci, gmax2, dirty, w + L.coarse, L.total - L.coarse, stream));
     GRL_TRY(grl_rescore(h, metric, q, g, nq, ng, dim, idx_base, ci, L.kp, ed, stream));
-    GRL_TRY(grl_topk_finalize(h, metric, q, nq, dim, cd, ci, ed, L.kp, gmax2, k, top_d, top_i, flags, nflag, stream));
+    GRL_TRY(grl_topk_finalize(h, metric, q, nq, dim, cd, ci, ed, L.kp, gmax2, dirty, k, top_d, top_i, flags, nflag, stream));
     // rows whose candidate list could not be proven complete: brute force (needs their count on the host: one 4-byte read)
     int host_nflag = 0;
     GRL_CUDA(h, cudaMemcpyAsync(&host_nflag, nflag, 4, cudaMemcpyDeviceToHost, st));

@@ -55,10 +55,9 @@ struct GemmEpi {
     int mode;                 // 0 plain, 1 L2: v = sqrt(max(row_norm[m] + col_norm[n] - 2*acc, 1e-12)), 2: the same without the sqrt
     const float* row_norm;
     const float* col_norm;
-    // ---- top-k candidate filter (retrieval): the column number (within this GEMM's N) of every stored value v <= tk_thresh[m]
-    //      is appended to row m's candidate list (capacity tk_cap; tk_cnt keeps counting past it so the consumer sees the
-    //      overflow); the consumer reads the values back from C ----
-    uint32_t* tk_cand;
+    // ---- top-k candidate filter (retrieval): every value v <= tk_thresh[m] is appended, as a (distance, global column) key, to
+    //      row m's candidate list (capacity tk_cap; tk_cnt keeps counting past it so the consumer sees the overflow) ----
+    unsigned long long* tk_cand;
     int* tk_cnt;
     const float* tk_thresh;
     int tk_cap;
@@ -298,18 +297,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                     }
                 }
-                // ---- top-k candidates: a branch-free pass mask, then ONE atomic per row and chunk reserves the slots ----
-                if (e.tk_cand) {
-                    uint32_t mask = 0;
+                // ---- top-k candidates (small problems only; the large-problem kernel is coarse_gemm.cuh) ----
+                if (e.tk_cand && row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mask |= (v[j] <= rthresh && (full_chunk || col0 + j < p.N)) ? (1u << j) : 0u;
-                    if (!row_ok) mask = 0;
-                    if (mask) {
-                        int pos = atomicAdd(e.tk_cnt + grow, __popc(mask));
-                        while (mask && pos < e.tk_cap) {
-                            const int j = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            e.tk_cand[(long long)grow * e.tk_cap + pos++] = (uint32_t)(col0 + j);
+                    for (int j = 0; j < 32; ++j) {
+                        if (v[j] <= rthresh && (full_chunk || col0 + j < p.N)) {
+                            const int pos = atomicAdd(e.tk_cnt + grow, 1);
+                            if (pos < e.tk_cap)
+                                e.tk_cand[(long long)grow * e.tk_cap + pos] = make_key(v[j], (uint32_t)(e.tk_idx_base + col0 + j));
                         }
                     }
                 }

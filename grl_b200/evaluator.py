@@ -210,12 +210,13 @@ class CudaSearchStages(object):
             cd = torch.empty((nq, kp), dtype=torch.float32, device=qf.device)
             ci = torch.empty((nq, kp), dtype=torch.int64, device=qf.device)
             gmax2 = torch.zeros(1, dtype=torch.float32, device=qf.device)
+            dirty = torch.zeros(nq, dtype=torch.int32, device=qf.device)
             ws_bytes = lib.grl_coarse_topk_workspace_bytes(nq, ng, dim)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qf.device)
             _lib.check(h, lib.grl_coarse_topk(h, metric, qf.data_ptr(), gf.data_ptr(), nq, ng, dim, kp, idx_base, cd.data_ptr(),
-                                              ci.data_ptr(), gmax2.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(qf.device)),
-                       "grl_coarse_topk")
-        return cd, ci, gmax2
+                                              ci.data_ptr(), gmax2.data_ptr(), dirty.data_ptr(), ws.data_ptr(), ws_bytes,
+                                              _lib.stream_ptr(qf.device)), "grl_coarse_topk")
+        return cd, ci, gmax2, dirty
 
     merge = staticmethod(merge_topk)
 
@@ -231,7 +232,7 @@ class CudaSearchStages(object):
         return ed
 
     @staticmethod
-    def finalize(qf, cd, ci, ed, gmax2, k, metric):
+    def finalize(qf, cd, ci, ed, gmax2, dirty, k, metric):
         nq, dim, kp = qf.size(0), qf.size(1), ci.size(1)
         lib = _lib.load_library()
         with torch.cuda.device(qf.device):
@@ -241,8 +242,8 @@ class CudaSearchStages(object):
             flags = torch.empty(nq, dtype=torch.int32, device=qf.device)
             nflag = torch.zeros(1, dtype=torch.int32, device=qf.device)
             _lib.check(h, lib.grl_topk_finalize(h, metric, qf.data_ptr(), nq, dim, cd.data_ptr(), ci.data_ptr(), ed.data_ptr(), kp,
-                                                gmax2.data_ptr(), k, top_d.data_ptr(), top_i.data_ptr(), flags.data_ptr(),
-                                                nflag.data_ptr(), _lib.stream_ptr(qf.device)), "grl_topk_finalize")
+                                                gmax2.data_ptr(), dirty.data_ptr(), k, top_d.data_ptr(), top_i.data_ptr(),
+                                                flags.data_ptr(), nflag.data_ptr(), _lib.stream_ptr(qf.device)), "grl_topk_finalize")
         return top_d, top_i, flags
 
     @staticmethod
@@ -276,18 +277,19 @@ def sharded_retrieve(qf, gf_local, k, idx_base, group=None, metric=0, stages=Non
         stages = CudaSearchStages
         qf, gf_local = _padded_features(qf, gf_local)
     kp = stages.kprime(k)
-    cd, ci, gmax2 = stages.coarse(qf, gf_local, kp, idx_base, metric)
+    cd, ci, gmax2, dirty = stages.coarse(qf, gf_local, kp, idx_base, metric)
     if world > 1:
         all_d = [torch.empty_like(cd) for _ in range(world)]
         all_i = [torch.empty_like(ci) for _ in range(world)]
         dist.all_gather(all_d, cd.contiguous(), group=group)
         dist.all_gather(all_i, ci.contiguous(), group=group)
         dist.all_reduce(gmax2, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(dirty, op=dist.ReduceOp.MAX, group=group)   # a row whose candidate buffer overflowed on any shard
         cd, ci = stages.merge(torch.stack(all_d), torch.stack(all_i))
     ed = stages.rescore(qf, gf_local, ci, idx_base, metric)
     if world > 1:
         dist.all_reduce(ed, op=dist.ReduceOp.SUM, group=group)       # every candidate is owned by exactly one rank
-    top_d, top_i, flags = stages.finalize(qf, cd, ci, ed, gmax2, k, metric)
+    top_d, top_i, flags = stages.finalize(qf, cd, ci, ed, gmax2, dirty, k, metric)
     rows = torch.nonzero(flags).flatten()                            # identical on every rank (same inputs to finalize)
     if rows.numel():
         d_x, i_x = stages.exact(qf[rows].contiguous(), gf_local, k, idx_base, metric)

@@ -123,17 +123,19 @@ int grl_topk_merge(grl_handle* h, const float* all_d, const int64_t* all_i, int 
  * rows of other shards, so the per-rank results combine by a sum), finalize, and the flagged queries go through
  * grl_exact_topk per shard + grl_topk_merge.
  * coarse_d holds -q.g (metric 0) or the SQUARED L2 distance (metric 1); gmax2 [1] = max |g|^2 over the shard (combine
- * shards with a max); flags int32 [nq], nflag int32 [1].                                                                */
+ * shards with a max); dirty int32 [nq] = 1 where a per-chunk candidate buffer overflowed (only the first chunk's distance
+ * tile is ever stored, so such a row cannot be rescanned: it is flagged and brute-forced; combine shards with a max; may be
+ * NULL for grl_topk_finalize); flags int32 [nq], nflag int32 [1].                                                                */
 int grl_topk_kprime(int k);
 size_t grl_coarse_topk_workspace_bytes(int nq, int ng, int dim);
 int grl_coarse_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int kprime,
-                    int64_t idx_base, float* coarse_d, int64_t* coarse_i, float* gmax2, void* workspace,
+                    int64_t idx_base, float* coarse_d, int64_t* coarse_i, float* gmax2, int32_t* dirty, void* workspace,
                     size_t workspace_bytes, void* stream);
 int grl_rescore(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int64_t idx_base,
                 const int64_t* cand_i, int kprime, float* exact_d, void* stream);
 int grl_topk_finalize(grl_handle* h, int metric, const float* q, int nq, int dim, const float* coarse_d, const int64_t* cand_i,
-                      const float* exact_d, int kprime, const float* gmax2, int k, float* top_d, int64_t* top_i,
-                      int32_t* flags, int32_t* nflag, void* stream);
+                      const float* exact_d, int kprime, const float* gmax2, const int32_t* dirty, int k, float* top_d,
+                      int64_t* top_i, int32_t* flags, int32_t* nflag, void* stream);
 size_t grl_exact_topk_workspace_bytes(int nq, int ng, int dim);
 int grl_exact_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k, int64_t idx_base,
                    float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream);

@@ -40,7 +40,10 @@ class NumpyStages(object):
             v = np.concatenate([v, np.full((v.shape[0], pad), np.inf, np.float32)], 1)
             i = np.concatenate([i, np.full((i.shape[0], pad), -1, np.int64)], 1)
         gmax2 = float((gf.numpy().astype(np.float64) ** 2).sum(1).max())
-        return torch.from_numpy(v), torch.from_numpy(i), torch.tensor([gmax2], dtype=torch.float32)
+        dirty = torch.zeros(qf.shape[0], dtype=torch.int32)
+        if idx_base == 0:
+            dirty[1] = 1                            # pretend one candidate buffer overflowed on the first shard
+        return torch.from_numpy(v), torch.from_numpy(i), torch.tensor([gmax2], dtype=torch.float32), dirty
 
     @staticmethod
     def merge(all_d, all_i):
@@ -62,9 +65,10 @@ class NumpyStages(object):
         return torch.from_numpy(out)
 
     @staticmethod
-    def finalize(qf, cd, ci, ed, gmax2, k, metric):
+    def finalize(qf, cd, ci, ed, gmax2, dirty, k, metric):
         from oracle import eval_oracle as eo
         d, i, f = eo.finalize_topk(qf.numpy(), cd.numpy(), ci.numpy(), ed.numpy(), float(gmax2[0]), k, metric)
+        f = np.maximum(f, dirty.numpy().astype(np.int32))
         return torch.from_numpy(d), torch.from_numpy(i), torch.from_numpy(f)
 
     @staticmethod

@@ -197,9 +197,10 @@ def test_staged_search_over_simulated_shards(metric, dup_every, k):
         spans = [ev.shard_bounds(ng, shards, r) for r in range(shards)]
         coarse = [st.coarse(qd, gd[lo:lo + n].contiguous(), kp, lo, metric) for lo, n in spans]
         gmax2 = torch.stack([c[2] for c in coarse]).max(dim=0).values
+        dirty = torch.stack([c[3] for c in coarse]).max(dim=0).values
         cd, ci = st.merge(torch.stack([c[0] for c in coarse]), torch.stack([c[1] for c in coarse]))
         ed = sum(st.rescore(qd, gd[lo:lo + n].contiguous(), ci, lo, metric) for lo, n in spans)
-        top_d, top_i, flags = st.finalize(qd, cd, ci, ed, gmax2, k, metric)
+        top_d, top_i, flags = st.finalize(qd, cd, ci, ed, gmax2, dirty, k, metric)
         rows = torch.nonzero(flags).flatten()
         n_flagged.append(int(rows.numel()))
         if rows.numel():
@@ -240,6 +241,26 @@ def test_dist_topk_large_query_block(metric):
         od, oi = ev.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
         assert np.array_equal(oi.cpu().numpy(), i_ref), shards
         assert np.array_equal(od.cpu().numpy(), v_ref), shards
+
+
+@pytest.mark.parametrize("nq", [8, 1100])
+def test_dist_topk_adversarial_order_overflows_to_brute_force(nq):
+    """A gallery sorted so that every later row is closer to query 0 than all earlier ones: after the first (stored) chunk every
+    column of every chunk passes query 0's threshold, its candidate buffer overflows with no tile to rescan, the row is marked
+    dirty and must come back exact from the brute-force leg.  nq = 8: gemm.cuh single-plane kernel; 1100: coarse_gemm.cuh."""
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    ng, dim, k = 6000, 64, 30
+    q, g = _retrieval_inputs(nq, ng, dim, 77, dup_every=0)
+    g = g[np.argsort(-(g @ q[0]), kind="stable")[::-1].copy()]            # ascending similarity to q[0] == descending distance
+    qd, gd = torch.from_numpy(q).cuda(), torch.from_numpy(np.ascontiguousarray(g)).cuda()
+    for metric in (0, 1):
+        st = ev.CudaSearchStages
+        cd, ci, gmax2, dirty = st.coarse(qd, gd, st.kprime(k), 0, metric)
+        assert int(dirty[0]) == 1 and int(dirty.sum()) < max(2, nq // 10)
+        d, i = ev.retrieve_topk(qd, gd, k, metric=metric)
+        v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q, g, metric), k)
+        assert np.array_equal(i.cpu().numpy(), i_ref) and np.array_equal(d.cpu().numpy(), v_ref)
 
 
 def test_exact_topk_brute_force_matches_oracle():
