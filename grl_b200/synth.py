@@ -220,3 +220,22 @@ def make_tail_input(n: int, T: int, seed: int = 11, dtype=torch.float32):
     fc = np.abs(base + 0.4 * rng.standard_normal((n, T, C_FEAT), dtype=np.float32)).astype(np.float32)
     fu = np.abs(base[:, 0] + 0.4 * rng.standard_normal((n, C_FEAT), dtype=np.float32)).astype(np.float32)
     return torch.from_numpy(fu).to(dtype), torch.from_numpy(fc).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# Loss neighbours: clip descriptors, identity labels and an OIM look-up table.
+# ------------------------------------------------------------------------------------------------
+def make_loss_inputs(B: int, D: int, C: int, seed: int = 0, n_ids: int = 8):
+    """Unit-norm descriptors clustered by identity (like the model's normalised outputs), labels with repeats (the
+    sampler draws several clips per identity: the OIM update must compose them in batch order), a row-normalised table.
+    One identity appears once only (no positive) and two rows are duplicates (zero distance)."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, n_ids, (B,), generator=g)
+    ids[0] = n_ids                                   # singleton identity: no positive in the batch
+    cent = torch.randn((n_ids + 1, D), generator=g)
+    feat = torch.nn.functional.normalize(cent[ids] + 0.7 * torch.randn((B, D), generator=g), dim=1)
+    feat[2] = feat[1]
+    ids[2] = ids[1]
+    lut = torch.nn.functional.normalize(torch.randn((C, D), generator=g), dim=1)
+    targets = (ids * 7 + 3) % C                      # class indices spread over the table, repeats preserved
+    return feat.float(), ids.long(), lut.float(), targets.long()

@@ -267,6 +267,25 @@ size_t grl_eval_descriptor_workspace_bytes(int n, int T);
 int grl_eval_descriptor(grl_handle* h, const grl_tail_params* p, const float* f_uncorr, const float* f_corr, int n, int T,
                         int apply_tail_bn, float* out, long long ld_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- loss neighbours of the head ------------------------------------------------------------------- */
+/* OIMLoss (reid/loss/oim.py:8-58): logits = scalar * x @ lut^T [B][C] (the module's second return value), probs = softmax,
+ * row_loss [B], loss [1] = mean cross-entropy (F.cross_entropy).  Backward = the legacy OIM.backward contract (:19-27):
+ * dx = d_loss * scalar / B * (probs - onehot) @ lut with the table BEFORE its update (dx may be NULL), then
+ * lut[y] = momentum * lut[y] + (1 - momentum) * x_i; lut[y] /= |lut[y]| for every sample in batch order (in place).       */
+int grl_oim_forward(grl_handle* h, const float* x, const int64_t* targets, const float* lut, int B, int C, int D, float scalar,
+                    float* logits, float* probs, float* row_loss, float* loss, void* stream);
+int grl_oim_backward(grl_handle* h, const float* x, const int64_t* targets, float* lut, const float* probs, int B, int C, int D,
+                     float scalar, float momentum, const float* d_loss, float* dx, void* stream);
+/* TripletLoss(margin, batch_hard=True).forward(feat, id) (reid/loss/triplet.py:16-90; mode 'id', dis_func 'eu', n_dis 0):
+ * loss [B] = log(1 + exp(z)) (soft != 0) or clamp(z + margin, 0), z = hardest positive - hardest negative distance.
+ * The forward also returns what the backward needs: z, the two arg-extrema (pos_idx = -1 when the row has no positive)
+ * and their distances.                                                                                                   */
+int grl_triplet_forward(grl_handle* h, const float* feat, const int64_t* ids, int B, int D, int soft, float margin, float* loss,
+                        float* z, int32_t* pos_idx, int32_t* neg_idx, float* pos_d, float* neg_d, void* stream);
+int grl_triplet_backward(grl_handle* h, const float* feat, int B, int D, int soft, float margin, const float* z,
+                         const int32_t* pos_idx, const int32_t* neg_idx, const float* pos_d, const float* neg_d,
+                         const float* d_loss, float* dfeat, void* stream);
+
 /* Debug/test: byte offset and size of a named intermediate inside the head workspace
  * (e.g. "xp_hi", "y1", "m", "f2", "memo_h1").  Returns GRL_EINVAL for unknown names.         */
 int grl_head_ws_lookup(int B, int T, int save_for_backward, const char* name, size_t* offset, size_t* bytes);

@@ -179,6 +179,31 @@ def rerank_fixture(att, name, nq, ng_extra, dim, seed, k1, k2, lam, noise=0.6):
     print("wrote", name, final.shape, final.dtype)
 
 
+def loss_fixture(name, B, D, C, seed, n_ids):
+    """The REAL TripletLoss('soft', True) (reid/loss/triplet.py, as built at reid/train/trainer.py:12) on seeded features:
+    values and autograd gradients in float64; plus OIMLoss's forward arithmetic (oim.py:15,54,56) with torch's own ops."""
+    from reid.loss.triplet import TripletLoss
+    from grl_b200 import synth
+    feat, ids, lut, targets = synth.make_loss_inputs(B, D, C, seed, n_ids)
+    out = dict(B=B, D=D, C=C, seed=seed, n_ids=n_ids)
+    for margin, tag in (('soft', 'soft'), (0.3, 'm03')):
+        f = feat.double().clone().requires_grad_(True)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            b_loss = TripletLoss(margin, True)(f, ids)
+        gw = torch.linspace(0.5, 1.5, B, dtype=torch.float64)
+        (b_loss * gw).sum().backward()
+        out["tri_%s_loss" % tag] = b_loss.detach().numpy()
+        out["tri_%s_dfeat" % tag] = f.grad.numpy()
+    x = feat.double().clone().requires_grad_(True)
+    logits = x.mm(lut.double().t()) * 30.0
+    loss = torch.nn.functional.cross_entropy(logits, targets)
+    loss.backward()
+    out.update(oim_loss=float(loss), oim_logits=logits.detach().numpy(), oim_dx=x.grad.numpy())
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name, "triplet soft mean %.4f oim loss %.4f" % (out["tri_soft_loss"].mean(), float(loss)))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -193,6 +218,8 @@ def main():
     # fewer than max_rank gallery rows, so "num_g < max_rank" (:136-138) cannot be pinned; use max_rank=10.
     eval_fixture(att, eva, "eval_rank10", 20, 100, 32, seed=4, noise=1.0, max_rank=10)
     eval_fixture(att, eva, "eval_ties", 40, 160, 16, seed=5, noise=1.0, quantize=8)  # exact ties
+    loss_fixture("loss_b32", 32, 2048, 625, seed=21, n_ids=8)
+    loss_fixture("loss_b12", 12, 256, 40, seed=22, n_ids=5)
     rerank_fixture(att, "rerank_k20", 48, 160, 64, seed=11, k1=20, k2=6, lam=0.3)
     rerank_fixture(att, "rerank_k6", 30, 100, 32, seed=12, k1=6, k2=3, lam=0.5)
     rerank_fixture(att, "rerank_k5_noqe", 25, 90, 32, seed=13, k1=5, k2=1, lam=0.3)      # k2 == 1 skips :78-83
