@@ -241,6 +241,51 @@ def head_backward_raw(sd, x, B, T, ws, d_f_uncorr, d_f_corr, d_x_uncorr=None, d_
     return dx, grads
 
 
+class GraphedHeadStep(object):
+    """One train-mode head step -- grl_head_forward (activations saved) + grl_head_backward -- captured ONCE in a CUDA graph
+    and replayed: ~300 kernel launches, the fork/join events of the library's internal side stream and the BatchNorm
+    bookkeeping become a single graph launch, so the step costs the host one call and the device no launch gaps.
+
+        step = GraphedHeadStep(sd, B, T)           # sd: {reference state_dict key: CUDA tensor}, parameters AND buffers
+        step.x.copy_(layer4_maps); step.d_f_uncorr.copy_(...); step.d_f_corr.copy_(...)
+        step()                                     # replay on the current stream
+        step.f_uncorr, step.f_corr, step.corr_map, step.dx, step.grads[name]   # static output tensors
+
+    The tensors of `sd` are read (and the BN running buffers / num_batches_tracked updated) in place at every replay, so an
+    optimizer that updates the parameters in place composes with it.  The reference has no counterpart (it runs eager)."""
+
+    def __init__(self, sd, B, T, device=None):
+        dev = torch.device(device) if device is not None else next(iter(sd.values())).device
+        self.B, self.T, self.sd = B, T, sd
+        self.x = torch.zeros((B * T, 2048, 16, 8), device=dev)
+        self.d_f_uncorr = torch.zeros((B, 2048), device=dev)
+        self.d_f_corr = torch.zeros((B, T, 2048), device=dev)
+        self._ws = _alloc_ws(workspace_bytes(B, T, True), dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                    # warm-up outside the capture: attribute calls, tensor-map cache, allocator
+            self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._run()
+
+    def _run(self):
+        B, T = self.B, self.T
+        self.f_uncorr, self.f_corr, self.corr_map, _, _, _ = head_forward_raw(self.sd, self.x, B, T, True, save=True, ws=self._ws)
+        self.dx, self.grads = head_backward_raw(self.sd, self.x, B, T, self._ws, self.d_f_uncorr, self.d_f_corr)
+        with torch.no_grad():                            # torch/nn/modules/batchnorm.py: +1 per BN call in train mode
+            for prefix in head_buffer_names():
+                key = prefix + ".num_batches_tracked"
+                if key in self.sd:
+                    self.sd[key] += T if "uncorr_memo" in prefix else 1
+
+    def __call__(self):
+        self.graph.replay()
+        return self.f_uncorr, self.f_corr, self.dx, self.grads
+
+
 def _check_maps(t, B, T, what):
     if not t.is_cuda:
         raise RuntimeError("grl_b200 head needs CUDA tensors (no CPU path exists)")

@@ -339,3 +339,33 @@ def test_fused_head_with_map_outputs_backward_vs_fp64_reference():
     named = dict(model.named_parameters())
     for k in ("backbone.corr_atte.0.weight", "backbone.corr_atte.2.weight", "temporal_learning_block.forward_f1.0.weight"):
         assert rel(named[k].grad, p64[k].grad.reshape(named[k].shape)) < KINK_TOL, k
+
+
+def test_graphed_head_step_replays_bit_identically():
+    """GraphedHeadStep (CUDA graph of grl_head_forward + grl_head_backward, side-stream fork/join included) == the eager
+    calls, bit for bit, including the BN running buffers and num_batches_tracked after several replays."""
+    from grl_b200 import head
+    B, T = 2, 3
+    x = synth.make_head_input(B, T).cuda()
+    gu, gc = synth.make_head_grads(B, T)
+    gu, gc = gu.cuda(), gc.cuda()
+    fresh = lambda: {k: v.cuda().contiguous() for k, v in synth.make_head_params(0).items()}
+    sd_e, sd_g = fresh(), fresh()
+    step = head.GraphedHeadStep(sd_g, B, T)               # construction itself runs the step (warm-up + capture)
+    for k, v in fresh().items():
+        sd_g[k].copy_(v)
+    step.x.copy_(x); step.d_f_uncorr.copy_(gu); step.d_f_corr.copy_(gc)
+    ws = None
+    for it in range(3):
+        fu, fc, cm, _, _, ws = head.head_forward_raw(sd_e, x, B, T, True, save=True, ws=ws)
+        dx, grads = head.head_backward_raw(sd_e, x, B, T, ws, gu, gc)
+        gfu, gfc, gdx, ggr = step()
+        torch.cuda.synchronize()
+        assert torch.equal(gfu, fu) and torch.equal(gfc, fc) and torch.equal(gdx, dx) and torch.equal(step.corr_map, cm), it
+        for k in grads:
+            assert torch.equal(ggr[k], grads[k]), (it, k)
+    for k in sd_e:
+        if "running" in k:
+            assert torch.equal(sd_g[k], sd_e[k]), k
+    k = "temporal_learning_block.uncorr_memo_forward.bn1.num_batches_tracked"
+    assert int(sd_g[k]) == 3 * T                          # the eager raw calls leave the counter to the module wrapper
