@@ -243,16 +243,38 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_update_kernel(const float* 
     int64_t* ti = top_i + (long long)row * k;
     int nsort;
     if (cnt <= cap) {
-        int npad = 2;
-        while (npad < k + cnt) npad <<= 1;
-        for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-            uint64_t key = ~0ull;
-            if (i < k) { if (ti[i] >= 0) key = make_key(td[i], (uint32_t)ti[i]); }
-            else if (i < k + cnt) key = cand[(long long)row * cap + (i - k)];
-            keys[i] = key;
+        // sort the candidates alone (cnt <= cap keys), then merge them into the sorted list by rank: a list key moves down by
+        // the number of candidates below it, a candidate lands at its rank plus the number of list keys below it
+        uint64_t* cs = keys;                        // [npc] sorted candidates
+        uint64_t* ls = keys + TOPK_BUF / 2;         // [k]   the running list (k <= TOPK_MAXK <= TOPK_BUF / 2)
+        int npc = 2;
+        while (npc < cnt) npc <<= 1;
+        for (int i = threadIdx.x; i < npc; i += blockDim.x) cs[i] = i < cnt ? cand[(long long)row * cap + i] : ~0ull;
+        for (int i = threadIdx.x; i < k; i += blockDim.x) ls[i] = ti[i] >= 0 ? make_key(td[i], (uint32_t)ti[i]) : ~0ull;
+        block_bitonic_sort(cs, npc);
+        for (int i = threadIdx.x; i < k + cnt; i += blockDim.x) {
+            uint64_t key;
+            int pos;
+            if (i < k) {
+                key = ls[i];
+                int lo = 0, hi = cnt;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid] < key) lo = mid + 1; else hi = mid; }
+                pos = i + lo;
+                if (lo == 0) pos = (pos == k - 1) ? pos : -1 - pos;      // unmoved: nothing to write unless it defines the threshold
+            } else {
+                key = cs[i - k];
+                int lo = 0, hi = k;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (ls[mid] < key) lo = mid + 1; else hi = mid; }
+                pos = (i - k) + lo;
+            }
+            if (pos >= 0 && pos < k) {
+                if (key == ~0ull) { td[pos] = CUDART_INF_F; ti[pos] = -1; }
+                else { td[pos] = from_orderable((uint32_t)(key >> 32)); ti[pos] = (int64_t)(key & 0xFFFFFFFFu); }
+                if (pos == k - 1) thresh_out[row] = key == ~0ull ? CUDART_INF_F : from_orderable((uint32_t)(key >> 32));
+            }
         }
-        block_bitonic_sort(keys, npad);
-        nsort = npad;
+        if (threadIdx.x == 0) cand_cnt[row] = 0;
+        return;
     } else {
         if (dist == nullptr) {
             // The candidate list overflowed in a chunk whose tile was not stored (only the first, threshold-less chunk is):
@@ -261,6 +283,24 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_update_kernel(const float* 
             return;
         }
         const float* drow = dist + (long long)row * ld;
+        if (ti[0] < 0 && ncols <= TOPK_BUF) {
+            // bootstrap (empty list, first chunk): one sort of the tile row, sized to the row
+            int npad = 2;
+            while (npad < ncols) npad <<= 1;
+            for (int i = threadIdx.x; i < npad; i += blockDim.x) keys[i] = i < ncols ? make_key(drow[i], (uint32_t)(idx_base + i)) : ~0ull;
+            block_bitonic_sort(keys, npad);
+            for (int i = threadIdx.x; i < k; i += blockDim.x) {
+                const uint64_t key = i < npad ? keys[i] : ~0ull;
+                if (key == ~0ull) { td[i] = CUDART_INF_F; ti[i] = -1; }
+                else { td[i] = from_orderable((uint32_t)(key >> 32)); ti[i] = (int64_t)(key & 0xFFFFFFFFu); }
+            }
+            if (threadIdx.x == 0) {
+                const uint64_t kth = (k - 1 < npad) ? keys[k - 1] : ~0ull;
+                thresh_out[row] = kth == ~0ull ? CUDART_INF_F : from_orderable((uint32_t)(kth >> 32));
+                cand_cnt[row] = 0;
+            }
+            return;
+        }
         for (int i = threadIdx.x; i < TOPK_BUF; i += blockDim.x) {
             uint64_t key = ~0ull;
             if (i < k && ti[i] >= 0) key = make_key(td[i], (uint32_t)ti[i]);
@@ -658,10 +698,10 @@ extern "C" int grl_distance(grl_handle* h, int metric, const float* q, const flo
 
 // ------------------------------------------------------------------ gallery-shard search: coarse tiles + streaming top-K', exact re-score
 // Column chunks of one search.  The first chunk has no thresholds yet: its tile IS stored and every row is rescanned, so it is
-// kept small (TOPK_FIRST_CHUNK columns).  Afterwards the K'-th best of n_seen columns lets ~K' * nc / n_seen candidates per row
+// kept small (TOPK_FIRST_CHUNK columns, one 1024-key sort per row).  Afterwards the K'-th best of n_seen columns lets ~K' * nc / n_seen candidates per row
 // through, so chunks grow with n_seen (at most doubling the columns seen) up to the steady-state size, whose 256 x 256 tiles
 // fill whole waves of the persistent grid; their tiles are never stored.
-constexpr int TOPK_FIRST_CHUNK = 2048;
+constexpr int TOPK_FIRST_CHUNK = 1024;
 constexpr int TOPK_CAND_CAP = 512;      // candidates per query row per column chunk (expected <= K' = 256..1024 / growth factor)
 
 static int topk_chunk_max(int nq, int ng, int num_sms) {
