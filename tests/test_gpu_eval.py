@@ -271,3 +271,31 @@ def test_exact_topk_brute_force_matches_oracle():
         d, i = ev.CudaSearchStages.exact(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda(), 50, 1000, metric)
         v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q, g, metric), 50, 1000)
         assert np.array_equal(i.cpu().numpy(), i_ref) and np.array_equal(d.cpu().numpy(), v_ref)
+
+@pytest.mark.parametrize("nq,ng,dim,k,metric", [(1, 50, 8, 1, 0), (3, 40, 100, 64, 1), (17, 700, 72, 512, 0), (5, 3000, 30, 7, 1),
+                                                (2, 5, 16, 5, 0)])
+def test_dist_topk_edge_shapes(nq, ng, dim, k, metric):
+    """One query, k = 1, k = 512 (K' = 1024), k > ng (lists padded with +inf / -1), feature sizes that are not multiples
+    of 8 (zero-padded by the wrapper: the distance definition must not change)."""
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    q, g = _retrieval_inputs(nq, ng, dim, 100 + nq + k, dup_every=0)
+    d, i = ev.retrieve_topk(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda(), k, metric=metric)
+    pad = (-dim) % 8
+    qp, gp = np.pad(q, ((0, 0), (0, pad))), np.pad(g, ((0, 0), (0, pad)))
+    v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(qp, gp, metric), k)
+    kk = min(k, ng)
+    assert np.array_equal(i.cpu().numpy()[:, :kk], i_ref) and np.array_equal(d.cpu().numpy()[:, :kk], v_ref)
+    if k > ng:
+        assert bool((i[:, ng:] == -1).all()) and bool(torch.isinf(d[:, ng:]).all())
+
+
+def test_retrieval_rejects_bad_arguments():
+    _, ev = _mods()
+    q = torch.zeros((4, 16), device="cuda")
+    with pytest.raises(RuntimeError):
+        ev.retrieve_topk(q, torch.zeros((10, 24), device="cuda"), 3)        # feature sizes differ
+    with pytest.raises(RuntimeError):
+        ev.retrieve_topk(q, torch.zeros((10, 16), device="cuda"), 513)      # k above the supported 512
+    with pytest.raises(RuntimeError):
+        ev.retrieve_topk(q, torch.zeros((10, 16), device="cuda"), 3, idx_base=2 ** 32)   # global index must fit 32 bits

@@ -369,3 +369,33 @@ def test_graphed_head_step_replays_bit_identically():
             assert torch.equal(sd_g[k], sd_e[k]), k
     k = "temporal_learning_block.uncorr_memo_forward.bn1.num_batches_tracked"
     assert int(sd_g[k]) == 3 * T                          # the eager raw calls leave the counter to the module wrapper
+
+
+@pytest.mark.parametrize("B,T,training", [(1, 1, False), (3, 5, True), (5, 8, False), (2, 1, True), (7, 2, True)])
+def test_forward_odd_shapes_vs_reference_transcription(B, T, training):
+    """Ragged sizes: a single clip / single frame (T = 1: both temporal directions degenerate to one step), odd batch sizes
+    (row counts that are not multiples of the 256-row tile pair), train and eval BN.  B = 1 in train mode is excluded:
+    BatchNorm1d over one sample raises in the reference (glo_fc.1)."""
+    _, head, ho = _mods()
+    sd = device_params()
+    x = synth.make_head_input(B, T).cuda()
+    fu, fc, cm, xu, xc, _ = head.head_forward_raw(sd, x, B, T, training, save=False, want_maps=True)
+    p64 = synth.make_head_params(0, dtype=torch.float64)
+    o = ho.ref_forward(p64, synth.make_head_input(B, T, dtype=torch.float64), B, T, training)
+    for k, v in (("f_uncorr", fu), ("f_corr", fc), ("corr_map", cm), ("x_uncorr", xu), ("x_corr", xc)):
+        assert rel(v, o[k]) < 1e-4, (k, rel(v, o[k]))
+    if training:
+        for k in p64:
+            if "running" in k:
+                assert rel(sd[k], p64[k]) < 2e-5, k
+
+
+def test_head_rejects_bad_inputs():
+    _, head, _ = _mods()
+    sd = device_params()
+    with pytest.raises(RuntimeError):
+        head.head_forward_raw(sd, torch.zeros((6, 2048, 16, 8)), 2, 3, False, save=False)           # CPU tensor
+    with pytest.raises(RuntimeError):
+        head.head_forward_raw(sd, torch.zeros((6, 2048, 8, 16), device="cuda"), 2, 3, False, save=False)   # wrong map size
+    with pytest.raises(RuntimeError):
+        head.head_forward_raw(sd, torch.zeros((5, 2048, 16, 8), device="cuda"), 2, 3, False, save=False)   # b*t mismatch

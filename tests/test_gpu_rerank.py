@@ -72,3 +72,19 @@ def test_rerank_mars_shape_properties():
     cmc0, map0 = evaluator.evaluate(q_g, qp, gp, qc, gcam)
     cmc1, map1 = evaluator.evaluate(final, qp, gp, qc, gcam)
     assert map1 >= map0 - 1e-3, (map0, map1)
+
+
+@pytest.mark.parametrize("nq,ng,k1,k2", [(1, 6, 20, 6), (4, 9, 3, 2), (30, 90, 20, 6)])
+def test_rerank_tiny_and_tied_inputs(nq, ng, k1, k2):
+    """N smaller than k1 + 1 (every row is everybody's neighbour), a single query, and exact distance ties (quantised
+    distances): neighbour ties go to the lower index on both sides (the oracle argsorts stably, like the kernel)."""
+    from grl_b200.rerank import re_ranking
+    from oracle import rerank_oracle as ro
+    rng = np.random.default_rng(nq * 100 + ng)
+    f = rng.standard_normal((nq + ng, 12)).astype(np.float32)
+    d = np.sqrt(np.maximum(((f[:, None] - f[None]) ** 2).sum(-1), 1e-12)).astype(np.float32)
+    d = (np.round(d * 4) / 4 + 0.25).astype(np.float32)          # heavy ties, strictly positive
+    q_g, q_q, g_g = d[:nq, nq:], d[:nq, :nq], d[nq:, nq:]
+    got = re_ranking(np.ascontiguousarray(q_g), np.ascontiguousarray(q_q), np.ascontiguousarray(g_g), k1=k1, k2=k2)
+    ref = ro.re_ranking(q_g, q_q, g_g, k1, k2, 0.3)
+    assert got.shape == ref.shape and np.abs(got - ref).max() < TOL
