@@ -486,6 +486,18 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline()
+        if eval_line is not None:
+            # the reference's evaluate (literal restatement: np.argsort + the per-query Python loop, eva_functions.py:134-184)
+            # on a BOUNDED sample: the first 200 of the 1,980 queries against the full 9,330-row gallery
+            from oracle import eval_oracle as eo
+            qf_c, gf_c, qp_c, gp_c, qc_c, gc_c = synth.make_eval_set(1980, 7350, 2048, seed=0, noise=4.0)
+            t0 = time.perf_counter()
+            eo.evaluate_literal(eo.cosin_dist(qf_c[:200], gf_c), qp_c[:200], gp_c, qc_c[:200], gc_c)
+            dt_c = time.perf_counter() - t0
+            eval_line["cpu_port"] = {"queries_per_s": 200 / dt_c, "cores": 1, "kind": "port",
+                                     "sample": "cosin_dist + evaluate, 200 queries x 9,330 gallery rows x 2048-d in %.2f s (the port vectorises the "
+                                               "reference's per-query Python list comprehension, eva_functions.py:172, which alone takes "
+                                               "31.9 s for the 1,980 queries: SURVEY.md section 6)" % dt_c}
         if rerank_line is not None:
             # the reference's re_ranking (oracle restatement, bit-identical to it) on a BOUNDED sample: 200 queries + 1,000 gallery rows;
             # its dense N x N stages grow with N^2, so the full 11,310-row problem is ~90x this time
