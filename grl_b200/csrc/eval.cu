@@ -189,7 +189,9 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_rows_kernel(const float* __
     __syncthreads();
     if (threadIdx.x == 0) thresh = keys[k - 1];      // lists are kept sorted, so this is the k-th best
     __syncthreads();
-    const int stage_cap = TOPK_BUF - TOPK_WAVE;      // flush when a full wave might not fit
+    // flush when a full wave might not fit -- and, for short lists, as soon as one wave is staged: the first flush is what
+    // establishes a threshold, after which almost nothing passes the filter
+    const int stage_cap = k <= 256 ? TOPK_WAVE : TOPK_BUF - TOPK_WAVE;
     for (int c0 = 0; c0 < ncols; c0 += TOPK_WAVE) {
         const uint64_t th = thresh;
 #pragma unroll
@@ -204,8 +206,10 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_rows_kernel(const float* __
         const bool last = c0 + TOPK_WAVE >= ncols;
         if (count > stage_cap || (last && count > k)) {
             const int n = count;
-            for (int i = n + threadIdx.x; i < TOPK_BUF; i += blockDim.x) keys[i] = ~0ull;
-            block_bitonic_sort(keys, TOPK_BUF);
+            int npad = 2;
+            while (npad < n) npad <<= 1;                 // sort no more than what is staged
+            for (int i = n + threadIdx.x; i < npad; i += blockDim.x) keys[i] = ~0ull;
+            block_bitonic_sort(keys, npad);
             if (threadIdx.x == 0) { count = k; thresh = keys[k - 1]; }
             __syncthreads();
         }
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_update_kernel(const float* 
         __syncthreads();
         if (threadIdx.x == 0) thresh = keys[k - 1];
         __syncthreads();
-        const int stage_cap = TOPK_BUF - TOPK_WAVE;
+        const int stage_cap = k <= 256 ? TOPK_WAVE : TOPK_BUF - TOPK_WAVE;
         for (int c0 = 0; c0 < ncols; c0 += TOPK_WAVE) {
             const uint64_t th = thresh;
 #pragma unroll
@@ -325,8 +329,10 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_update_kernel(const float* 
             const bool last = c0 + TOPK_WAVE >= ncols;
             if (count > stage_cap || (last && count > k)) {
                 const int n = count;
-                for (int i = n + threadIdx.x; i < TOPK_BUF; i += blockDim.x) keys[i] = ~0ull;
-                block_bitonic_sort(keys, TOPK_BUF);
+                int npad = 2;
+                while (npad < n) npad <<= 1;
+                for (int i = n + threadIdx.x; i < npad; i += blockDim.x) keys[i] = ~0ull;
+                block_bitonic_sort(keys, npad);
                 if (threadIdx.x == 0) { count = k; thresh = keys[k - 1]; }
                 __syncthreads();
             }
