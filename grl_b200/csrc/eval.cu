@@ -192,10 +192,14 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_rows_kernel(const float* __
     // flush when a full wave might not fit -- and, for short lists, as soon as one wave is staged: the first flush is what
     // establishes a threshold, after which almost nothing passes the filter
     const int stage_cap = k <= 256 ? TOPK_WAVE : TOPK_BUF - TOPK_WAVE;
-    for (int c0 = 0; c0 < ncols; c0 += TOPK_WAVE) {
+    int c0 = 0;
+    while (c0 < ncols) {
         const uint64_t th = thresh;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        // a short list without a threshold yet: stage ONE column per thread and sort right away (a 512-key sort instead of a
+        // 2048-key one); with the threshold of 256 columns in place only ~k * ln(ncols / 256) more keys are ever staged
+        const bool boot = th == ~0ull && k <= 128;
+        const int nu = boot ? 1 : 4;
+        for (int u = 0; u < nu; ++u) {
             const int c = c0 + u * TOPK_THREADS + threadIdx.x;
             if (c < ncols) {
                 const uint64_t key = make_key(drow[c], (uint32_t)(idx_base + c));
@@ -203,8 +207,9 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_rows_kernel(const float* __
             }
         }
         __syncthreads();
-        const bool last = c0 + TOPK_WAVE >= ncols;
-        if (count > stage_cap || (last && count > k)) {
+        c0 += nu * TOPK_THREADS;
+        const bool last = c0 >= ncols;
+        if (count > stage_cap || (boot && count > k) || (last && count > k)) {
             const int n = count;
             int npad = 2;
             while (npad < n) npad <<= 1;                 // sort no more than what is staged
