@@ -63,6 +63,17 @@ class TailParams(C.Structure):
                 ("featK_w", C.c_void_p), ("featK_b", C.c_void_p), ("featK_bn", BnParams)]
 
 
+class SiameseParams(C.Structure):
+    _fields_ = [("featQ_w", C.c_void_p), ("featQ_b", C.c_void_p), ("featQ_bn", BnParams),
+                ("featK_w", C.c_void_p), ("featK_b", C.c_void_p), ("featK_bn", BnParams),
+                ("cls_bn", BnParams), ("cls_w", C.c_void_p), ("cls_b", C.c_void_p)]
+
+
+class SiameseGrads(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("featQ_w", "featQ_b", "featQ_bn_w", "featQ_bn_b", "featK_w", "featK_b", "featK_bn_w",
+                                          "featK_bn_b", "cls_bn_w", "cls_bn_b", "cls_w", "cls_b")]
+
+
 _SIGNATURES = {
     "grl_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "grl_destroy": (None, [C.c_void_p]),
@@ -130,6 +141,13 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "grl_triplet_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "grl_siamese_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "grl_siamese_forward": (C.c_int, [C.c_void_p, C.POINTER(SiameseParams), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_size_t, C.c_void_p]),
+    "grl_siamese_backward": (C.c_int, [C.c_void_p, C.POINTER(SiameseParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.POINTER(SiameseGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "grl_pair_loss_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "grl_pair_loss_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "grl_head_ws_lookup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
 }
 

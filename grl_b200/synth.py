@@ -239,3 +239,35 @@ def make_loss_inputs(B: int, D: int, C: int, seed: int = 0, n_ids: int = 8):
     lut = torch.nn.functional.normalize(torch.randn((C, D), generator=g), dim=1)
     targets = (ids * 7 + 3) % C                      # class indices spread over the table, repeats preserved
     return feat.float(), ids.long(), lut.float(), targets.long()
+
+
+def make_siamese_inputs(n2: int, T: int, seed: int = 0):
+    """Parameters of Siamese(2048, 512, 2) under the reference's key names (kaiming-style Q/K/classifier weights, non-trivial
+    BN affine parameters and running buffers), normalised clip features x [2n, T, 2048] clustered by identity, seeded
+    upstream gradients for both outputs, and identity labels [2n] (pairs (2i, 2i+1) share an identity half of the time)."""
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *shape: torch.randn(shape, generator=g)
+    p = {}
+    for nm in ("featQ", "featK", "featV"):
+        p[nm + ".weight"] = r(512, 2048) * (2.0 / 2048) ** 0.5
+        p[nm + ".bias"] = 0.1 * r(512)
+        p[nm + "_bn.weight"] = 1.0 + 0.2 * r(512)
+        p[nm + "_bn.bias"] = 0.1 * r(512)
+        p[nm + "_bn.running_mean"] = 0.1 * r(512)
+        p[nm + "_bn.running_var"] = 1.0 + 0.2 * torch.rand(512, generator=g)
+        p[nm + "_bn.num_batches_tracked"] = torch.tensor(3, dtype=torch.long)
+    p["classifierBN.weight"] = 1.0 + 0.2 * r(2048)
+    p["classifierBN.bias"] = 0.1 * r(2048)
+    p["classifierBN.running_mean"] = 0.001 * torch.rand(2048, generator=g)
+    p["classifierBN.running_var"] = 1e-6 * (1.0 + torch.rand(2048, generator=g))
+    p["classifierBN.num_batches_tracked"] = torch.tensor(3, dtype=torch.long)
+    p["classifierlinear.weight"] = 0.05 * r(2, 2048)
+    p["classifierlinear.bias"] = 0.1 * r(2)
+    n_ids = max(2, n2 // 4)
+    ids = torch.randint(0, n_ids, (n2,), generator=g)
+    ids[1::4] = ids[0::4][: ids[1::4].numel()]          # every other pair shares its identity
+    cent = r(n_ids, 2048)
+    x = torch.nn.functional.normalize(cent[ids].unsqueeze(1) + 0.5 * r(n2, 1, 2048) + 0.3 * r(n2, T, 2048), dim=2)
+    d_cls = r(n2 // 2, n2 // 2, 2)
+    d_out = r(n2, 2048)
+    return p, x.float(), d_cls.float(), d_out.float(), ids.long()

@@ -286,6 +286,36 @@ int grl_triplet_backward(grl_handle* h, const float* feat, int B, int D, int sof
                          const int32_t* pos_idx, const int32_t* neg_idx, const float* pos_d, const float* neg_d,
                          const float* d_loss, float* dfeat, void* stream);
 
+/* Siamese.forward in training (reid/models/Siamese.py:108-142): temporal self-attention pooling (:79-106) of the probe half
+ * and of the gallery half (train-mode BatchNorm statistics per half, running buffers updated probe first), squared pair
+ * differences -> classifierBN -> classifierlinear.  x [2n][T][2048] holds the n probe clips first, then the n gallery clips
+ * (the reference pairs samples (2i, 2i+1): the Python mirror regroups); siamese_out [2n][2048] in the same order;
+ * cls_encode [n][n][2].  The backward needs the forward's workspace and siamese_out; d_siamese_out may be NULL; grads are
+ * overwritten.  featV / featV_bn exist in the module but take no part in forward (Siamese.py:99).  T <= 32.               */
+typedef struct grl_siamese_params {
+    const float* featQ_w; const float* featQ_b; grl_bn_params featQ_bn;     /* Linear(2048, 512), BatchNorm1d(512) */
+    const float* featK_w; const float* featK_b; grl_bn_params featK_bn;
+    grl_bn_params cls_bn; const float* cls_w; const float* cls_b;          /* BatchNorm1d(2048), Linear(2048, 2) */
+} grl_siamese_params;
+typedef struct grl_siamese_grads {
+    float* featQ_w; float* featQ_b; float* featQ_bn_w; float* featQ_bn_b;
+    float* featK_w; float* featK_b; float* featK_bn_w; float* featK_bn_b;
+    float* cls_bn_w; float* cls_bn_b; float* cls_w; float* cls_b;
+} grl_siamese_grads;
+size_t grl_siamese_workspace_bytes(int n2, int T);
+int grl_siamese_forward(grl_handle* h, const grl_siamese_params* p, const float* x, int n2, int T, int train, float* cls_encode,
+                        float* siamese_out, void* workspace, size_t workspace_bytes, void* stream);
+int grl_siamese_backward(grl_handle* h, const grl_siamese_params* p, const float* x, const float* siamese_out, int n2, int T,
+                         const float* d_cls_encode, const float* d_siamese_out, float* dx, const grl_siamese_grads* g,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* PairLoss.forward(score [n][n], tar_probe [n], tar_gallery [n]) -> (loss, prec)   reid/loss/pairloss.py:19-48: mean binary
+ * cross-entropy of the pair scores (log clamped at -100 like torch.nn.BCELoss) against label[p][g] =
+ * (tar_probe[g] == tar_gallery[p]) -- the reference's expand/eq order -- and the fraction of correct decisions.          */
+int grl_pair_loss_forward(grl_handle* h, const float* score, const int64_t* tar_probe, const int64_t* tar_gallery, int n,
+                          float* loss, float* prec, void* stream);
+int grl_pair_loss_backward(grl_handle* h, const float* score, const int64_t* tar_probe, const int64_t* tar_gallery, int n,
+                           const float* d_loss, float* d_score, void* stream);
+
 /* Debug/test: byte offset and size of a named intermediate inside the head workspace
  * (e.g. "xp_hi", "y1", "m", "f2", "memo_h1").  Returns GRL_EINVAL for unknown names.         */
 int grl_head_ws_lookup(int B, int T, int save_for_backward, const char* name, size_t* offset, size_t* bytes);

@@ -47,3 +47,48 @@ def triplet_loss(feat, ids, margin='soft', d_loss=None):
     g = torch.ones_like(b_loss) if d_loss is None else d_loss
     (b_loss * g).sum().backward()
     return b_loss.detach(), f.grad.detach()
+
+
+# --------------------------------------------------------------------------------------------
+# Verification head in training: Siamese.forward (reid/models/Siamese.py:79-142) and PairLoss (reid/loss/pairloss.py:19-48).
+# Functional restatement over a {state_dict key: tensor} dict (BN running buffers updated in place like nn.BatchNorm1d);
+# pinned to the REAL reference modules by tests/golden/siamese_*.npz.
+# --------------------------------------------------------------------------------------------
+def _sia_bn(p, prefix, x, training):
+    return F.batch_norm(x, p[prefix + ".running_mean"], p[prefix + ".running_var"], p[prefix + ".weight"], p[prefix + ".bias"],
+                        training, 0.1, 1e-5)
+
+
+def _sia_self_attention(p, inp, training):                 # Siamese.py:79-106
+    batch, length = inp.size(0), inp.size(1)
+    flat = inp.reshape(batch * length, -1)
+    q = _sia_bn(p, "featQ_bn", F.linear(flat, p["featQ.weight"], p["featQ.bias"]), training)
+    q = (q / q.norm(2, 1).unsqueeze(1)).view(batch, length, -1)
+    k = _sia_bn(p, "featK_bn", F.linear(flat, p["featK.weight"], p["featK.bias"]), training)
+    k = (k / k.norm(2, 1).unsqueeze(1)).view(batch, length, -1)
+    w = torch.softmax(torch.matmul(q, k.transpose(-1, -2)), dim=-1)
+    pool = torch.matmul(w, inp).sum(1)
+    return pool / pool.norm(2, 1).unsqueeze(1)
+
+
+def siamese_forward(p, x, training=True):
+    """Siamese.py:108-142: returns (cls_encode [n, n, 2], siamese_out [2n, D])."""
+    n2, T = x.size(0), x.size(1)
+    xv = x.view(n2 // 2, 2, T, -1)
+    pp = _sia_self_attention(p, xv[:, 0].contiguous(), training)
+    pg = _sia_self_attention(p, xv[:, 1].contiguous(), training)
+    out = torch.cat((pp, pg))
+    diff = (pp.unsqueeze(1) - pg.unsqueeze(0)) ** 2
+    y = _sia_bn(p, "classifierBN", diff.view(pp.size(0) * pg.size(0), -1), training)
+    z = F.linear(y, p["classifierlinear.weight"], p["classifierlinear.bias"])
+    return z.view(pp.size(0), pg.size(0), -1), out
+
+
+def pair_loss(score, tar_probe, tar_gallery):
+    """pairloss.py:19-48: (loss, prec); label[i][j] = (tar_probe[j] == tar_gallery[i])."""
+    n = score.size(0)
+    mask = tar_probe.unsqueeze(0).expand(n, n).eq(tar_gallery.unsqueeze(1).expand(n, n)).reshape(-1)
+    s = score.reshape(-1)
+    loss = F.binary_cross_entropy(s, mask.to(s.dtype))
+    prec = ((s.detach() > 1 - s.detach()) == mask).to(s.dtype).mean()
+    return loss, prec

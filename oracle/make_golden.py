@@ -204,6 +204,50 @@ def loss_fixture(name, B, D, C, seed, n_ids):
     print("wrote", name, "triplet soft mean %.4f oim loss %.4f" % (out["tri_soft_loss"].mean(), float(loss)))
 
 
+def siamese_fixture(name, n2, T, seed):
+    """The REAL Siamese(2048, 512, 2).forward in train mode (reid/models/Siamese.py:108-142, as built at mars_train.py:77) and the
+    REAL PairLoss (reid/loss/pairloss.py), float64 / float32: outputs, gradients for seeded upstream grads, BN buffers."""
+    from reid.models.Siamese import Siamese
+    from reid.loss.pairloss import PairLoss
+    from grl_b200 import synth
+    params, x, d_cls, d_out, tar = synth.make_siamese_inputs(n2, T, seed)
+    sia = Siamese(2048, 512, 2)
+    sd = sia.state_dict()
+    for k, v in params.items():
+        assert k in sd and sd[k].shape == v.shape, k
+        sd[k] = v.clone()
+    sia.load_state_dict(sd)
+    sia = sia.double().train()
+    xin = x.double().clone().requires_grad_(True)
+    cls, out = sia(xin)
+    ((cls * d_cls.double()).sum() + (out * d_out.double()).sum()).backward()
+    # fixtures stay small: full cls_encode, strided samples + norms of the big tensors (same sampling as the head fixtures)
+    res = dict(n2=n2, T=T, seed=seed, cls=cls.detach().numpy(), out_sample=grad_sample(out, 512), out_norm=float(out.norm()),
+               dx_sample=grad_sample(xin.grad, 512), dx_norm=float(xin.grad.norm()))
+    names, norms, samples = [], [], []
+    for k, v in sia.named_parameters():
+        if v.grad is not None:
+            names.append(k)
+            norms.append(float(v.grad.norm()))
+            smp = grad_sample(v.grad, 16)
+            samples.append(np.pad(smp, (0, 16 - smp.size)))
+    res["grad_names"] = np.array(names)
+    res["grad_norms"] = np.array(norms)
+    res["grad_samples"] = np.stack(samples)
+    bufs = {k: v for k, v in sia.state_dict().items() if "running" in k or "num_batches" in k}
+    res["buf_names"] = np.array(list(bufs.keys()))
+    res["buf_values"] = np.concatenate([v.double().reshape(-1).numpy() for v in bufs.values()])
+    # PairLoss on the softmax-ed scores exactly as the trainer feeds it (trainer.py:142-147), float32 like its labels
+    n = n2 // 2
+    score = torch.softmax(cls.detach().float().view(-1, 2), dim=-1).view(n, n, 2)[:, :, 1].clone().requires_grad_(True)
+    tv = tar.view(n, -1)
+    loss, prec = PairLoss()(score, tv[:, 0], tv[:, 1])
+    (loss * 1.7).backward()
+    res.update(pair_loss=float(loss), pair_prec=float(prec), pair_dscore=score.grad.numpy())
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **res)
+    print("wrote", name, tuple(cls.shape), "pair loss %.4f prec %.3f" % (float(loss), float(prec)))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -218,6 +262,8 @@ def main():
     # fewer than max_rank gallery rows, so "num_g < max_rank" (:136-138) cannot be pinned; use max_rank=10.
     eval_fixture(att, eva, "eval_rank10", 20, 100, 32, seed=4, noise=1.0, max_rank=10)
     eval_fixture(att, eva, "eval_ties", 40, 160, 16, seed=5, noise=1.0, quantize=8)  # exact ties
+    siamese_fixture("siamese_n32t8", 32, 8, seed=31)
+    siamese_fixture("siamese_n6t3", 6, 3, seed=32)
     loss_fixture("loss_b32", 32, 2048, 625, seed=21, n_ids=8)
     loss_fixture("loss_b12", 12, 256, 40, seed=22, n_ids=5)
     rerank_fixture(att, "rerank_k20", 48, 160, 64, seed=11, k1=20, k2=6, lam=0.3)
