@@ -221,14 +221,16 @@ def head_forward_raw(sd, x, B, T, training, save, want_maps=False, ws=None):
     return f_uncorr, f_corr, corr_map, xu, xc, ws
 
 
-def head_backward_raw(sd, x, B, T, ws, d_f_uncorr, d_f_corr, d_x_uncorr=None, d_x_corr=None, d_corr_map=None):
-    """One grl_head_backward call.  Returns (dx, {param name: grad})."""
+def head_backward_raw(sd, x, B, T, ws, d_f_uncorr, d_f_corr, d_x_uncorr=None, d_x_corr=None, d_corr_map=None, grads=None):
+    """One grl_head_backward call.  Returns (dx, {param name: grad}).  `grads`: optional pre-allocated gradient tensors
+    (e.g. views of a flat all-reduce buffer, replicas.GradientAllReduce.views()); they are overwritten."""
     lib = _lib.load_library()
     dev = x.device
     with torch.cuda.device(dev):
         h = _lib.get_handle(dev)
         p = pack_params(sd)
-        grads = {k: torch.empty_like(sd[k]) for k in head_param_names()}
+        if grads is None:
+            grads = {k: torch.empty_like(sd[k]) for k in head_param_names()}
         g = pack_grads(grads)
         dx = torch.empty_like(x)
         cont = lambda t: None if t is None else t.contiguous().float()

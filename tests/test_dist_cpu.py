@@ -133,3 +133,34 @@ def test_sharded_retrieve_world2_gloo(tmp_path, metric):
     q, g = _inputs(ng)
     v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q, g, metric), 10)
     assert np.array_equal(r["i"], i_ref) and np.array_equal(r["d"], v_ref)
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from grl_b200.replicas import GradientAllReduce
+    names, shapes = ["a.weight", "b.bias", "c"], [(3, 5), (7,), (2, 2, 2)]
+    sync = GradientAllReduce(names, shapes, "cpu")
+    results = []
+    for step in range(3):                                 # double-buffered: three steps reuse buffer 0
+        v = sync.views()
+        for i, k in enumerate(names):
+            v[k].copy_(torch.full(shapes[i], float((rank + 1) * (step + 1) * (i + 1))))
+        sync.start()
+        results.append({k: t.clone() for k, t in sync.finish().items()})
+    if rank == 0:
+        torch.save(results, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo(tmp_path):
+    """replicas.GradientAllReduce: flat double-buffered gradient all-reduce, averaged over the ranks."""
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_grad_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    results = torch.load(out)
+    for step, r in enumerate(results):
+        for i, k in enumerate(["a.weight", "b.bias", "c"]):
+            expect = (1 + 2) / 2.0 * (step + 1) * (i + 1)          # mean over ranks of (rank + 1) * (step + 1) * (i + 1)
+            assert torch.all(r[k] == expect), (step, k)
