@@ -29,6 +29,7 @@ struct grl_handle {
     cudaStream_t side;          // low-priority internal stream: work that is off the recurrence's critical path
     cudaEvent_t* events;        // pool of timing-disabled events for fork/join between the caller's stream and `side`
     int n_events, overlap;
+    void* func_attrs;           // per-device record of cudaFuncAttributeMaxDynamicSharedMemorySize settings (gemm.cu)
     char err[512];
 };
 
@@ -86,6 +87,10 @@ int split_planes(grl_handle* h, cudaStream_t st, const float* src, long long ld_
 // fp32 [rows][cols] -> transposed planes [cols][rows] (ld_dst = leading dim of the transposed planes)
 int split_planes_transposed(grl_handle* h, cudaStream_t st, const float* src, long long ld_src, __nv_bfloat16* hi,
                             __nv_bfloat16* lo, long long ld_dst, int rows, int cols);
+
+// Function attributes are per device: a process that drives several GPUs (nn.DataParallel, mars_train.py:80) must opt every
+// kernel in on every device.  Raises `func`'s dynamic shared-memory limit to `bytes` on the handle's device (once per size).
+int ensure_dyn_smem(grl_handle* h, const void* func, int bytes);
 
 // Event k of the handle's pool (grown on demand).  Events are only ever recorded/waited by the thread driving the handle.
 cudaEvent_t pool_event(grl_handle* h, int k);

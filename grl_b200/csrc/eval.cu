@@ -795,8 +795,7 @@ extern "C" int grl_coarse_topk(grl_handle* h, int metric, const float* q, const 
     unsigned long long* cand = (unsigned long long*)(w + L.cand);
     GRL_CUDA(h, cudaMemsetAsync(gmax2, 0, 4, st));
     GRL_CUDA(h, cudaMemsetAsync(dirty, 0, (size_t)nq * 4, st));
-    if ((size_t)8 * kprime * 8 > 48 * 1024)
-        GRL_CUDA(h, cudaFuncSetAttribute(topk_update_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * TOPK_MAXK * 8));
+    GRL_TRY(ensure_dyn_smem(h, (const void*)topk_update_small_kernel, 8 * kprime * 8));
     topk_filter_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(thresh, cand_cnt, nq, TOPK_CAND_CAP);
     GRL_LAUNCH_CHECK(h);
     // the query norms go to a scratch max (cand is free until the first GEMM): only the gallery maximum is reported
@@ -833,7 +832,7 @@ extern "C" int grl_rescore(grl_handle* h, int metric, const float* q, const floa
     if (!h || !q || !g || !cand_i || !exact_d) return set_error(h, GRL_EINVAL, "grl_rescore: NULL argument");
     if (nq <= 0 || ng <= 0 || dim <= 0 || (dim & 7) || dim > 32768 || kprime <= 0) return set_error(h, GRL_EINVAL, "grl_rescore: bad sizes");
     const size_t smem = (size_t)dim * 4;
-    if (smem > 48 * 1024) GRL_CUDA(h, cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GRL_TRY(ensure_dyn_smem(h, (const void*)rescore_kernel, (int)smem));
     rescore_kernel<<<nq, 256, smem, (cudaStream_t)stream>>>(metric, q, g, ng, dim, idx_base, cand_i, kprime, exact_d);
     GRL_LAUNCH_CHECK(h);
     return GRL_OK;
@@ -868,7 +867,7 @@ static int exact_topk_rows(grl_handle* h, int metric, const float* q, const int3
     // rows == NULL: query r is row r of q and results go to top_d/top_i[r]; else query rows[r], results scattered to row rows[r]
     const int R = exact_group_rows(dim);
     const size_t smem = (size_t)R * dim * 4;
-    if (smem > 48 * 1024) GRL_CUDA(h, cudaFuncSetAttribute(exact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GRL_TRY(ensure_dyn_smem(h, (const void*)exact_rows_kernel, (int)smem));
     for (int r0 = 0; r0 < nrows; r0 += R) {
         const int rq = std::min(R, nrows - r0);
         exact_rows_kernel<<<h->num_sms * 4, 256, (size_t)rq * dim * 4, st>>>(metric, q, rows, r0, rq, g, ng, dim, tile, ng);
@@ -982,11 +981,7 @@ extern "C" int grl_argsort_rows(grl_handle* h, const float* dist, long long ld_d
     if (nq <= 0 || ng <= 0 || ng > 16384) return set_error(h, GRL_EINVAL, "grl_argsort_rows: need 0 < ng <= 16384 (ng=%d)", ng);
     const int npad = next_pow2(ng < 2 ? 2 : ng);
     const size_t smem = (size_t)npad * 8;
-    static bool configured = false;
-    if (!configured) {
-        GRL_CUDA(h, cudaFuncSetAttribute(argsort_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-        configured = true;
-    }
+    GRL_TRY(ensure_dyn_smem(h, (const void*)argsort_rows_kernel, 16384 * 8));
     argsort_rows_kernel<<<nq, 1024, smem, (cudaStream_t)stream>>>(dist, ld_dist, ng, npad, order);
     GRL_LAUNCH_CHECK(h);
     return GRL_OK;
@@ -1015,11 +1010,7 @@ extern "C" int grl_topk_merge(grl_handle* h, const float* all_d, const int64_t* 
     if (!h || !all_d || !all_i || !out_d || !out_i) return set_error(h, GRL_EINVAL, "grl_topk_merge: NULL argument");
     if (nshards <= 0 || nq <= 0 || k <= 0 || (long long)nshards * k > 16384) return set_error(h, GRL_EINVAL, "grl_topk_merge: nshards*k must be <= 16384");
     const int npad = next_pow2(nshards * k < 2 ? 2 : nshards * k);
-    static bool configured = false;
-    if (!configured) {
-        GRL_CUDA(h, cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-        configured = true;
-    }
+    GRL_TRY(ensure_dyn_smem(h, (const void*)topk_merge_kernel, 16384 * 8));
     topk_merge_kernel<<<nq, 256, (size_t)npad * 8, (cudaStream_t)stream>>>(all_d, all_i, nshards, nq, k, npad, out_d, out_i);
     GRL_LAUNCH_CHECK(h);
     return GRL_OK;

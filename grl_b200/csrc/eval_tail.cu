@@ -211,14 +211,8 @@ extern "C" int grl_eval_descriptor(grl_handle* h, const grl_tail_params* p, cons
         GRL_TRY(gemm_launch(h, st, rows, 2 * TA, TC, 1, a, b, e, 128));
     }
     const size_t smem = ((size_t)2 * T * TA + (size_t)T * T + T) * sizeof(float);
-    if (smem > 48 * 1024) {
-        static bool configured = false;
-        if (!configured) {
-            GRL_CUDA(h, cudaFuncSetAttribute(tail_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            configured = true;
-        }
-        if (smem > 220 * 1024) return set_error(h, GRL_EINVAL, "grl_eval_descriptor: T = %d needs %zu bytes of shared memory", T, smem);
-    }
+    if (smem > 220 * 1024) return set_error(h, GRL_EINVAL, "grl_eval_descriptor: T = %d needs %zu bytes of shared memory", T, smem);
+    GRL_TRY(ensure_dyn_smem(h, (const void*)tail_attention_kernel, (int)smem));
     tail_attention_kernel<<<n, 256, smem, st>>>(qk, xc, T, p->featQ_bn, p->featK_bn, out, ld_out);
     GRL_LAUNCH_CHECK(h);
     return GRL_OK;

@@ -3,9 +3,11 @@
 #include "api.h"
 #include "coarse_gemm.cuh"
 
+#include <utility>
 #include <vector>
 
 struct grl_prof { std::vector<grl_prof_rec> recs; };
+typedef std::vector<std::pair<const void*, int>> grl_func_attrs;
 
 namespace grl {
 
@@ -17,6 +19,21 @@ int set_error(grl_handle* h, int code, const char* fmt, ...) {
     vsnprintf(dst, 512, fmt, ap);
     va_end(ap);
     return code;
+}
+
+int ensure_dyn_smem(grl_handle* h, const void* func, int bytes) {
+    if (bytes <= 48 * 1024) return GRL_OK;
+    grl_func_attrs* fa = static_cast<grl_func_attrs*>(h->func_attrs);
+    for (auto& e : *fa)
+        if (e.first == func) {
+            if (e.second >= bytes) return GRL_OK;
+            GRL_CUDA(h, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            e.second = bytes;
+            return GRL_OK;
+        }
+    GRL_CUDA(h, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    fa->push_back(std::make_pair(func, bytes));
+    return GRL_OK;
 }
 
 // ------------------------------------------------------------------ fork / join helpers
@@ -140,11 +157,7 @@ static int make_tmap(grl_handle* h, CUtensorMap* map, const void* base, long lon
 template <int BN, bool A_MN, bool B_MN, int PLANES = 3>
 static int launch_variant(grl_handle* h, cudaStream_t st, const GemmParams& p, int grid) {
     auto kern = gemm_bf16x3_kernel<BN, A_MN, B_MN, PLANES>;
-    static bool configured = false;   // per instantiation
-    if (!configured) {
-        GRL_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, PLANES>::SMEM_BYTES));
-        configured = true;
-    }
+    GRL_TRY(ensure_dyn_smem(h, (const void*)kern, GemmCfg<BN, PLANES>::SMEM_BYTES));
     grl_prof_rec rec;
     if (h->prof_on) {    // bench.py roofline: bracket the launch with events on the caller's stream
         GRL_CUDA(h, cudaEventCreate(&rec.e0));
@@ -238,11 +251,7 @@ int coarse_gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, cons
     p.epi = epi;
     GRL_TRY(make_tmap(h, &p.ta, A, lda, 0, 0, M, K, 1, CG_BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
     GRL_TRY(make_tmap(h, &p.tb, B, ldb, 0, 0, N, K, 1, CG_BN, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
-    static bool configured = false;
-    if (!configured) {
-        GRL_CUDA(h, cudaFuncSetAttribute(coarse_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM_BYTES));
-        configured = true;
-    }
+    GRL_TRY(ensure_dyn_smem(h, (const void*)coarse_gemm_kernel, CG_SMEM_BYTES));
     const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
     const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
     grl_prof_rec rec;
@@ -290,11 +299,12 @@ extern "C" int grl_create(int device, grl_handle** out) {
     }
     h->encode = reinterpret_cast<grl_encode_tiled_fn>(fn);
     h->prof = new grl_prof();
+    h->func_attrs = new grl_func_attrs();
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // numerically: lo >= hi; `lo` is the least urgent
     e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_lo);
     if (e != cudaSuccess) {
-        delete h->prof; delete h;
+        delete h->prof; delete static_cast<grl_func_attrs*>(h->func_attrs); delete h;
         return set_error(nullptr, GRL_ECUDA, "cudaStreamCreateWithPriority: %s", cudaGetErrorString(e));
     }
     h->overlap = 3;
@@ -311,6 +321,7 @@ extern "C" void grl_destroy(grl_handle* h) {
     for (int i = 0; i < h->n_events; ++i) cudaEventDestroy(h->events[i]);
     delete[] h->events;
     if (h->side) cudaStreamDestroy(h->side);
+    delete static_cast<grl_func_attrs*>(h->func_attrs);
     delete h;
 }
 

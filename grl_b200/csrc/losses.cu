@@ -240,7 +240,7 @@ extern "C" int grl_triplet_forward(grl_handle* h, const float* feat, const int64
     if (!feat || !ids || !loss || !z || !pos_idx || !neg_idx || !pos_d || !neg_d) return set_error(h, GRL_EINVAL, "grl_triplet_forward: NULL argument");
     if (B <= 0 || D <= 0 || (size_t)(D + B) * 4 > 200 * 1024) return set_error(h, GRL_EINVAL, "grl_triplet_forward: bad sizes (B=%d, D=%d)", B, D);
     const size_t smem = (size_t)(D + B) * 4;
-    if (smem > 48 * 1024) GRL_CUDA(h, cudaFuncSetAttribute(triplet_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GRL_TRY(ensure_dyn_smem(h, (const void*)triplet_fwd_kernel, (int)smem));
     triplet_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(feat, ids, B, D, soft, margin, loss, z, pos_idx, neg_idx, pos_d, neg_d);
     GRL_LAUNCH_CHECK(h);
     return GRL_OK;

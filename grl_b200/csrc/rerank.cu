@@ -434,8 +434,7 @@ extern "C" int grl_rerank(grl_handle* h, const float* q_g, const float* q_q, con
     GRL_LAUNCH_CHECK(h);
     // ---- stage 4
     const size_t smem_q = (size_t)p.npad_q * 4;
-    if (smem_q > 48 * 1024)
-        GRL_CUDA(h, cudaFuncSetAttribute(rr_qe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+    GRL_TRY(ensure_dyn_smem(h, (const void*)rr_qe_kernel, (int)smem_q));
     rr_qe_kernel<<<N, RR_THREADS, smem_q, st>>>(top_i, p.K, N, nq, k2, p.cap, p.qcap, p.npad_q, v_idx, v_w, v_cnt, Vt, q_idx, q_w, q_cnt);
     GRL_LAUNCH_CHECK(h);
     // ---- stage 5 + 6

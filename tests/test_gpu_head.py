@@ -399,3 +399,27 @@ def test_head_rejects_bad_inputs():
         head.head_forward_raw(sd, torch.zeros((6, 2048, 8, 16), device="cuda"), 2, 3, False, save=False)   # wrong map size
     with pytest.raises(RuntimeError):
         head.head_forward_raw(sd, torch.zeros((5, 2048, 16, 8), device="cuda"), 2, 3, False, save=False)   # b*t mismatch
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process (the reference's nn.DataParallel layout)")
+def test_two_devices_in_one_process():
+    """nn.DataParallel (mars_train.py:80) drives several GPUs from ONE process: every device needs its own handle, its own
+    per-function shared-memory opt-in and its own stream; results must be identical on both."""
+    _, head, _ = _mods()
+    from grl_b200 import evaluator
+    B, T = 2, 3
+    outs = []
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        sd = {k: v.to(dev).contiguous() for k, v in synth.make_head_params(0).items()}
+        x = synth.make_head_input(B, T).to(dev)
+        gu, gc = synth.make_head_grads(B, T)
+        fu, fc, cm, _, _, ws = head.head_forward_raw(sd, x, B, T, True, save=True)
+        dx, grads = head.head_backward_raw(sd, x, B, T, ws, gu.to(dev), gc.to(dev))
+        q = torch.nn.functional.normalize(torch.randn((1100, 64), generator=torch.Generator().manual_seed(1))).to(dev)
+        g = torch.nn.functional.normalize(torch.randn((3000, 64), generator=torch.Generator().manual_seed(2))).to(dev)
+        td, ti = evaluator.retrieve_topk(q, g, 10)
+        torch.cuda.synchronize(dev)
+        outs.append((fu.cpu(), fc.cpu(), dx.cpu(), td.cpu(), ti.cpu()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
