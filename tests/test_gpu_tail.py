@@ -83,3 +83,60 @@ def test_head_to_descriptor_to_ranking_end_to_end():
     dist = evaluator.cosin_dist(q, g).cpu().numpy()
     ref = eo.cosin_dist(d64[:2].numpy().astype(np.float32), d64.numpy().astype(np.float32))
     assert np.abs(dist - ref).max() < 1e-4 * 3.0       # |descriptor|^2 = 3 (three unit-norm parts), descriptors agree to 1e-4 relative
+
+
+class _StubCnn(torch.nn.Module):
+    """Stands in for the backbone + head: the 'images' already carry the clip features ([b, T, 2048])."""
+
+    def forward(self, imgs):
+        x_corr = torch.nn.functional.normalize(imgs, dim=2)
+        return torch.nn.functional.normalize(imgs.mean(1), dim=1), x_corr
+
+
+class _StubSiamese(torch.nn.Module):
+    def self_attention(self, feats_corr):
+        return torch.nn.functional.normalize(feats_corr.sum(1), dim=1)
+
+
+@pytest.mark.parametrize("rerank", [0, 1])
+def test_attevaluator_evaluate_orchestration(rerank, capsys):
+    """ATTEvaluator.evaluate (attevaluator.py:125-163) end to end on the device -- feature extraction loop, queries joined to the
+    gallery, cosine distances, optional k-reciprocal re-ranking, CMC/mAP, the reference's prints and return value -- against
+    the oracle chain on the same features."""
+    from grl_b200 import evaluator
+    from oracle import eval_oracle as eo
+    from oracle import rerank_oracle as ro
+    rng = np.random.default_rng(3)
+    n_id, T, D = 12, 4, 2048
+    cent = rng.standard_normal((n_id, D)).astype(np.float32)
+
+    def loader(n, seed):
+        r = np.random.default_rng(seed)
+        pids = r.integers(0, n_id, n)
+        cams = r.integers(0, 4, n)
+        feats = cent[pids][:, None, :] + 0.8 * r.standard_normal((n, T, D)).astype(np.float32)
+        batches = []
+        for i in range(0, n, 5):
+            batches.append((torch.from_numpy(feats[i:i + 5]), list(pids[i:i + 5]), list(cams[i:i + 5])))
+        return batches, feats, pids, cams
+
+    ql, qfeat, qp, qc = loader(23, 1)
+    gl, gfeat, gp, gc = loader(150, 2)          # > max_rank rows after junk removal (the reference crashes on ragged rows otherwise)
+    ev = evaluator.ATTEvaluator(_StubCnn(), _StubSiamese(), only_eval=False)
+    rank1 = ev.evaluate(None, None, ql, gl, path=None, visual=0, rerank=rerank)
+    printed = capsys.readouterr().out
+    assert "Mean AP" in printed and "Rank-1" in printed and ("Applying person re-ranking" in printed) == bool(rerank)
+
+    def descr(f):
+        t = torch.from_numpy(f)
+        xc = torch.nn.functional.normalize(t, dim=2)
+        return torch.cat((torch.nn.functional.normalize(t.mean(1), dim=1), torch.nn.functional.normalize(xc.sum(1), dim=1), xc.mean(1)), 1).numpy()
+    qf, gf = descr(qfeat), np.concatenate([descr(qfeat), descr(gfeat)])
+    g_pids, g_cams = np.append(qp, gp), np.append(qc, gc)
+    d = eo.cosin_dist(qf, gf)
+    if rerank:
+        d = ro.re_ranking(d, eo.pairwise_distance(qf, qf), eo.pairwise_distance(gf, gf))
+    r1, cmc, mAP = eo.evaluate_seq(d, qp, qc, g_pids, g_cams)
+    assert abs(float(rank1) - float(r1)) < 0.05          # re-ranking is discontinuous in its 5e-6-accurate input distances
+    if not rerank:
+        assert abs(float(rank1) - float(r1)) < 1e-6
