@@ -5,13 +5,20 @@
 
 A "step" = one grl_head_forward (train-mode BN, activations saved) + one grl_head_backward over one batch of
 synthetic layer4 maps [B*T, 2048, 16, 8].  The head does not shard (train-mode BN couples the clips of a batch and
-the reference keeps BN statistics per replica): N GPUs run N independent replicas, "scaling":
-"weak", value = N*B*K / max-over-ranks device time.
+the reference keeps BN statistics per replica): N GPUs run N replicas, "scaling": "weak",
+value = N*B*K / max-over-ranks device time; at N > 1 the replicas average their parameter gradients over NCCL every step
+(grl_b200/replicas.py), the all-reduce overlapping the next forward.
 
-Keys beyond the base contract: `roofline` (dominant kernel = the split-bf16 tcgen05 GEMM, tensor bound),
-`cpu_baseline` (the oracle's transcription of the reference head on the host cores, bounded sample), `e2e`
-(same metric through the nn.Module API with pinned-host inputs and a D2H read of the outputs every step),
-`eval` (MARS-shape evaluation, BASELINE.json configs[2], queries/s through the evaluator API).
+Keys beyond the base contract:
+  roofline      dominant kernel = the split-bf16 tcgen05 GEMM (tensor bound): event-timed algorithmic TFLOP/s vs the measured
+                sustained bf16 peak; `traffic` = DRAM bytes per launch from the committed ncu capture of the same step
+  cpu_baseline  the oracle's transcription of the reference head on the host cores (bounded sample: B=4 clips per step)
+  e2e           the same metric through the nn.Module API with pinned-host inputs and a D2H read of the outputs every step;
+                e2e.graph_replay = the same loop through head.GraphedHeadStep (one CUDA-graph launch per step)
+  inference     eval-mode forward (BASELINE.json configs[3]: chunks of 8 clips x 16 frames, and B=32 x T=8)
+  eval          MARS-shape evaluation (configs[2]) through the evaluator API, host features in, CMC/mAP out (+ a CPU sample)
+  rerank        the same evaluation with k-reciprocal re-ranking (3 distance matrices + re_ranking + CMC/mAP) (+ a CPU sample)
+  retrieval     10k x 1M exact top-100 (configs[4]), gallery sharded over the ranks; its own `roofline` = the coarse search GEMM
 """
 from __future__ import annotations
 
