@@ -299,3 +299,29 @@ def test_retrieval_rejects_bad_arguments():
         ev.retrieve_topk(q, torch.zeros((10, 16), device="cuda"), 513)      # k above the supported 512
     with pytest.raises(RuntimeError):
         ev.retrieve_topk(q, torch.zeros((10, 16), device="cuda"), 3, idx_base=2 ** 32)   # global index must fit 32 bits
+
+
+def test_retrieval_full_size_properties_10k_x_1m():
+    """BASELINE configs[4] at full size (10,000 queries x 1,000,000 gallery rows x 2048-d, top-100): too large for the CPU
+    oracle, so check what the search guarantees -- lists sorted by (distance, index), indices unique and in range, and for a
+    sample of queries bit-identity with the brute-force search in the same arithmetic (grl_exact_topk)."""
+    _, ev = _mods()
+    nq, ng, dim, k = 10000, 1000000, 2048, 100
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    g = torch.randn((ng, dim), generator=gen, device="cuda")
+    g /= g.norm(dim=1, keepdim=True)
+    q = torch.nn.functional.normalize(torch.randn((nq, dim), generator=gen, device="cuda"))
+    d, i = ev.retrieve_topk(q, g, k, idx_base=7)
+    assert d.shape == (nq, k) and i.shape == (nq, k) and bool(torch.isfinite(d).all())
+    assert bool((i >= 7).all()) and bool((i < ng + 7).all())
+    assert bool((d[:, 1:] >= d[:, :-1]).all())
+    ties = d[:, 1:] == d[:, :-1]
+    assert bool((i[:, 1:][ties] > i[:, :-1][ties]).all())
+    assert int((torch.sort(i, dim=1).values[:, 1:] == torch.sort(i, dim=1).values[:, :-1]).sum()) == 0
+    rows = torch.arange(0, nq, nq // 16, device="cuda")[:16]
+    d_x, i_x = ev.CudaSearchStages.exact(q[rows].contiguous(), g, k, 7, 0)
+    assert torch.equal(i[rows], i_x) and torch.equal(d[rows], d_x)
+    # the distances are the fixed-order fp32 inner products: within 2e-6 of an fp64 evaluation
+    ref = -(q[rows].double() @ g[(i[rows] - 7).reshape(-1)].double().T).reshape(16, 16 * k)
+    pick = torch.stack([ref[r, r * k:(r + 1) * k] for r in range(16)])
+    assert float((d[rows].double() - pick).abs().max()) < 2e-6
