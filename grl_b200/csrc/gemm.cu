@@ -249,11 +249,18 @@ int coarse_gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, cons
     p.num_n_tiles = (N + CG_BN - 1) / CG_BN;
     p.group_m = p.num_m_tiles > 16 ? 8 : p.num_m_tiles;
     p.epi = epi;
-    GRL_TRY(make_tmap(h, &p.ta, A, lda, 0, 0, M, K, 1, CG_BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
-    GRL_TRY(make_tmap(h, &p.tb, B, ldb, 0, 0, N, K, 1, CG_BN, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
-    GRL_TRY(ensure_dyn_smem(h, (const void*)coarse_gemm_kernel, CG_SMEM_BYTES));
+    const bool pair_boxes = (h->overlap & 8) == 0;   // the CTA-pair kernel loads 128-row boxes per CTA
+    GRL_TRY(make_tmap(h, &p.ta, A, lda, 0, 0, M, K, 1, pair_boxes ? 128 : CG_BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
+    GRL_TRY(make_tmap(h, &p.tb, B, ldb, 0, 0, N, K, 1, pair_boxes ? 128 : CG_BN, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
+    const bool pairs = (h->overlap & 8) == 0;        // CTA-pair kernel (cta_group::2) unless grl_set_overlap bit 3 asks for the single-CTA one
+    if (pairs) GRL_TRY(ensure_dyn_smem(h, (const void*)coarse_gemm2_kernel, C2_SMEM_BYTES));
+    else GRL_TRY(ensure_dyn_smem(h, (const void*)coarse_gemm_kernel, CG_SMEM_BYTES));
     const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles;
-    const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    if (pairs) {
+        long long g2 = 2 * tiles < (long long)(h->num_sms & ~1) ? 2 * tiles : (long long)(h->num_sms & ~1);
+        grid = (int)g2;
+    }
     grl_prof_rec rec;
     if (h->prof_on) {
         GRL_CUDA(h, cudaEventCreate(&rec.e0));
@@ -261,7 +268,8 @@ int coarse_gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, cons
         rec.flops = 2.0 * M * (double)N * K;
         GRL_CUDA(h, cudaEventRecord(rec.e0, st));
     }
-    coarse_gemm_kernel<<<grid, CG_THREADS, CG_SMEM_BYTES, st>>>(p);
+    if (pairs) coarse_gemm2_kernel<<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(p);
+    else coarse_gemm_kernel<<<grid, CG_THREADS, CG_SMEM_BYTES, st>>>(p);
     GRL_LAUNCH_CHECK(h);
     if (h->prof_on) {
         GRL_CUDA(h, cudaEventRecord(rec.e1, st));
@@ -327,7 +335,7 @@ extern "C" void grl_destroy(grl_handle* h) {
 
 extern "C" int grl_set_overlap(grl_handle* h, int on) {
     if (!h) return GRL_EINVAL;
-    h->overlap = on & 3;
+    h->overlap = on & 15;
     return GRL_OK;
 }
 

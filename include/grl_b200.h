@@ -326,7 +326,8 @@ long long grl_launch_count(const grl_handle* h);
 /* The head entry points fork work that is off the recurrence's critical path (f1 / f2 convolutions, weight
  * gradients) onto an internal low-priority stream and join it back into the caller's stream before returning, so
  * HBM-bound glue overlaps tensor-core work.  `mask`: bit 0 = forward, bit 1 = backward; default 3; 0 runs everything
- * on the caller's stream (debugging, per-kernel profiling).                                                          */
+ * on the caller's stream (debugging, per-kernel profiling).  Bit 3 (value 8) is a debugging switch of the retrieval search: it
+ * replaces the CTA-pair (cta_group::2) coarse GEMM by the single-CTA 256 x 256-tile kernel.                                                          */
 int grl_set_overlap(grl_handle* h, int mask);
 
 /* Profiling aid for bench.py's roofline: while enabled, every tcgen05 GEMM launch is bracketed by CUDA
