@@ -98,6 +98,12 @@ _SIGNATURES = {
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "grl_topk_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    "grl_gallery_prepared_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "grl_gallery_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "grl_coarse_topk_prepared": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "grl_dist_topk_prepared": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "grl_topk_kprime": (C.c_int, [C.c_int]),
     "grl_coarse_topk_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "grl_coarse_topk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,

@@ -770,10 +770,43 @@ extern "C" size_t grl_coarse_topk_workspace_bytes(int nq, int ng, int dim) {
     return L.total;
 }
 
-extern "C" int grl_coarse_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int kprime,
-                               int64_t idx_base, float* coarse_d, int64_t* coarse_i, float* gmax2, int32_t* dirty, void* workspace,
-                               size_t workspace_bytes, void* stream) {
-    if (!h || !q || !g || !coarse_d || !coarse_i || !gmax2 || !dirty || !workspace) return set_error(h, GRL_EINVAL, "grl_coarse_topk: NULL argument");
+// A gallery shard converted once (fp16 rows with their per-row scales, squared norms, the largest squared norm): searches
+// against a static gallery skip the per-chunk conversion.
+struct PreparedLayout { size_t g16, inv, n2, gmax2, total; };
+static PreparedLayout prepared_layout(int ng, int dim) {
+    PreparedLayout P;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    P.g16 = take((size_t)ng * dim * 2);
+    P.inv = take((size_t)ng * 4);
+    P.n2 = take((size_t)ng * 4);
+    P.gmax2 = take(4);
+    P.total = off;
+    return P;
+}
+extern "C" size_t grl_gallery_prepared_bytes(int ng, int dim) {
+    if (ng <= 0 || dim <= 0 || (dim & 7)) return 0;
+    return prepared_layout(ng, dim).total;
+}
+extern "C" int grl_gallery_prepare(grl_handle* h, const float* g, int ng, int dim, void* prepared, size_t prepared_bytes, void* stream) {
+    if (!h || !g || !prepared) return set_error(h, GRL_EINVAL, "grl_gallery_prepare: NULL argument");
+    if (ng <= 0 || dim <= 0 || (dim & 7)) return set_error(h, GRL_EINVAL, "grl_gallery_prepare: need ng > 0 and dim %% 8 == 0 (dim=%d)", dim);
+    const PreparedLayout P = prepared_layout(ng, dim);
+    if (prepared_bytes < P.total) return set_error(h, GRL_ENOMEM, "grl_gallery_prepare: buffer %zu < %zu bytes", prepared_bytes, P.total);
+    if (reinterpret_cast<uintptr_t>(prepared) & 255) return set_error(h, GRL_EINVAL, "grl_gallery_prepare: buffer must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* b = (uint8_t*)prepared;
+    GRL_CUDA(h, cudaMemsetAsync(b + P.gmax2, 0, 4, st));
+    f16_rows_kernel<<<(int)(((long long)ng * 32 + 255) / 256), 256, 0, st>>>(g, ng, dim, (__half*)(b + P.g16), (float*)(b + P.inv), (float*)(b + P.n2),
+                                                                             (unsigned int*)(b + P.gmax2));
+    GRL_LAUNCH_CHECK(h);
+    return GRL_OK;
+}
+
+static int coarse_topk_impl(grl_handle* h, int metric, const float* q, const float* g, const void* prepared, int nq, int ng, int dim, int kprime,
+                            int64_t idx_base, float* coarse_d, int64_t* coarse_i, float* gmax2, int32_t* dirty, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    if (!h || !q || (!g && !prepared) || !coarse_d || !coarse_i || !gmax2 || !dirty || !workspace) return set_error(h, GRL_EINVAL, "grl_coarse_topk: NULL argument");
     if (nq <= 0 || ng <= 0 || dim <= 0 || (dim & 7)) return set_error(h, GRL_EINVAL, "grl_coarse_topk: need nq,ng > 0 and dim %% 8 == 0 (dim=%d)", dim);
     if (kprime <= 0 || kprime > TOPK_MAXK) return set_error(h, GRL_EINVAL, "grl_coarse_topk: need 0 < kprime <= %d", TOPK_MAXK);
     if (metric != GRL_METRIC_NEG_DOT && metric != GRL_METRIC_L2) return set_error(h, GRL_EINVAL, "grl_coarse_topk: unknown metric %d", metric);
@@ -793,7 +826,10 @@ extern "C" int grl_coarse_topk(grl_handle* h, int metric, const float* q, const 
     float* thresh = (float*)(w + L.thresh);
     int* cand_cnt = (int*)(w + L.cnt);
     unsigned long long* cand = (unsigned long long*)(w + L.cand);
-    GRL_CUDA(h, cudaMemsetAsync(gmax2, 0, 4, st));
+    const PreparedLayout P = prepared_layout(ng, dim);
+    const uint8_t* pb = (const uint8_t*)prepared;
+    if (prepared) GRL_CUDA(h, cudaMemcpyAsync(gmax2, pb + P.gmax2, 4, cudaMemcpyDeviceToDevice, st));
+    else GRL_CUDA(h, cudaMemsetAsync(gmax2, 0, 4, st));
     GRL_CUDA(h, cudaMemsetAsync(dirty, 0, (size_t)nq * 4, st));
     GRL_TRY(ensure_dyn_smem(h, (const void*)topk_update_small_kernel, 8 * kprime * 8));
     topk_filter_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(thresh, cand_cnt, nq, TOPK_CAND_CAP);
@@ -805,17 +841,26 @@ extern "C" int grl_coarse_topk(grl_handle* h, int metric, const float* q, const 
     for (int c0 = 0; c0 < ng;) {
         const int nc = topk_next_chunk(c0, ng, L.chunk);
         const bool first = c0 == 0;
-        const float* gc = g + (size_t)c0 * dim;
-        f16_rows_kernel<<<(int)(((long long)nc * 32 + 255) / 256), 256, 0, st>>>(gc, nc, dim, g16, g_inv, g_n2, (unsigned int*)gmax2);
-        GRL_LAUNCH_CHECK(h);
+        const __half* g16c = g16;
+        const float* g_invc = g_inv;
+        const float* g_n2c = g_n2;
+        if (prepared) {                               // chunk starts are multiples of 256 columns: the slices stay 16-byte aligned
+            g16c = (const __half*)(pb + P.g16) + (size_t)c0 * dim;
+            g_invc = (const float*)(pb + P.inv) + c0;
+            g_n2c = (const float*)(pb + P.n2) + c0;
+        } else {
+            f16_rows_kernel<<<(int)(((long long)nc * 32 + 255) / 256), 256, 0, st>>>(g + (size_t)c0 * dim, nc, dim, g16, g_inv, g_n2,
+                                                                                     (unsigned int*)gmax2);
+            GRL_LAUNCH_CHECK(h);
+        }
         GemmEpi e = epi_default();
         if (first) { e.C = tile; e.ldc = L.first; }   // later chunks never store their tile
-        e.row_scale = q_inv; e.col_scale = g_inv;
-        if (metric == GRL_METRIC_L2) { e.mode = 2; e.row_norm = q_n2; e.col_norm = g_n2; }
+        e.row_scale = q_inv; e.col_scale = g_invc;
+        if (metric == GRL_METRIC_L2) { e.mode = 2; e.row_norm = q_n2; e.col_norm = g_n2c; }
         else e.alpha = -1.f;
         // the epilogue keeps only distances that can still enter a row's list (v <= current K'-th best) as candidates
         e.tk_cand = cand; e.tk_cnt = cand_cnt; e.tk_thresh = thresh; e.tk_cap = TOPK_CAND_CAP; e.tk_idx_base = idx_base + c0;
-        GRL_TRY(coarse_gemm_launch(h, st, nq, nc, dim, q16, dim, g16, dim, e));
+        GRL_TRY(coarse_gemm_launch(h, st, nq, nc, dim, q16, dim, g16c, dim, e));
         topk_update_small_kernel<<<(nq + 7) / 8, 256, (size_t)8 * kprime * 8, st>>>(nq, kprime, coarse_d, coarse_i, thresh, cand, cand_cnt,
                                                                                      TOPK_CAND_CAP);
         GRL_LAUNCH_CHECK(h);
@@ -825,6 +870,21 @@ extern "C" int grl_coarse_topk(grl_handle* h, int metric, const float* q, const 
         c0 += nc;
     }
     return GRL_OK;
+}
+
+extern "C" int grl_coarse_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int kprime,
+                               int64_t idx_base, float* coarse_d, int64_t* coarse_i, float* gmax2, int32_t* dirty, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    if (!g) return set_error(h, GRL_EINVAL, "grl_coarse_topk: NULL argument");
+    return coarse_topk_impl(h, metric, q, g, nullptr, nq, ng, dim, kprime, idx_base, coarse_d, coarse_i, gmax2, dirty, workspace, workspace_bytes,
+                            stream);
+}
+extern "C" int grl_coarse_topk_prepared(grl_handle* h, int metric, const float* q, const void* prepared, int nq, int ng, int dim, int kprime,
+                                        int64_t idx_base, float* coarse_d, int64_t* coarse_i, float* gmax2, int32_t* dirty,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (!prepared) return set_error(h, GRL_EINVAL, "grl_coarse_topk_prepared: NULL argument");
+    return coarse_topk_impl(h, metric, q, nullptr, prepared, nq, ng, dim, kprime, idx_base, coarse_d, coarse_i, gmax2, dirty, workspace,
+                            workspace_bytes, stream);
 }
 
 extern "C" int grl_rescore(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int64_t idx_base,
@@ -923,8 +983,8 @@ extern "C" size_t grl_dist_topk_workspace_bytes(int nq, int ng, int dim) {
     return L.total;
 }
 
-extern "C" int grl_dist_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k,
-                             int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream) {
+static int dist_topk_impl(grl_handle* h, int metric, const float* q, const float* g, const void* prepared, int nq, int ng, int dim, int k,
+                          int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h || !q || !g || !top_d || !top_i || !workspace) return set_error(h, GRL_EINVAL, "grl_dist_topk: NULL argument");
     if (nq <= 0 || ng <= 0 || dim <= 0 || (dim & 7) || dim > 32768) return set_error(h, GRL_EINVAL, "grl_dist_topk: need nq,ng > 0, dim %% 8 == 0, dim <= 32768 (dim=%d)", dim);
     if (k <= 0 || k > TOPK_MAXK / 2) return set_error(h, GRL_EINVAL, "grl_dist_topk: need 0 < k <= %d", TOPK_MAXK / 2);
@@ -945,7 +1005,7 @@ extern "C" int grl_dist_topk(grl_handle* h, int metric, const float* q, const fl
     int32_t* rows = (int32_t*)(w + L.rows);
     int32_t* dirty = (int32_t*)(w + L.dirty);
     GRL_CUDA(h, cudaMemsetAsync(w + L.misc, 0, 64, st));
-    GRL_TRY(grl_coarse_topk(h, metric, q, g, nq, ng, dim, L.kp, idx_base, cd, ci, gmax2, dirty, w + L.coarse, L.total - L.coarse, stream));
+    GRL_TRY(coarse_topk_impl(h, metric, q, g, prepared, nq, ng, dim, L.kp, idx_base, cd, ci, gmax2, dirty, w + L.coarse, L.total - L.coarse, stream));
     GRL_TRY(grl_rescore(h, metric, q, g, nq, ng, dim, idx_base, ci, L.kp, ed, stream));
     GRL_TRY(grl_topk_finalize(h, metric, q, nq, dim, cd, ci, ed, L.kp, gmax2, dirty, k, top_d, top_i, flags, nflag, stream));
     // rows whose candidate list could not be proven complete: brute force (needs their count on the host: one 4-byte read)
@@ -959,6 +1019,17 @@ extern "C" int grl_dist_topk(grl_handle* h, int metric, const float* q, const fl
                                 (int64_t*)(w + L.tmp_i), (float*)(w + L.brute), st));
     }
     return GRL_OK;
+}
+
+extern "C" int grl_dist_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k,
+                             int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream) {
+    return dist_topk_impl(h, metric, q, g, nullptr, nq, ng, dim, k, idx_base, top_d, top_i, workspace, workspace_bytes, stream);
+}
+extern "C" int grl_dist_topk_prepared(grl_handle* h, int metric, const float* q, const float* g, const void* prepared, int nq, int ng, int dim,
+                                      int k, int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+    if (!prepared) return set_error(h, GRL_EINVAL, "grl_dist_topk_prepared: NULL argument");
+    return dist_topk_impl(h, metric, q, g, prepared, nq, ng, dim, k, idx_base, top_d, top_i, workspace, workspace_bytes, stream);
 }
 
 extern "C" int grl_cmc_map(grl_handle* h, const float* dist, long long ld_dist, const int64_t* q_pid, const int64_t* g_pid,

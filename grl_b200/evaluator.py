@@ -160,10 +160,46 @@ def _padded_features(qf, gf):
     return qf, gf
 
 
+class PreparedGallery(object):
+    """A static gallery shard converted once for the coarse pass (grl_gallery_prepare: fp16 rows with per-row scales, squared
+    norms): pass it to retrieve_topk / sharded_retrieve in place of the feature tensor and every search skips the conversion.
+    Keeps the fp32 rows (`.gf`, feature axis zero-padded to a multiple of 8) for the exact re-score."""
+
+    def __init__(self, gf):
+        gf = _as_cuda_f32(gf)
+        if gf.size(1) % 8:
+            gf = torch.nn.functional.pad(gf, (0, 8 - gf.size(1) % 8))
+        self.gf = gf.contiguous()
+        ng, dim = self.gf.shape
+        lib = _lib.load_library()
+        with torch.cuda.device(gf.device):
+            h = _lib.get_handle(gf.device)
+            nbytes = lib.grl_gallery_prepared_bytes(ng, dim)
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=gf.device)
+            _lib.check(h, lib.grl_gallery_prepare(h, self.gf.data_ptr(), ng, dim, self.buf.data_ptr(), nbytes, _lib.stream_ptr(gf.device)),
+                       "grl_gallery_prepare")
+
+    def size(self, i):
+        return self.gf.size(i)
+
+
+def _pad_queries(qf, dim):
+    qf = _as_cuda_f32(qf)
+    if qf.size(1) > dim or dim - qf.size(1) >= 8:
+        raise RuntimeError("size mismatch, qf %s vs prepared gallery [*, %d]" % (tuple(qf.shape), dim))
+    return torch.nn.functional.pad(qf, (0, dim - qf.size(1))) if qf.size(1) < dim else qf
+
+
 def retrieve_topk(qf, gf, k, idx_base=0, metric=0):
     """k nearest rows of this gallery shard per query (grl_dist_topk: coarse fp16 tensor-core pass + exact fp32 re-score).
-    Returns CUDA (dist f32 [nq,k], index i64 [nq,k]), the stable top-k of the fixed-order fp32 distances."""
-    qf, gf = _padded_features(qf, gf)
+    `gf`: features [ng, dim] or a PreparedGallery.  Returns CUDA (dist f32 [nq,k], index i64 [nq,k]), the stable top-k of the
+    fixed-order fp32 distances."""
+    prepared = gf if isinstance(gf, PreparedGallery) else None
+    if prepared is not None:
+        gf = prepared.gf
+        qf = _pad_queries(qf, gf.size(1))
+    else:
+        qf, gf = _padded_features(qf, gf)
     nq, ng, dim = qf.size(0), gf.size(0), qf.size(1)
     lib = _lib.load_library()
     with torch.cuda.device(qf.device):
@@ -172,8 +208,13 @@ def retrieve_topk(qf, gf, k, idx_base=0, metric=0):
         top_i = torch.empty((nq, k), dtype=torch.int64, device=qf.device)
         ws_bytes = lib.grl_dist_topk_workspace_bytes(nq, ng, dim)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qf.device)
-        _lib.check(h, lib.grl_dist_topk(h, metric, qf.data_ptr(), gf.data_ptr(), nq, ng, dim, k, idx_base, top_d.data_ptr(),
-                                        top_i.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(qf.device)), "grl_dist_topk")
+        if prepared is None:
+            _lib.check(h, lib.grl_dist_topk(h, metric, qf.data_ptr(), gf.data_ptr(), nq, ng, dim, k, idx_base, top_d.data_ptr(),
+                                            top_i.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(qf.device)), "grl_dist_topk")
+        else:
+            _lib.check(h, lib.grl_dist_topk_prepared(h, metric, qf.data_ptr(), gf.data_ptr(), prepared.buf.data_ptr(), nq, ng, dim, k, idx_base,
+                                                     top_d.data_ptr(), top_i.data_ptr(), ws.data_ptr(), ws_bytes,
+                                                     _lib.stream_ptr(qf.device)), "grl_dist_topk_prepared")
     return top_d, top_i
 
 
@@ -202,7 +243,7 @@ class CudaSearchStages(object):
         return int(_lib.load_library().grl_topk_kprime(k))
 
     @staticmethod
-    def coarse(qf, gf, kp, idx_base, metric):
+    def coarse(qf, gf, kp, idx_base, metric, prepared=None):
         nq, ng, dim = qf.size(0), gf.size(0), qf.size(1)
         lib = _lib.load_library()
         with torch.cuda.device(qf.device):
@@ -213,9 +254,14 @@ class CudaSearchStages(object):
             dirty = torch.zeros(nq, dtype=torch.int32, device=qf.device)
             ws_bytes = lib.grl_coarse_topk_workspace_bytes(nq, ng, dim)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qf.device)
-            _lib.check(h, lib.grl_coarse_topk(h, metric, qf.data_ptr(), gf.data_ptr(), nq, ng, dim, kp, idx_base, cd.data_ptr(),
-                                              ci.data_ptr(), gmax2.data_ptr(), dirty.data_ptr(), ws.data_ptr(), ws_bytes,
-                                              _lib.stream_ptr(qf.device)), "grl_coarse_topk")
+            if prepared is None:
+                _lib.check(h, lib.grl_coarse_topk(h, metric, qf.data_ptr(), gf.data_ptr(), nq, ng, dim, kp, idx_base, cd.data_ptr(),
+                                                  ci.data_ptr(), gmax2.data_ptr(), dirty.data_ptr(), ws.data_ptr(), ws_bytes,
+                                                  _lib.stream_ptr(qf.device)), "grl_coarse_topk")
+            else:
+                _lib.check(h, lib.grl_coarse_topk_prepared(h, metric, qf.data_ptr(), prepared.buf.data_ptr(), nq, ng, dim, kp, idx_base,
+                                                           cd.data_ptr(), ci.data_ptr(), gmax2.data_ptr(), dirty.data_ptr(), ws.data_ptr(),
+                                                           ws_bytes, _lib.stream_ptr(qf.device)), "grl_coarse_topk_prepared")
         return cd, ci, gmax2, dirty
 
     merge = staticmethod(merge_topk)
@@ -271,13 +317,21 @@ def sharded_retrieve(qf, gf_local, k, idx_base, group=None, metric=0, stages=Non
     The result is identical on every rank and for every shard count."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    prepared = gf_local if isinstance(gf_local, PreparedGallery) else None
     if stages is None:
         if world == 1:
             return retrieve_topk(qf, gf_local, k, idx_base=idx_base, metric=metric)
         stages = CudaSearchStages
-        qf, gf_local = _padded_features(qf, gf_local)
+        if prepared is not None:
+            gf_local = prepared.gf
+            qf = _pad_queries(qf, gf_local.size(1))
+        else:
+            qf, gf_local = _padded_features(qf, gf_local)
     kp = stages.kprime(k)
-    cd, ci, gmax2, dirty = stages.coarse(qf, gf_local, kp, idx_base, metric)
+    if prepared is not None:
+        cd, ci, gmax2, dirty = stages.coarse(qf, gf_local, kp, idx_base, metric, prepared=prepared)
+    else:
+        cd, ci, gmax2, dirty = stages.coarse(qf, gf_local, kp, idx_base, metric)
     if world > 1:
         all_d = [torch.empty_like(cd) for _ in range(world)]
         all_i = [torch.empty_like(ci) for _ in range(world)]

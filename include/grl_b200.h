@@ -126,6 +126,18 @@ int grl_topk_merge(grl_handle* h, const float* all_d, const int64_t* all_i, int 
  * shards with a max); dirty int32 [nq] = 1 where a per-chunk candidate buffer overflowed (only the first chunk's distance
  * tile is ever stored, so such a row cannot be rescanned: it is flagged and brute-forced; combine shards with a max; may be
  * NULL for grl_topk_finalize); flags int32 [nq], nflag int32 [1].                                                                */
+/* A static gallery shard can be converted ONCE (fp16 rows with their per-row scales, squared norms, largest squared norm) and
+ * searched many times: grl_gallery_prepare fills a caller-owned buffer of grl_gallery_prepared_bytes(ng, dim) bytes (256-byte
+ * aligned); the *_prepared entry points take it in place of the per-search conversion.  The fp32 rows are still needed for
+ * the re-score (grl_rescore / grl_dist_topk_prepared / grl_exact_topk).                                                    */
+size_t grl_gallery_prepared_bytes(int ng, int dim);
+int grl_gallery_prepare(grl_handle* h, const float* g, int ng, int dim, void* prepared, size_t prepared_bytes, void* stream);
+int grl_coarse_topk_prepared(grl_handle* h, int metric, const float* q, const void* prepared, int nq, int ng, int dim, int kprime,
+                             int64_t idx_base, float* coarse_d, int64_t* coarse_i, float* gmax2, int32_t* dirty, void* workspace,
+                             size_t workspace_bytes, void* stream);
+int grl_dist_topk_prepared(grl_handle* h, int metric, const float* q, const float* g, const void* prepared, int nq, int ng, int dim,
+                           int k, int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes,
+                           void* stream);
 int grl_topk_kprime(int k);
 size_t grl_coarse_topk_workspace_bytes(int nq, int ng, int dim);
 int grl_coarse_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int kprime,

@@ -325,3 +325,24 @@ def test_retrieval_full_size_properties_10k_x_1m():
     ref = -(q[rows].double() @ g[(i[rows] - 7).reshape(-1)].double().T).reshape(16, 16 * k)
     pick = torch.stack([ref[r, r * k:(r + 1) * k] for r in range(16)])
     assert float((d[rows].double() - pick).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_prepared_gallery_gives_identical_results(metric):
+    """A gallery converted once (grl_gallery_prepare) must give bit-identical searches to the per-search conversion, for both
+    coarse kernels' shapes (nq >= 1024 and small nq), an unpadded feature size, and across simulated shards."""
+    _, ev = _mods()
+    for nq, ng, dim, k in ((1100, 5000, 64, 20), (37, 3001, 100, 50)):
+        q, g = _retrieval_inputs(nq, ng, dim, 40 + nq, dup_every=11)
+        qd, gd = torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda()
+        d0, i0 = ev.retrieve_topk(qd, gd, k, metric=metric)
+        pg = ev.PreparedGallery(gd)
+        for _ in range(2):                                  # reusable
+            d1, i1 = ev.retrieve_topk(qd, pg, k, metric=metric)
+            assert torch.equal(i0, i1) and torch.equal(d0, d1)
+        parts = []
+        for r in range(3):
+            lo, n = ev.shard_bounds(ng, 3, r)
+            parts.append(ev.retrieve_topk(qd, ev.PreparedGallery(gd[lo:lo + n]), k, idx_base=lo, metric=metric))
+        dm, im = ev.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+        assert torch.equal(im, i0) and torch.equal(dm, d0)
