@@ -8,9 +8,11 @@ Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this fil
 
 Pinning: `triplet_loss` is checked against the REAL reference class (values and autograd gradients, tests/golden/loss_*.npz,
 oracle/make_golden.py).  The reference's `OIM` is a legacy autograd.Function with a non-static forward, which PyTorch >= 1.5
-refuses to execute, so its backward contract (input gradient from the table BEFORE the update, then the sequential momentum
-update) is restated here line by line and is NOT pinned by an execution of the reference: "parity unpinned" for OIM.backward;
-its forward (`inputs.mm(lut.t())`, scaling, F.cross_entropy) is plain torch and is what the golden file holds.
+refuses to *apply*; its `backward` (input gradient from the table BEFORE the update, then the sequential momentum update,
+oim.py:18-27) is nevertheless a plain method, so oracle/make_golden.py executes the REAL `OIM.backward` unbound on a stub that
+carries the attributes it reads (saved_tensors, needs_input_grad, lut, momentum) and the golden files hold its `grad_inputs`
+and the table rows it rewrote: `oim_loss` below is pinned to them (tests/test_oracle_loss.py).  The forward
+(`inputs.mm(lut.t())`, scaling, F.cross_entropy) is plain torch and is pinned the same way.
 """
 from __future__ import annotations
 

@@ -108,6 +108,46 @@ def head_fixture(Model, name, B, T, training, dtype=torch.float64, with_grads=Tr
     print("wrote", name, {k: getattr(v, "shape", v) for k, v in out.items() if k in ("f_uncorr", "f_corr")})
 
 
+def head_fixture_full_size(Model, name="head_train_b32t8", B=32, T=8):
+    """The benchmark configuration itself (BASELINE configs[1], B=32, T=8, train-mode BN) through the REAL reference in
+    float64 (truth) and in float32 (the reference's own rounding floor per tensor: rel |fp32 - fp64|).  Outputs are stored
+    as float32 (gate 1e-4), gradients as norms + strided samples + the fp32 floor.  Takes a few minutes and ~25 GB of RAM."""
+    from grl_b200 import synth
+    params = synth.make_head_params(0, dtype=torch.float32)
+    gu, gc = synth.make_head_grads(B, T)
+    res = {}
+    for dtype in (torch.float64, torch.float32):
+        model = build_reference_model(Model, params, dtype).train()
+        x = synth.make_head_input(B, T).to(dtype).requires_grad_(True)
+        x_uncorr, x_corr, corr_map = model.backbone(x, B, T)
+        f_uncorr, f_corr = model.temporal_learning_block(x_uncorr.view(B, T, 2048, 16, 8), x_corr.view(B, T, 2048, 16, 8))
+        ((f_uncorr * gu.to(dtype)).sum() + (f_corr * gc.to(dtype)).sum()).backward()
+        r = dict(f_uncorr=f_uncorr.detach().double(), f_corr=f_corr.detach().double(), corr_map=corr_map.detach().double(),
+                 dx=x.grad.double())
+        r["grads"] = {k: v.grad.double().clone() for k, v in model.named_parameters() if k in params and v.grad is not None}
+        r["bufs"] = {k: v.double().clone() for k, v in model.state_dict().items()
+                     if k in params and ("running" in k or "num_batches" in k)}
+        res[dtype] = r
+        del model, x, x_uncorr, x_corr, f_uncorr, f_corr
+    t, f = res[torch.float64], res[torch.float32]
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-300))
+    names = list(t["grads"].keys())
+    out = dict(B=B, T=T, f_uncorr=t["f_uncorr"].float().numpy(), f_corr=t["f_corr"].float().numpy(),
+               corr_map=t["corr_map"].float().numpy(),
+               floor_f_uncorr=rel(f["f_uncorr"], t["f_uncorr"]), floor_f_corr=rel(f["f_corr"], t["f_corr"]),
+               floor_corr_map=rel(f["corr_map"], t["corr_map"]),
+               dx_sample=grad_sample(t["dx"], 4096), dx_norm=float(t["dx"].norm()), floor_dx=rel(f["dx"], t["dx"]),
+               grad_names=np.array(names), grad_norms=np.array([float(t["grads"][k].norm()) for k in names]),
+               grad_samples=np.stack([np.pad(grad_sample(t["grads"][k], 64), (0, 64 - min(64, grad_sample(t["grads"][k], 64).size)))
+                                      for k in names]),
+               grad_floor=np.array([rel(f["grads"][k], t["grads"][k]) for k in names]),
+               buf_names=np.array(list(t["bufs"].keys())),
+               buf_values=np.concatenate([v.reshape(-1).numpy() for v in t["bufs"].values()]))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name, "floors: f_uncorr %.1e f_corr %.1e dx %.1e max grad %.1e" %
+          (out["floor_f_uncorr"], out["floor_f_corr"], out["floor_dx"], out["grad_floor"].max()))
+
+
 def eval_fixture(att, eva, name, nq, ng_extra, dim, seed, noise, max_rank=100, quantize=None):
     from grl_b200 import synth
     qf, gf, qp, gp, qc, gc = synth.make_eval_set(nq, ng_extra, dim, seed=seed, num_ids=25, noise=noise,
@@ -200,6 +240,22 @@ def loss_fixture(name, B, D, C, seed, n_ids):
     loss = torch.nn.functional.cross_entropy(logits, targets)
     loss.backward()
     out.update(oim_loss=float(loss), oim_logits=logits.detach().numpy(), oim_dx=x.grad.numpy())
+    # OIM.backward (oim.py:18-27) by the REAL reference code: the class is a legacy (non-static) autograd.Function that modern
+    # PyTorch refuses to *apply*, but its `backward` is a plain method -- call it unbound on a stub carrying exactly the
+    # attributes it reads (saved_tensors, needs_input_grad, lut, momentum).  grad_outputs = d loss / d (inputs.mm(lut.t())),
+    # i.e. the cross-entropy gradient through OIMLoss.forward's `inputs *= self.scalar` (:54).
+    from types import SimpleNamespace
+    from reid.loss.oim import OIM
+    raw = feat.double().mm(lut.double().t()).requires_grad_(True)
+    torch.nn.functional.cross_entropy(raw * 30.0, targets).backward()
+    stub = SimpleNamespace(saved_tensors=(feat.double(), targets), needs_input_grad=(True, False), lut=lut.double().clone(),
+                           momentum=0.5)
+    grad_inputs, none = OIM.backward(stub, raw.grad)
+    assert none is None
+    touched = np.unique(targets.numpy())                 # only these rows may change; the fixture stores them alone
+    rest = np.setdiff1d(np.arange(C), touched)
+    assert np.array_equal(stub.lut.numpy()[rest], lut.double().numpy()[rest])
+    out.update(oim_bwd_dx=grad_inputs.numpy(), oim_new_lut_rows=touched, oim_new_lut_vals=stub.lut.numpy()[touched])
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
     print("wrote", name, "triplet soft mean %.4f oim loss %.4f" % (out["tri_soft_loss"].mean(), float(loss)))
 
@@ -252,6 +308,13 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     Model, att, eva = import_reference()
+    if "--loss" in sys.argv:               # only the loss fixtures
+        loss_fixture("loss_b32", 32, 2048, 625, seed=21, n_ids=8)
+        loss_fixture("loss_b12", 12, 256, 40, seed=22, n_ids=5)
+        return
+    if "--full-size" in sys.argv:          # only the benchmark-size head fixture (minutes, ~25 GB of RAM)
+        head_fixture_full_size(Model)
+        return
     head_fixture(Model, "head_train_b2t3", 2, 3, True)
     head_fixture(Model, "head_train_b4t2", 4, 2, True)
     head_fixture(Model, "head_eval_b3t4", 3, 4, False, with_grads=False)

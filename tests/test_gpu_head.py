@@ -224,6 +224,62 @@ def test_full_size_properties_b32_t8():
     assert rel(part, full[8:16]) < 1e-5
 
 
+def test_full_size_b32_t8_vs_real_reference(golden_dir):
+    """The benchmark configuration itself (BASELINE configs[1]: B=32, T=8, train-mode BN) against ONE fp64 run of the REAL
+    reference (tests/golden/head_train_b32t8.npz, oracle/make_golden.py --full-size): forward outputs at 1e-4, BN running
+    buffers at 2e-5, and every gradient at SURVEY.md section 7.2's rule  err <= max(1e-3, 2 * err(reference fp32, fp64))
+    -- the reference's own fp32 rounding floor at this size travels in the fixture (dx: 1.2e-3, memory-block weights 1-3e-4).
+    Gradients are stored as strided samples + norms; both are gated.  The per-tensor table is printed (and written to
+    gpurun_out/ when that directory exists) so it can be committed under profiles/."""
+    from helpers_sample import grad_sample
+    _, head, ho = _mods()
+    g = np.load(os.path.join(golden_dir, "head_train_b32t8.npz"))
+    B, T = int(g["B"]), int(g["T"])
+    assert (B, T) == (32, 8)
+    sd = device_params()
+    x = synth.make_head_input(B, T).cuda()
+    gu, gc = synth.make_head_grads(B, T)
+    fu, fc, cm, _, _, ws = head.head_forward_raw(sd, x, B, T, True, save=True)
+    for k, v in (("f_uncorr", fu), ("f_corr", fc), ("corr_map", cm)):
+        assert rel(v, g[k]) < 1e-4, (k, rel(v, g[k]))
+    off = 0
+    for k in g["buf_names"]:
+        k = str(k)
+        n = max(1, int(sd[k].numel()))
+        ref = g["buf_values"][off:off + n]
+        off += n
+        if "num_batches" not in k:
+            assert rel(sd[k], ref) < 2e-5, (k, rel(sd[k], ref))
+    dx, grads = head.head_backward_raw(sd, x, B, T, ws, gu.cuda(), gc.cuda())
+    lines, bad = [], {}
+
+    def gate(name, ours, ref_sample, ref_norm, floor):
+        n = ref_sample.size
+        e_s = rel(grad_sample(ours, n), ref_sample)
+        e_n = abs(float(ours.double().norm()) / ref_norm - 1.0)
+        tol = max(1e-3, 2.0 * floor)
+        lines.append("%-72s sample %.2e  norm %.2e | reference fp32 floor %.2e | gate %.2e" % (name, e_s, e_n, floor, tol))
+        # a strided sample of a tensor whose error sits in a few flipped ReLU masks scatters around the tensor-wide figure:
+        # the sample is gated at 2x, the norm (a whole-tensor statistic) at 1x
+        if e_s > 2.0 * tol or e_n > tol:
+            bad[name] = (e_s, e_n, tol)
+
+    gate("dx", dx, g["dx_sample"], float(g["dx_norm"]), float(g["floor_dx"]))
+    for k, nrm, smp, fl in zip(g["grad_names"], g["grad_norms"], g["grad_samples"], g["grad_floor"]):
+        k = str(k)
+        if k in ZERO_GRADS:
+            assert float(grads[k].double().norm()) < 1e-3 * float(grads[ZERO_GRADS[k]].double().norm()), k
+            continue
+        gate(k, grads[k], smp[:min(64, grads[k].numel())], float(nrm), float(fl))
+    table = "full-size (B=32, T=8) gradient error, ours vs the REAL reference in fp64:\n  " + "\n  ".join(lines)
+    print(table)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "full_size_gradient_table.txt"), "w") as f:
+            f.write(table + "\n")
+    assert not bad, bad
+
+
 def test_config1_b2_t8_forward_vs_oracle():
     """BASELINE configs[0]: head forward, B=2, T=8, train-mode BN (the reference's CPU-runnable case)."""
     _, head, ho = _mods()

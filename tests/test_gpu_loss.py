@@ -53,6 +53,12 @@ def test_oim_matches_golden_and_oracle(golden_dir, name):
     assert rel(x.grad.cpu().numpy(), 0.7 * g["oim_dx"]) < 1e-5
     _, _, _, new_lut = lo.oim_loss(feat.double(), targets, lut.double(), 30.0, 0.5)
     assert rel(crit.lut.cpu().numpy(), new_lut.numpy()) < 1e-6
+    # ... and against the REAL reference's OIM.backward (executed unbound on a stub, oracle/make_golden.py)
+    assert rel(x.grad.cpu().numpy(), 0.7 * g["oim_bwd_dx"]) < 1e-5
+    rows = g["oim_new_lut_rows"]
+    assert rel(crit.lut.cpu().numpy()[rows], g["oim_new_lut_vals"]) < 1e-6
+    rest = np.setdiff1d(np.arange(C), rows)
+    assert np.array_equal(crit.lut.cpu().numpy()[rest], lut.numpy()[rest])
     assert not torch.equal(before, crit.lut)              # the update happened in backward, not in forward
     # a second step composes on the updated table, like the reference's persistent buffer
     x2 = feat.cuda().requires_grad_(True)

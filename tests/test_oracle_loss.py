@@ -27,3 +27,8 @@ def test_loss_oracle_matches_reference_golden(golden_dir, name):
     rest = np.setdiff1d(np.arange(C), touched)
     assert np.array_equal(new_lut.numpy()[rest], lut.double().numpy()[rest])
     assert np.allclose(np.linalg.norm(new_lut.numpy()[touched], axis=1), 1.0, atol=1e-12)
+    # OIM.backward as executed by the REAL reference method (unbound call on a stub, oracle/make_golden.py): the input
+    # gradient and every table row it rewrote
+    assert np.allclose(dx.numpy(), g["oim_bwd_dx"], rtol=0, atol=1e-12)
+    assert np.array_equal(g["oim_new_lut_rows"], touched)
+    assert np.allclose(new_lut.numpy()[touched], g["oim_new_lut_vals"], rtol=0, atol=1e-12)
