@@ -14,8 +14,10 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgrl_b200.so")
 
-GRL_OK, GRL_EINVAL, GRL_ECUDA, GRL_EARCH, GRL_ENOMEM = 0, -1, -2, -3, -4
-_CODES = {GRL_EINVAL: "GRL_EINVAL", GRL_ECUDA: "GRL_ECUDA", GRL_EARCH: "GRL_EARCH", GRL_ENOMEM: "GRL_ENOMEM"}
+GRL_OK, GRL_EINVAL, GRL_ECUDA, GRL_EARCH, GRL_ENOMEM, GRL_ENCCL = 0, -1, -2, -3, -4, -5
+_CODES = {GRL_EINVAL: "GRL_EINVAL", GRL_ECUDA: "GRL_ECUDA", GRL_EARCH: "GRL_EARCH", GRL_ENOMEM: "GRL_ENOMEM", GRL_ENCCL: "GRL_ENCCL"}
+GRL_COMM_ID_BYTES = 128
+GRL_SEARCH_STAGES = 9
 
 c_float_p = C.c_void_p   # device pointers travel as integers
 
@@ -92,6 +94,10 @@ _SIGNATURES = {
                                C.c_void_p, C.c_size_t, C.c_void_p]),
     "grl_cmc_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "grl_cmc_map_sharded_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "grl_cmc_map_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.c_void_p]),
     "grl_argsort_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "grl_topk_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "grl_topk_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int64,
@@ -118,6 +124,16 @@ _SIGNATURES = {
     "grl_dist_topk_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "grl_dist_topk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "grl_comm_unique_id": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "grl_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
+    "grl_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "grl_comm_destroy": (C.c_int, [C.c_void_p]),
+    "grl_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "grl_sharded_topk_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "grl_sharded_topk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "grl_search_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "grl_search_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     "grl_rerank_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "grl_rerank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -30,6 +30,13 @@ struct grl_handle {
     cudaEvent_t* events;        // pool of timing-disabled events for fork/join between the caller's stream and `side`
     int n_events, overlap;
     void* func_attrs;           // per-device record of cudaFuncAttributeMaxDynamicSharedMemorySize settings (gemm.cu)
+    // communicator of the gallery-sharded search (comm.cu): an ncclComm_t created by grl_comm_init (owned) or handed in by
+    // grl_comm_attach (borrowed); NULL == single rank
+    void* comm;
+    int comm_world, comm_rank, comm_owned;
+    // per-stage events of the last grl_sharded_topk call (search.cu), recorded when stage_prof is on
+    int stage_prof, n_stage_ev;
+    cudaEvent_t* stage_ev;
     char err[512];
 };
 
@@ -99,6 +106,9 @@ int stream_wait(grl_handle* h, cudaStream_t signaler, cudaStream_t waiter, int k
 // record pool event k on `s` / make `s` wait for pool event k
 int ev_record(grl_handle* h, int k, cudaStream_t s);
 int ev_wait(grl_handle* h, int k, cudaStream_t s);
+
+// Drops the handle's communicator (destroys it when the library created it).
+void comm_release(grl_handle* h);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline GemmEpi epi_default() {

@@ -329,6 +329,9 @@ extern "C" void grl_destroy(grl_handle* h) {
     for (int i = 0; i < h->n_events; ++i) cudaEventDestroy(h->events[i]);
     delete[] h->events;
     if (h->side) cudaStreamDestroy(h->side);
+    grl::comm_release(h);
+    for (int i = 0; i < h->n_stage_ev; ++i) cudaEventDestroy(h->stage_ev[i]);
+    delete[] h->stage_ev;
     delete static_cast<grl_func_attrs*>(h->func_attrs);
     delete h;
 }

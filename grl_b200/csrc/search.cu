@@ -1,0 +1,1087 @@
+// grl_b200 — gallery-sharded exact top-k retrieval (sm_100a + NCCL): BASELINE.json configs[4].
+//
+// The reference has no counterpart beyond `-qf @ gf.T` + a full argsort on the CPU (reid/evaluator/attevaluator.py:44-46,
+// reid/evaluator/eva_functions.py:139); what this file promises is the exact stable top-k of fixed-order fp32 distances,
+// independent of chunking and of the number of gallery shards.
+//
+// Two-stage exact search.  Stage 1 ranks every (query, gallery row) pair by a COARSE distance: operands rounded to fp16 after a
+// per-row power-of-two scaling, one tcgen05 MMA per k-step instead of three.  For any pair the coarse and the exact inner
+// product differ by at most
+//        E(q, g) = CE * |q| * |g|,     CE = 2^-10 + 2^-17 + 2 * dim * 2^-24
+// (two fp16 roundings of <= 2^-11 relative each, their product term, subnormal/flush slack, and fp32 accumulation of `dim`
+// terms on either side), so the K' coarse-nearest rows of a query contain its k exact-nearest whenever
+//        coarse[K'-th] - E_max  >  exact[k-th among the K' re-scored]                                       (*)
+// Stage 2 re-scores the candidates with a fixed-order fp32 inner product and checks (*) per query; queries that fail it
+// (near-duplicate galleries, overflowed candidate buffers) are searched by brute force in the same fixed-order arithmetic.
+// Only candidates that can still reach the top k are re-scored: a candidate whose coarse distance exceeds the coarse k-th
+// by more than 2 E_max has at least k rows strictly closer in exact arithmetic and is skipped (it sorts last).
+//
+// Lists are packed 8-byte keys (orderable(distance) << 32 | global row index), ascending, KEY_EMPTY for unused slots: one
+// array to sort, merge and send.
+//
+// Sharded protocol (grl_sharded_topk; W ranks, gallery rows split contiguously, rank r owns query slice r for the list work):
+//   S0  every rank contributes nq/W query rows, ncclAllGather -> all nq rows          (or takes the full block as given)
+//   S1  queries -> fp16 plane + scales + fixed-order |q|^2
+//   S2  coarse pass over the local shard: K' coarse-nearest keys per query
+//   S3  ncclAllReduce(max) of {overflow marks, max |g|^2}; all-to-all (grouped ncclSend/ncclRecv) of the lists by query slice;
+//       rank r merges the W lists of its slice -> the global coarse K'; ncclAllGather of the merged slices
+//   S4  every rank re-scores the candidates whose gallery rows it owns (0 elsewhere)
+//   S5  ncclReduceScatter(sum) of the disjoint contributions -> exact distances of the own slice
+//   S6  finalize the own slice: sort by (exact distance, index), top k, completeness proof -> flags
+//   S7  ncclAllGather of the [nq/W, k+1] result keys (flag in the extra column); flagged rows compacted on the device;
+//       keys -> top_d / top_i on every rank
+//   S8  flagged rows: brute force per shard + all-gather + merge, scattered over the results (synchronous mode reads the
+//       count on the host -- the one synchronisation; asynchronous mode gates a fixed number of row slots on the device)
+#include <algorithm>
+
+#include "api.h"
+#include "comm.h"
+#include "eval_common.cuh"
+
+namespace grl {
+
+// ------------------------------------------------------------------ operand conversion
+// fp32 row -> fp16 row scaled by a power of two so that max|x| lands in [2^14, 2^15); one warp per row.
+// inv_scale[row] = 1/scale, sqnorm[row] = |x|^2 (fixed order), gmax2 = max over rows of sqnorm (uint-ordered atomicMax).
+__global__ void f16_rows_kernel(const float* __restrict__ x, long long rows, int dim, __half* __restrict__ out,
+                                float* __restrict__ inv_scale, float* __restrict__ sqnorm, unsigned int* __restrict__ gmax2) {
+    const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const int lane = lane_id();
+    const float4* r4 = reinterpret_cast<const float4*>(x + row * dim);
+    const int nv = dim >> 2;
+    float m = 0.f, acc = 0.f;
+    for (int j = lane; j < nv; j += 32) {
+        const float4 v = __ldg(r4 + j);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        acc = __fadd_rn(acc, __fmul_rn(v.x, v.x)); acc = __fadd_rn(acc, __fmul_rn(v.y, v.y));
+        acc = __fadd_rn(acc, __fmul_rn(v.z, v.z)); acc = __fadd_rn(acc, __fmul_rn(v.w, v.w));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+    }
+    int e = 0;
+    if (m > 0.f && m < CUDART_INF_F) e = (int)((__float_as_uint(m) >> 23) & 0xff) - 127;
+    e = max(-100, min(100, e));
+    const float s = ldexpf(1.f, 14 - e);
+    __half2* o2 = reinterpret_cast<__half2*>(out + row * dim);
+    for (int j = lane; j < nv; j += 32) {
+        const float4 v = __ldg(r4 + j);
+        o2[2 * j] = __floats2half2_rn(v.x * s, v.y * s);
+        o2[2 * j + 1] = __floats2half2_rn(v.z * s, v.w * s);
+    }
+    if (lane == 0) {
+        inv_scale[row] = ldexpf(1.f, e - 14);
+        sqnorm[row] = acc;
+        atomicMax(gmax2, __float_as_uint(acc));
+    }
+}
+
+// ------------------------------------------------------------------ streaming top-K' lists (packed keys)
+constexpr int TOPK_SMALL = 32;                  // candidate counts up to this are merged by one warp per row
+
+__global__ void fill_keys_kernel(uint64_t* keys, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = KEY_EMPTY;
+}
+
+// Before the first chunk no threshold exists: mark every row "overflowed" (cnt = cap + 1, threshold -inf) so the first
+// update rescans its tile row and the epilogue of the first GEMM appends nothing.
+__global__ void topk_filter_init_kernel(float* thresh, int* cnt, int nq, int cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) { thresh[i] = -CUDART_INF_F; cnt[i] = cap + 1; }
+}
+
+__device__ __forceinline__ float thresh_of(uint64_t kth) { return kth == KEY_EMPTY ? CUDART_INF_F : key_value(kth); }
+
+// One column chunk folded into the running lists, fed by the distance GEMM's candidate filter.  One block per query row:
+//   cnt <= TOPK_SMALL : handled by list_update_small_kernel (or nothing to do)
+//   cnt <= cap        : sort the candidates alone, then merge them into the sorted list by rank
+//   cnt  > cap        : the candidate buffer overflowed.  First chunk (its tile IS stored): rescan the tile row; any other
+//                       chunk: the row's list can no longer be trusted -> dirty (finalisation sends it to brute force)
+// and publish the new K'-th best distance as the row's filter threshold.
+__global__ void __launch_bounds__(TOPK_THREADS) list_update_kernel(const float* __restrict__ dist, long long ld, int ncols, int k, int64_t idx_base,
+                                                                   uint64_t* __restrict__ list, float* __restrict__ thresh_out,
+                                                                   const unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt, int cap,
+                                                                   uint32_t* __restrict__ dirty) {
+    __shared__ uint64_t keys[TOPK_BUF];
+    __shared__ int count;
+    __shared__ uint64_t thresh;
+    const int row = blockIdx.x;
+    const int cnt = cand_cnt[row];
+    if (cnt <= TOPK_SMALL) return;
+    uint64_t* lrow = list + (long long)row * k;
+    if (cnt <= cap) {
+        // a list key moves down by the number of candidates below it, a candidate lands at its rank plus the number of list
+        // keys below it (keys are unique: the index is part of the key)
+        uint64_t* cs = keys;                        // [npc] sorted candidates (cap <= TOPK_BUF / 2)
+        uint64_t* ls = keys + TOPK_BUF / 2;         // [k]   the running list (k <= TOPK_MAXK <= TOPK_BUF / 2)
+        int npc = 2;
+        while (npc < cnt) npc <<= 1;
+        for (int i = threadIdx.x; i < npc; i += blockDim.x) cs[i] = i < cnt ? cand[(long long)row * cap + i] : KEY_EMPTY;
+        for (int i = threadIdx.x; i < k; i += blockDim.x) ls[i] = lrow[i];
+        block_bitonic_sort(cs, npc);
+        for (int i = threadIdx.x; i < k + cnt; i += blockDim.x) {
+            uint64_t key;
+            int pos;
+            if (i < k) {
+                key = ls[i];
+                int lo = 0, hi = cnt;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid] < key) lo = mid + 1; else hi = mid; }
+                pos = i + lo;
+                if (lo == 0) pos = (pos == k - 1) ? pos : -1 - pos;      // unmoved: nothing to write unless it defines the threshold
+            } else {
+                key = cs[i - k];
+                int lo = 0, hi = k;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (ls[mid] < key) lo = mid + 1; else hi = mid; }
+                pos = (i - k) + lo;
+            }
+            if (pos >= 0 && pos < k) {
+                lrow[pos] = key;
+                if (pos == k - 1) thresh_out[row] = thresh_of(key);
+            }
+        }
+        if (threadIdx.x == 0) cand_cnt[row] = 0;
+        return;
+    }
+    if (dist == nullptr) {
+        if (threadIdx.x == 0) { dirty[row] = 1u; thresh_out[row] = -CUDART_INF_F; cand_cnt[row] = 0; }
+        return;
+    }
+    const float* drow = dist + (long long)row * ld;
+    if (lrow[0] == KEY_EMPTY && ncols <= TOPK_BUF) {
+        // bootstrap (empty list, first chunk): one sort of the tile row, sized to the row
+        int npad = 2;
+        while (npad < ncols) npad <<= 1;
+        for (int i = threadIdx.x; i < npad; i += blockDim.x) keys[i] = i < ncols ? make_key(drow[i], (uint32_t)(idx_base + i)) : KEY_EMPTY;
+        block_bitonic_sort(keys, npad);
+        for (int i = threadIdx.x; i < k; i += blockDim.x) lrow[i] = i < npad ? keys[i] : KEY_EMPTY;
+        if (threadIdx.x == 0) {
+            thresh_out[row] = thresh_of((k - 1 < npad) ? keys[k - 1] : KEY_EMPTY);
+            cand_cnt[row] = 0;
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < TOPK_BUF; i += blockDim.x) keys[i] = i < k ? lrow[i] : KEY_EMPTY;
+    if (threadIdx.x == 0) count = k;
+    __syncthreads();
+    if (threadIdx.x == 0) thresh = keys[k - 1];
+    __syncthreads();
+    const int stage_cap = k <= 256 ? TOPK_WAVE : TOPK_BUF - TOPK_WAVE;
+    for (int c0 = 0; c0 < ncols; c0 += TOPK_WAVE) {
+        const uint64_t th = thresh;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u * TOPK_THREADS + threadIdx.x;
+            if (c < ncols) {
+                const uint64_t key = make_key(drow[c], (uint32_t)(idx_base + c));
+                if (key < th) keys[atomicAdd(&count, 1)] = key;
+            }
+        }
+        __syncthreads();
+        const bool last = c0 + TOPK_WAVE >= ncols;
+        const int n = count;                         // one snapshot per thread, then a barrier: the flush decision is block-uniform
+        __syncthreads();
+        if (n > stage_cap || (last && n > k)) {
+            int npad = 2;
+            while (npad < n) npad <<= 1;
+            for (int i = n + threadIdx.x; i < npad; i += blockDim.x) keys[i] = KEY_EMPTY;
+            block_bitonic_sort(keys, npad);
+            if (threadIdx.x == 0) { count = k; thresh = keys[k - 1]; }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) lrow[i] = keys[i];
+    if (threadIdx.x == 0) { thresh_out[row] = thresh_of(keys[k - 1]); cand_cnt[row] = 0; }
+}
+
+// The common case once the thresholds have tightened: a handful of candidates per row and chunk.  One WARP per row, no block
+// barriers: the candidates are sorted across the lanes with a shuffle network and merged into the (sorted) running list by
+// rank, so the cost is one pass over the list instead of a block-wide sort.
+__global__ void __launch_bounds__(256) list_update_small_kernel(int nq, int k, uint64_t* __restrict__ list, float* __restrict__ thresh_out,
+                                                                const unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt, int cap) {
+    extern __shared__ uint64_t small_keys[];          // [8 warps][k]
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= nq) return;
+    const int cnt = cand_cnt[row];
+    if (cnt == 0 || cnt > TOPK_SMALL) return;
+    uint64_t* sl = small_keys + (size_t)warp * k;
+    uint64_t* lrow = list + (long long)row * k;
+    for (int t = lane; t < k; t += 32) sl[t] = lrow[t];
+    uint64_t c = lane < cnt ? cand[(long long)row * cap + lane] : KEY_EMPTY;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {      // bitonic sort across the lanes, ascending
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const uint64_t o = __shfl_xor_sync(0xffffffffu, c, stride);
+            const bool up = (lane & size) == 0;
+            const bool lower = (lane & stride) == 0;
+            c = ((c < o) == (up == lower)) ? c : o;
+        }
+    }
+    __syncwarp();
+    if (lane < cnt) {                                 // candidates: rank among the list keys
+        int lo = 0, hi = k;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sl[mid] < c) lo = mid + 1; else hi = mid; }
+        const int pos = lo + lane;
+        if (pos < k) {
+            lrow[pos] = c;
+            if (pos == k - 1) thresh_out[row] = key_value(c);
+        }
+    }
+    for (int t = lane; t < k; t += 32) {              // list keys: shifted down by the number of candidates below them
+        const uint64_t key = sl[t];
+        int below = 0;
+        for (int j = 0; j < cnt; ++j) below += (__shfl_sync(0xffffffffu, c, j) < key) ? 1 : 0;
+        const int pos = t + below;
+        if (below > 0 && pos < k) lrow[pos] = key;
+        if (pos == k - 1) thresh_out[row] = thresh_of(key);
+    }
+    if (lane == 0) cand_cnt[row] = 0;
+}
+
+// keys [nq][k] -> (distance f32, index i64) [nq][k]; empty slots become (+inf, -1)
+__global__ void unpack_keys_kernel(const uint64_t* __restrict__ keys, long long ld_keys, int nq, int k, float* __restrict__ out_d,
+                                   int64_t* __restrict__ out_i) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)nq * k) return;
+    const long long r = i / k;
+    const int t = (int)(i - r * k);
+    const uint64_t key = keys[r * ld_keys + t];
+    if (key == KEY_EMPTY) { out_d[i] = CUDART_INF_F; out_i[i] = -1; }
+    else { out_d[i] = key_value(key); out_i[i] = (int64_t)key_index(key); }
+}
+
+// ------------------------------------------------------------------ exact re-score
+// Staged API: exact_d[row][t] = exact distance of query `row` to candidate cand_i[row][t] when that gallery row lives in this
+// shard ([idx_base, idx_base + ng)), else 0 -- so that the per-shard results combine by a plain sum.  One block per query.
+__global__ void __launch_bounds__(256) rescore_kernel(int metric, const float* __restrict__ q, const float* __restrict__ g, int ng, int dim,
+                                                      long long idx_base, const int64_t* __restrict__ cand_i, int kp,
+                                                      float* __restrict__ exact_d) {
+    extern __shared__ float qs[];
+    const int row = blockIdx.x;
+    for (int j = threadIdx.x; j < (dim >> 2); j += blockDim.x)
+        reinterpret_cast<float4*>(qs)[j] = __ldg(reinterpret_cast<const float4*>(q + (long long)row * dim) + j);
+    __syncthreads();
+    const float qq = (metric == GRL_METRIC_L2) ? warp_sqnorm_fixed(qs, dim) : 0.f;
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int t = warp; t < kp; t += nw) {
+        const long long idx = cand_i[(long long)row * kp + t] - idx_base;
+        float d = 0.f;
+        if (idx >= 0 && idx < ng) {
+            float dot, gg;
+            warp_dot_fixed(qs, g + idx * dim, dim, dot, gg);
+            d = exact_distance(metric, dot, qq, gg);
+        }
+        if (lane_id() == 0) exact_d[(long long)row * kp + t] = d;
+    }
+}
+
+// E_max of condition (*) for one query: CE * |q| * max|g| (slightly inflated for the rounding of this very product)
+__device__ __forceinline__ float coarse_emax(float ce, float qq, float g2) { return ce * sqrtf(qq) * sqrtf(g2) * 1.00001f; }
+
+// The fused path: candidates come as the (merged) coarse key list of the row.  Candidate t >= k is SKIPPED (exact = +inf,
+// it sorts behind every re-scored one) when its coarse distance exceeds the coarse k-th by more than twice the worst-case
+// coarse error: each of the first k candidates is then strictly closer in exact arithmetic, so it cannot be among the k nearest.
+// Rows owned by another shard get 0 (sum-combinable); stats[2] / stats[3] count re-scored / skipped candidates of this rank.
+__global__ void __launch_bounds__(256) rescore_keys_kernel(int metric, const float* __restrict__ q, const float* __restrict__ q_n2,
+                                                           const float* __restrict__ g, int ng, int dim, long long idx_base,
+                                                           const uint64_t* __restrict__ list, int kp, int k, const uint32_t* __restrict__ gmax2_bits,
+                                                           float ce, float* __restrict__ exact_d, int32_t* __restrict__ stats) {
+    extern __shared__ float qs[];
+    __shared__ int n_done, n_skip;
+    const int row = blockIdx.x;
+    if (threadIdx.x == 0) { n_done = 0; n_skip = 0; }
+    for (int j = threadIdx.x; j < (dim >> 2); j += blockDim.x)
+        reinterpret_cast<float4*>(qs)[j] = __ldg(reinterpret_cast<const float4*>(q + (long long)row * dim) + j);
+    __syncthreads();
+    const float qq = q_n2[row];                       // fixed-order |q|^2 (f16_rows_kernel), the value warp_sqnorm_fixed returns
+    const float g2 = __uint_as_float(*gmax2_bits);
+    const float emax = coarse_emax(ce, qq, g2);
+    const uint64_t* lrow = list + (long long)row * kp;
+    const uint64_t kth = (k - 1 < kp) ? lrow[k - 1] : KEY_EMPTY;
+    float cut = CUDART_INF_F;                         // coarse values above `cut` cannot reach the top k
+    if (kth != KEY_EMPTY) {
+        const float ck = key_value(kth);
+        cut = (metric == GRL_METRIC_L2) ? ck + 4.f * emax + 2e-5f * (qq + g2) + 4e-12f : ck + 2.f * emax + 2e-6f * fabsf(ck);
+        if (!(cut == cut)) cut = CUDART_INF_F;        // NaN anywhere: re-score everything
+    }
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int done = 0, skip = 0;
+    for (int t = warp; t < kp; t += nw) {
+        const uint64_t key = lrow[t];
+        float d = 0.f;
+        if (key != KEY_EMPTY) {
+            const long long idx = (long long)key_index(key) - idx_base;
+            if (idx >= 0 && idx < ng) {
+                if (t >= k && key_value(key) > cut) { d = CUDART_INF_F; ++skip; }
+                else {
+                    float dot, gg;
+                    warp_dot_fixed(qs, g + idx * dim, dim, dot, gg);
+                    d = exact_distance(metric, dot, qq, gg);
+                    ++done;
+                }
+            }
+        }
+        if (lane_id() == 0) exact_d[(long long)row * kp + t] = d;
+    }
+    if (stats) {
+        if (lane_id() == 0) { atomicAdd(&n_done, done); atomicAdd(&n_skip, skip); }
+        __syncthreads();
+        if (threadIdx.x == 0) { atomicAdd(stats + 2, n_done); atomicAdd(stats + 3, n_skip); }
+    }
+}
+
+// ------------------------------------------------------------------ finalisation + completeness proof
+// Staged API.  coarse_d holds -q.g (metric 0) or the SQUARED L2 distance (metric 1) of the coarse pass, ascending.
+__global__ void __launch_bounds__(256) topk_finalize_kernel(int metric, const float* __restrict__ q, int dim, const float* __restrict__ coarse_d,
+                                                            const int64_t* __restrict__ cand_i, const float* __restrict__ exact_d, int kp,
+                                                            int npad, const float* __restrict__ gmax2, float ce, int k,
+                                                            const int32_t* __restrict__ dirty, float* __restrict__ top_d,
+                                                            int64_t* __restrict__ top_i, int32_t* __restrict__ flags,
+                                                            int32_t* __restrict__ nflag) {
+    extern __shared__ uint64_t fkeys[];
+    __shared__ float red[8];
+    __shared__ int nvalid_s;
+    const int row = blockIdx.x;
+    if (threadIdx.x == 0) nvalid_s = 0;
+    __syncthreads();
+    int local_valid = 0;
+    for (int t = threadIdx.x; t < npad; t += blockDim.x) {
+        uint64_t key = KEY_EMPTY;
+        if (t < kp) {
+            const int64_t idx = cand_i[(long long)row * kp + t];
+            if (idx >= 0) { key = make_key(exact_d[(long long)row * kp + t], (uint32_t)idx); ++local_valid; }
+        }
+        fkeys[t] = key;
+    }
+    if (local_valid) atomicAdd(&nvalid_s, local_valid);
+    // |q|^2 (any order: only an upper bound is needed, a relative 1e-5 is added below)
+    float qq = 0.f;
+    for (int j = threadIdx.x; j < dim; j += blockDim.x) { const float v = q[(long long)row * dim + j]; qq += v * v; }
+    qq = warp_sum(qq);
+    if (lane_id() == 0) red[threadIdx.x >> 5] = qq;
+    block_bitonic_sort(fkeys, npad);                  // also orders the writes above before the reads below
+    qq = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) qq += red[w];
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const uint64_t key = fkeys[t];
+        if (key == KEY_EMPTY) { top_d[(long long)row * k + t] = CUDART_INF_F; top_i[(long long)row * k + t] = -1; }
+        else { top_d[(long long)row * k + t] = key_value(key); top_i[(long long)row * k + t] = (int64_t)key_index(key); }
+    }
+    if (threadIdx.x == 0) {
+        bool ok = !(dirty && dirty[row]);             // a shard's candidate list overflowed: not provable
+        const int nvalid = nvalid_s;
+        if (ok && nvalid == kp && nvalid > k - 1 && fkeys[k - 1] != KEY_EMPTY) {   // a full list may have cut off relevant rows
+            const float u = key_value(fkeys[k - 1]);
+            const float ck = coarse_d[(long long)row * kp + kp - 1];
+            const float g2 = *gmax2;
+            const float emax = coarse_emax(ce, qq, g2);
+            if (metric == GRL_METRIC_L2) {
+                const float lb = ck - 2.f * emax - 1e-5f * (qq + g2);
+                ok = lb > 1e-12f && sqrtf(lb) * 0.999999f > u;
+            } else {
+                ok = ck - emax - 1e-6f * fabsf(ck) > u;
+            }
+            if (!(ok)) ok = false;                    // NaN anywhere -> brute force
+        }
+        flags[row] = ok ? 0 : 1;
+        if (!ok) atomicAdd(nflag, 1);
+    }
+}
+
+// The fused path: row r of this rank's query slice.  list = merged global coarse keys of the slice rows, exact_d their
+// re-scored distances (+inf for skipped candidates); writes k result keys + the flag (0/1) as the (k+1)-th 8-byte word.
+__global__ void __launch_bounds__(256) finalize_keys_kernel(int metric, const float* __restrict__ q_n2, const uint64_t* __restrict__ list,
+                                                            const float* __restrict__ exact_d, int kp, int npad, const uint32_t* __restrict__ gmax2_bits,
+                                                            float ce, int k, const uint32_t* __restrict__ dirty, int rows_valid,
+                                                            uint64_t* __restrict__ out) {
+    extern __shared__ uint64_t fkeys[];
+    __shared__ int nvalid_s;
+    const int row = blockIdx.x;
+    uint64_t* orow = out + (long long)row * (k + 1);
+    if (row >= rows_valid) {                          // padding rows of the last slice: empty result, never flagged
+        for (int t = threadIdx.x; t < k; t += blockDim.x) orow[t] = KEY_EMPTY;
+        if (threadIdx.x == 0) orow[k] = 0;
+        return;
+    }
+    if (threadIdx.x == 0) nvalid_s = 0;
+    __syncthreads();
+    const uint64_t* lrow = list + (long long)row * kp;
+    int local_valid = 0;
+    for (int t = threadIdx.x; t < npad; t += blockDim.x) {
+        uint64_t key = KEY_EMPTY;
+        if (t < kp) {
+            const uint64_t c = lrow[t];
+            if (c != KEY_EMPTY) { key = make_key(exact_d[(long long)row * kp + t], key_index(c)); ++local_valid; }
+        }
+        fkeys[t] = key;
+    }
+    if (local_valid) atomicAdd(&nvalid_s, local_valid);
+    block_bitonic_sort(fkeys, npad);
+    for (int t = threadIdx.x; t < k; t += blockDim.x) orow[t] = fkeys[t];
+    if (threadIdx.x == 0) {
+        bool ok = !(dirty && dirty[row]);
+        const int nvalid = nvalid_s;
+        if (ok && nvalid == kp && nvalid > k - 1 && fkeys[k - 1] != KEY_EMPTY) {
+            const float u = key_value(fkeys[k - 1]);
+            const float ck = key_value(lrow[kp - 1]);
+            const float qq = q_n2[row] * 1.00001f, g2 = __uint_as_float(*gmax2_bits);
+            const float emax = coarse_emax(ce, qq, g2);
+            if (metric == GRL_METRIC_L2) {
+                const float lb = ck - 2.f * emax - 1e-5f * (qq + g2);
+                ok = lb > 1e-12f && sqrtf(lb) * 0.999999f > u;
+            } else {
+                ok = ck - emax - 1e-6f * fabsf(ck) > u;
+            }
+            if (!(ok)) ok = false;
+        }
+        orow[k] = ok ? 0ull : 1ull;
+    }
+}
+
+// lists [nlists][rows][kp] (sorted keys) -> out [rows][kp]: the kp smallest of each row's nlists * kp keys
+__global__ void __launch_bounds__(256) merge_key_lists_kernel(const uint64_t* __restrict__ lists, int nlists, int rows, int kp, int npad,
+                                                              uint64_t* __restrict__ out) {
+    extern __shared__ uint64_t mkeys[];
+    const int row = blockIdx.x;
+    const int n = nlists * kp;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        uint64_t key = KEY_EMPTY;
+        if (i < n) {
+            const int s = i / kp, j = i - s * kp;
+            key = lists[((long long)s * rows + row) * kp + j];
+        }
+        mkeys[i] = key;
+    }
+    block_bitonic_sort(mkeys, npad);
+    for (int i = threadIdx.x; i < kp; i += blockDim.x) out[(long long)row * kp + i] = mkeys[i];
+}
+
+// Flag column of the result keys -> ascending list of flagged rows + counters (ONE block: the order must be the same on every
+// rank).  stats[0] = flagged queries, stats[1] = rows with an overflow mark.
+__global__ void __launch_bounds__(1024) compact_flags_kernel(const uint64_t* __restrict__ out, int nq, int k, const uint32_t* __restrict__ dirty,
+                                                             int32_t* __restrict__ rows, int32_t* __restrict__ nflag, int32_t* __restrict__ stats) {
+    __shared__ int part[1024];
+    __shared__ int dpart[32];
+    const int per = (nq + blockDim.x - 1) / blockDim.x;
+    const int r0 = threadIdx.x * per, r1 = min(nq, r0 + per);
+    int c = 0, dcount = 0;
+    for (int r = r0; r < r1; ++r) {
+        c += out[(long long)r * (k + 1) + k] ? 1 : 0;
+        dcount += (dirty && dirty[r]) ? 1 : 0;
+    }
+    part[threadIdx.x] = c;
+    dcount = (int)warp_sum((float)dcount);
+    if (lane_id() == 0) dpart[threadIdx.x >> 5] = dcount;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < (int)blockDim.x; ++i) { const int v = part[i]; part[i] = run; run += v; }
+        int dsum = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) dsum += dpart[i];
+        *nflag = run;
+        if (stats) { stats[0] = run; stats[1] = dsum; }
+    }
+    __syncthreads();
+    int pos = part[threadIdx.x];
+    for (int r = r0; r < r1; ++r)
+        if (out[(long long)r * (k + 1) + k]) rows[pos++] = r;
+}
+
+// ------------------------------------------------------------------ brute force in the fixed-order arithmetic
+// tile[r][c] = exact distance of query rows[r0 + r] (or r0 + r when rows == NULL) to gallery row c.  Each block keeps rq query
+// rows in shared memory and streams a slab of gallery rows once, one warp per gallery row.  nrows_dev (optional) gates the
+// launch on a device-side row count (asynchronous mode: the host does not know how many rows are flagged).
+__global__ void __launch_bounds__(256) exact_rows_kernel(int metric, const float* __restrict__ q, const int32_t* __restrict__ rows, int r0, int rq,
+                                                         const int32_t* __restrict__ nrows_dev, const float* __restrict__ g, int ng, int dim,
+                                                         float* __restrict__ tile, long long ld_tile) {
+    extern __shared__ float qs[];                     // [rq][dim]
+    __shared__ float qqs[16];
+    if (nrows_dev) {
+        const int n = *nrows_dev;
+        if (r0 >= n) return;
+        rq = min(rq, n - r0);
+    }
+    for (int r = 0; r < rq; ++r) {
+        const long long src = rows ? rows[r0 + r] : (r0 + r);
+        for (int j = threadIdx.x; j < (dim >> 2); j += blockDim.x)
+            reinterpret_cast<float4*>(qs + (long long)r * dim)[j] = __ldg(reinterpret_cast<const float4*>(q + src * dim) + j);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (warp == 0) for (int r = 0; r < rq; ++r) { const float v = warp_sqnorm_fixed(qs + (long long)r * dim, dim); if (lane_id() == 0) qqs[r] = v; }
+    __syncthreads();
+    for (long long c = (long long)blockIdx.x * nw + warp; c < ng; c += (long long)gridDim.x * nw) {
+        for (int r = 0; r < rq; ++r) {                // the gallery row stays in L1 across the rq passes
+            float dot, gg;
+            warp_dot_fixed(qs + (long long)r * dim, g + c * dim, dim, dot, gg);
+            if (lane_id() == 0) tile[(long long)r * ld_tile + c] = exact_distance(metric, dot, qqs[r], gg);
+        }
+    }
+}
+
+// dst[rows[r0 + r]] = src[r] for r < min(n, *nrows_dev - r0)
+__global__ void scatter_rows_kernel(const float* __restrict__ src_d, const int64_t* __restrict__ src_i, const int32_t* __restrict__ rows, int r0,
+                                    const int32_t* __restrict__ nrows_dev, int k, float* __restrict__ dst_d, int64_t* __restrict__ dst_i) {
+    const int r = blockIdx.x;
+    if (nrows_dev && r0 + r >= *nrows_dev) return;
+    const long long dst = (long long)rows[r0 + r] * k;
+    for (int t = threadIdx.x; t < k; t += blockDim.x) { dst_d[dst + t] = src_d[(long long)r * k + t]; dst_i[dst + t] = src_i[(long long)r * k + t]; }
+}
+
+}  // namespace grl
+
+using namespace grl;
+
+// ==================================================================================================== host side
+static int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+// Column chunks of one coarse pass.  The first chunk has no thresholds yet: its tile IS stored and every row is rescanned, so it
+// is kept small (TOPK_FIRST_CHUNK columns, one 1024-key sort per row).  Afterwards the K'-th best of n_seen columns lets
+// ~K' * nc / n_seen candidates per row through, so chunks grow with n_seen (at most doubling the columns seen) up to the
+// steady-state size, whose 256 x 256 tiles fill whole waves of the persistent grid; their tiles are never stored.
+constexpr int TOPK_FIRST_CHUNK = 1024;
+// candidates per query row and column chunk: a chunk at most doubles the columns seen, so ~K' candidates per row are expected;
+// the buffer holds twice that (an overflow outside the first chunk marks the row dirty -> brute force)
+static int cand_cap(int kprime) { return std::max(512, 2 * kprime); }
+
+static int topk_chunk_max(int nq, int ng, int num_sms) {
+    long long c = 16384;
+    if (nq >= 1024 && c < ng) {
+        const long long mt = (nq + 255) / 256;
+        double best = 0.0; long long best_n = c / 256;
+        for (long long n = c / 256; n >= 16; --n) {
+            const long long tiles = mt * n, waves = (tiles + num_sms - 1) / num_sms;
+            const double eff = (double)tiles / (double)(waves * num_sms);
+            if (eff > best + 1e-9) { best = eff; best_n = n; }
+        }
+        c = best_n * 256;
+    }
+    if (c > ng) c = (ng + 7) / 8 * 8;
+    return (int)c;
+}
+static int topk_next_chunk(int c0, int ng, int chunk_max) {
+    long long nc = c0 == 0 ? TOPK_FIRST_CHUNK : (c0 < chunk_max ? c0 : chunk_max);
+    nc = (nc + 255) / 256 * 256;
+    if (nc > chunk_max) nc = chunk_max;
+    if (nc > ng - c0) nc = ng - c0;
+    return (int)nc;
+}
+
+extern "C" int grl_topk_kprime(int k) { return k <= 128 ? 256 : (k <= 256 ? 512 : 1024); }
+
+static float coarse_error_constant(int dim) {   // CE of the header comment
+    return 0x1p-10f + 0x1p-17f + 2.f * (float)dim * 0x1p-24f;
+}
+
+// ---- workspace of one coarse pass (nq query rows against a shard of ng rows)
+struct CoarseLayout {
+    int chunk, first, cap;
+    size_t q16, g16, qf, gf, tile, thresh, cnt, cand, total;
+};
+static void coarse_layout(int nq, int ng, int dim, int kprime, bool prepared, CoarseLayout* L) {
+    L->chunk = topk_chunk_max(nq, ng, 148);
+    L->first = ng < TOPK_FIRST_CHUNK ? (ng + 7) / 8 * 8 : TOPK_FIRST_CHUNK;
+    L->cap = cand_cap(kprime);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    L->q16 = take((size_t)nq * dim * 2);
+    L->g16 = take(prepared ? 0 : (size_t)L->chunk * dim * 2);
+    L->qf = take((size_t)nq * 4 * 2);                 // inv_scale | sqnorm
+    L->gf = take(prepared ? 0 : (size_t)L->chunk * 4 * 2);
+    L->tile = take((size_t)nq * L->first * 4);        // coarse distances of the first chunk only
+    L->thresh = take((size_t)nq * 4);
+    L->cnt = take((size_t)nq * 4);
+    L->cand = take((size_t)nq * L->cap * 8);
+    L->total = off;
+}
+
+// A gallery shard converted once (fp16 rows with their per-row scales, squared norms, the largest squared norm): searches
+// against a static gallery skip the per-chunk conversion.
+struct PreparedLayout { size_t g16, inv, n2, gmax2, total; };
+static PreparedLayout prepared_layout(int ng, int dim) {
+    PreparedLayout P;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    P.g16 = take((size_t)ng * dim * 2);
+    P.inv = take((size_t)ng * 4);
+    P.n2 = take((size_t)ng * 4);
+    P.gmax2 = take(4);
+    P.total = off;
+    return P;
+}
+extern "C" size_t grl_gallery_prepared_bytes(int ng, int dim) {
+    if (ng <= 0 || dim <= 0 || (dim & 7)) return 0;
+    return prepared_layout(ng, dim).total;
+}
+extern "C" int grl_gallery_prepare(grl_handle* h, const float* g, int ng, int dim, void* prepared, size_t prepared_bytes, void* stream) {
+    if (!h || !g || !prepared) return set_error(h, GRL_EINVAL, "grl_gallery_prepare: NULL argument");
+    if (ng <= 0 || dim <= 0 || (dim & 7)) return set_error(h, GRL_EINVAL, "grl_gallery_prepare: need ng > 0 and dim %% 8 == 0 (dim=%d)", dim);
+    const PreparedLayout P = prepared_layout(ng, dim);
+    if (prepared_bytes < P.total) return set_error(h, GRL_ENOMEM, "grl_gallery_prepare: buffer %zu < %zu bytes", prepared_bytes, P.total);
+    if (reinterpret_cast<uintptr_t>(prepared) & 255) return set_error(h, GRL_EINVAL, "grl_gallery_prepare: buffer must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* b = (uint8_t*)prepared;
+    GRL_CUDA(h, cudaMemsetAsync(b + P.gmax2, 0, 4, st));
+    f16_rows_kernel<<<(int)(((long long)ng * 32 + 255) / 256), 256, 0, st>>>(g, ng, dim, (__half*)(b + P.g16), (float*)(b + P.inv), (float*)(b + P.n2),
+                                                                             (unsigned int*)(b + P.gmax2));
+    GRL_LAUNCH_CHECK(h);
+    return GRL_OK;
+}
+
+// Queries -> fp16 plane + scales + fixed-order squared norms (stage S1).  `scratch_max` receives the largest query norm (unused).
+static int convert_queries(grl_handle* h, cudaStream_t st, const float* q, int nq, int dim, uint8_t* w, const CoarseLayout& L) {
+    float* q_inv = (float*)(w + L.qf);
+    f16_rows_kernel<<<(int)(((long long)nq * 32 + 255) / 256), 256, 0, st>>>(q, nq, dim, (__half*)(w + L.q16), q_inv, q_inv + nq,
+                                                                             (unsigned int*)(w + L.cand));   // cand is free until the first GEMM
+    GRL_LAUNCH_CHECK(h);
+    return GRL_OK;
+}
+
+// Stage S2: the K' coarse-nearest rows of the shard per query, as sorted keys list [nq][kprime].  Queries must have been
+// converted (convert_queries).  gmax2_bits (uint-ordered float) is max-combined with the shard's largest |g|^2; dirty[row] is
+// set where a candidate buffer overflowed outside the first chunk.  Both must be initialised by the caller.
+static int coarse_pass(grl_handle* h, cudaStream_t st, int metric, const float* g, const void* prepared, int nq, int ng, int dim, int kprime,
+                       int64_t idx_base, uint64_t* list, uint32_t* gmax2_bits, uint32_t* dirty, uint8_t* w, const CoarseLayout& L) {
+    __half* q16 = (__half*)(w + L.q16);
+    __half* g16 = (__half*)(w + L.g16);
+    float* q_inv = (float*)(w + L.qf);
+    float* q_n2 = q_inv + nq;
+    float* g_inv = (float*)(w + L.gf);
+    float* g_n2 = g_inv + L.chunk;
+    float* tile = (float*)(w + L.tile);
+    float* thresh = (float*)(w + L.thresh);
+    int* cand_cnt = (int*)(w + L.cnt);
+    unsigned long long* cand = (unsigned long long*)(w + L.cand);
+    const PreparedLayout P = prepared_layout(ng, dim);
+    const uint8_t* pb = (const uint8_t*)prepared;
+    GRL_TRY(ensure_dyn_smem(h, (const void*)list_update_small_kernel, 8 * kprime * 8));
+    topk_filter_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(thresh, cand_cnt, nq, L.cap);
+    GRL_LAUNCH_CHECK(h);
+    {
+        const long long n = (long long)nq * kprime;
+        fill_keys_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(list, n);
+        GRL_LAUNCH_CHECK(h);
+    }
+    for (int c0 = 0; c0 < ng;) {
+        const int nc = topk_next_chunk(c0, ng, L.chunk);
+        const bool first = c0 == 0;
+        const __half* g16c = g16;
+        const float* g_invc = g_inv;
+        const float* g_n2c = g_n2;
+        if (prepared) {                               // chunk starts are multiples of 256 columns: the slices stay 16-byte aligned
+            g16c = (const __half*)(pb + P.g16) + (size_t)c0 * dim;
+            g_invc = (const float*)(pb + P.inv) + c0;
+            g_n2c = (const float*)(pb + P.n2) + c0;
+        } else {
+            f16_rows_kernel<<<(int)(((long long)nc * 32 + 255) / 256), 256, 0, st>>>(g + (size_t)c0 * dim, nc, dim, g16, g_inv, g_n2, gmax2_bits);
+            GRL_LAUNCH_CHECK(h);
+        }
+        GemmEpi e = epi_default();
+        if (first) { e.C = tile; e.ldc = L.first; }   // later chunks never store their tile
+        e.row_scale = q_inv; e.col_scale = g_invc;
+        if (metric == GRL_METRIC_L2) { e.mode = 2; e.row_norm = q_n2; e.col_norm = g_n2c; }
+        else e.alpha = -1.f;
+        // the epilogue keeps only distances that can still enter a row's list (v <= current K'-th best) as candidates
+        e.tk_cand = cand; e.tk_cnt = cand_cnt; e.tk_thresh = thresh; e.tk_cap = L.cap; e.tk_idx_base = idx_base + c0;
+        GRL_TRY(coarse_gemm_launch(h, st, nq, nc, dim, q16, dim, g16c, dim, e));
+        list_update_small_kernel<<<(nq + 7) / 8, 256, (size_t)8 * kprime * 8, st>>>(nq, kprime, list, thresh, cand, cand_cnt, L.cap);
+        GRL_LAUNCH_CHECK(h);
+        list_update_kernel<<<nq, TOPK_THREADS, 0, st>>>(first ? tile : nullptr, L.first, nc, kprime, idx_base + c0, list, thresh, cand, cand_cnt,
+                                                        L.cap, dirty);
+        GRL_LAUNCH_CHECK(h);
+        c0 += nc;
+    }
+    if (prepared) {   // the prepared index carries the shard's largest squared norm
+        // max-combine (the value is a non-negative float: its bit pattern orders like an unsigned integer)
+        GRL_CUDA(h, cudaMemcpyAsync(gmax2_bits, pb + P.gmax2, 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return GRL_OK;
+}
+
+// ---- staged API (one shard; the caller runs its own collectives between the stages)
+struct StagedCoarseLayout { CoarseLayout C; size_t coarse, list, dirty, total; };
+static void staged_coarse_layout(int nq, int ng, int dim, int kprime, StagedCoarseLayout* S) {
+    coarse_layout(nq, ng, dim, kprime, false, &S->C);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    S->coarse = take(S->C.total);
+    S->list = take((size_t)nq * kprime * 8);
+    S->dirty = take((size_t)nq * 4);
+    S->total = off;
+}
+extern "C" size_t grl_coarse_topk_workspace_bytes(int nq, int ng, int dim) {
+    StagedCoarseLayout S;
+    staged_coarse_layout(nq, ng, dim, TOPK_MAXK, &S);     // sized for the largest K'
+    return S.total;
+}
+
+static int coarse_topk_impl(grl_handle* h, int metric, const float* q, const float* g, const void* prepared, int nq, int ng, int dim, int kprime,
+                            int64_t idx_base, float* coarse_d, int64_t* coarse_i, float* gmax2, int32_t* dirty, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    if (!h || !q || (!g && !prepared) || !coarse_d || !coarse_i || !gmax2 || !dirty || !workspace) return set_error(h, GRL_EINVAL, "grl_coarse_topk: NULL argument");
+    if (nq <= 0 || ng <= 0 || dim <= 0 || (dim & 7)) return set_error(h, GRL_EINVAL, "grl_coarse_topk: need nq,ng > 0 and dim %% 8 == 0 (dim=%d)", dim);
+    if (kprime <= 0 || kprime > TOPK_MAXK) return set_error(h, GRL_EINVAL, "grl_coarse_topk: need 0 < kprime <= %d", TOPK_MAXK);
+    if (metric != GRL_METRIC_NEG_DOT && metric != GRL_METRIC_L2) return set_error(h, GRL_EINVAL, "grl_coarse_topk: unknown metric %d", metric);
+    if (idx_base < 0 || idx_base + ng > 0xFFFFFFFFll) return set_error(h, GRL_EINVAL, "grl_coarse_topk: global index must fit 32 bits");
+    StagedCoarseLayout S;
+    staged_coarse_layout(nq, ng, dim, kprime, &S);
+    if (workspace_bytes < S.total) return set_error(h, GRL_ENOMEM, "grl_coarse_topk: workspace %zu < %zu bytes", workspace_bytes, S.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* w = (uint8_t*)workspace;
+    uint64_t* list = (uint64_t*)(w + S.list);
+    GRL_CUDA(h, cudaMemsetAsync(gmax2, 0, 4, st));
+    GRL_CUDA(h, cudaMemsetAsync(dirty, 0, (size_t)nq * 4, st));
+    GRL_TRY(convert_queries(h, st, q, nq, dim, w + S.coarse, S.C));
+    GRL_TRY(coarse_pass(h, st, metric, g, prepared, nq, ng, dim, kprime, idx_base, list, (uint32_t*)gmax2, (uint32_t*)dirty, w + S.coarse, S.C));
+    const long long n = (long long)nq * kprime;
+    unpack_keys_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(list, kprime, nq, kprime, coarse_d, coarse_i);
+    GRL_LAUNCH_CHECK(h);
+    return GRL_OK;
+}
+
+extern "C" int grl_coarse_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int kprime,
+                               int64_t idx_base, float* coarse_d, int64_t* coarse_i, float* gmax2, int32_t* dirty, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    if (!g) return set_error(h, GRL_EINVAL, "grl_coarse_topk: NULL argument");
+    return coarse_topk_impl(h, metric, q, g, nullptr, nq, ng, dim, kprime, idx_base, coarse_d, coarse_i, gmax2, dirty, workspace, workspace_bytes,
+                            stream);
+}
+extern "C" int grl_coarse_topk_prepared(grl_handle* h, int metric, const float* q, const void* prepared, int nq, int ng, int dim, int kprime,
+                                        int64_t idx_base, float* coarse_d, int64_t* coarse_i, float* gmax2, int32_t* dirty,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (!prepared) return set_error(h, GRL_EINVAL, "grl_coarse_topk_prepared: NULL argument");
+    return coarse_topk_impl(h, metric, q, nullptr, prepared, nq, ng, dim, kprime, idx_base, coarse_d, coarse_i, gmax2, dirty, workspace,
+                            workspace_bytes, stream);
+}
+
+extern "C" int grl_rescore(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int64_t idx_base,
+                           const int64_t* cand_i, int kprime, float* exact_d, void* stream) {
+    if (!h || !q || !g || !cand_i || !exact_d) return set_error(h, GRL_EINVAL, "grl_rescore: NULL argument");
+    if (nq <= 0 || ng <= 0 || dim <= 0 || (dim & 7) || dim > 32768 || kprime <= 0) return set_error(h, GRL_EINVAL, "grl_rescore: bad sizes");
+    const size_t smem = (size_t)dim * 4;
+    GRL_TRY(ensure_dyn_smem(h, (const void*)rescore_kernel, (int)smem));
+    rescore_kernel<<<nq, 256, smem, (cudaStream_t)stream>>>(metric, q, g, ng, dim, idx_base, cand_i, kprime, exact_d);
+    GRL_LAUNCH_CHECK(h);
+    return GRL_OK;
+}
+
+extern "C" int grl_topk_finalize(grl_handle* h, int metric, const float* q, int nq, int dim, const float* coarse_d, const int64_t* cand_i,
+                                 const float* exact_d, int kprime, const float* gmax2, const int32_t* dirty, int k, float* top_d,
+                                 int64_t* top_i, int32_t* flags, int32_t* nflag, void* stream) {
+    if (!h || !q || !coarse_d || !cand_i || !exact_d || !gmax2 || !top_d || !top_i || !flags || !nflag)
+        return set_error(h, GRL_EINVAL, "grl_topk_finalize: NULL argument");
+    if (nq <= 0 || dim <= 0 || kprime <= 0 || kprime > TOPK_MAXK || k <= 0 || k > kprime) return set_error(h, GRL_EINVAL, "grl_topk_finalize: need 0 < k <= kprime <= %d", TOPK_MAXK);
+    cudaStream_t st = (cudaStream_t)stream;
+    GRL_CUDA(h, cudaMemsetAsync(nflag, 0, 4, st));
+    const int npad = next_pow2(kprime < 2 ? 2 : kprime);
+    topk_finalize_kernel<<<nq, 256, (size_t)npad * 8, st>>>(metric, q, dim, coarse_d, cand_i, exact_d, kprime, npad, gmax2,
+                                                            coarse_error_constant(dim), k, dirty, top_d, top_i, flags, nflag);
+    GRL_LAUNCH_CHECK(h);
+    return GRL_OK;
+}
+
+// ---- brute force in the fixed-order arithmetic (fallback of the two-stage search; any query subset)
+static int exact_group_rows(int dim) {
+    int r = (160 * 1024) / (dim * 4);
+    return r < 1 ? 1 : (r > 8 ? 8 : r);
+}
+extern "C" size_t grl_exact_topk_workspace_bytes(int nq, int ng, int dim) {
+    const int R = std::min(exact_group_rows(dim), nq > 0 ? nq : 1);
+    return align_up((size_t)R * ng * 4, 1024);
+}
+// Queries rows[r0 .. r0 + nrows) (or r0 .. when rows == NULL) against the shard: out_d / out_i [nrows][k], contiguous.
+// nrows_dev != NULL: device-side row count gating the work (the host passes an upper bound as nrows).
+static int exact_topk_rows(grl_handle* h, int metric, const float* q, const int32_t* rows, int r0, int nrows, const int32_t* nrows_dev,
+                           const float* g, int ng, int dim, int k, int64_t idx_base, float* out_d, int64_t* out_i, float* tile, cudaStream_t st) {
+    const int R = exact_group_rows(dim);
+    GRL_TRY(ensure_dyn_smem(h, (const void*)exact_rows_kernel, (int)((size_t)R * dim * 4)));
+    for (int r = 0; r < nrows; r += R) {
+        const int rq = std::min(R, nrows - r);
+        exact_rows_kernel<<<h->num_sms * 4, 256, (size_t)rq * dim * 4, st>>>(metric, q, rows, r0 + r, rq, nrows_dev, g, ng, dim, tile, ng);
+        GRL_LAUNCH_CHECK(h);
+        float* od = out_d + (size_t)r * k;
+        int64_t* oi = out_i + (size_t)r * k;
+        GRL_TRY(grl_topk_init(h, od, oi, rq, k, st));
+        GRL_TRY(grl_topk_rows(h, tile, ng, rq, ng, k, idx_base, od, oi, st));
+    }
+    return GRL_OK;
+}
+extern "C" int grl_exact_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k, int64_t idx_base,
+                              float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !q || !g || !top_d || !top_i || !workspace) return set_error(h, GRL_EINVAL, "grl_exact_topk: NULL argument");
+    if (nq <= 0 || ng <= 0 || dim <= 0 || (dim & 7) || dim > 32768) return set_error(h, GRL_EINVAL, "grl_exact_topk: need nq,ng > 0, dim %% 8 == 0, dim <= 32768");
+    if (k <= 0 || k > TOPK_MAXK) return set_error(h, GRL_EINVAL, "grl_exact_topk: need 0 < k <= %d", TOPK_MAXK);
+    if (metric != GRL_METRIC_NEG_DOT && metric != GRL_METRIC_L2) return set_error(h, GRL_EINVAL, "grl_exact_topk: unknown metric %d", metric);
+    if (idx_base < 0 || idx_base + ng > 0xFFFFFFFFll) return set_error(h, GRL_EINVAL, "grl_exact_topk: global index must fit 32 bits");
+    if (workspace_bytes < grl_exact_topk_workspace_bytes(nq, ng, dim)) return set_error(h, GRL_ENOMEM, "grl_exact_topk: workspace too small");
+    return exact_topk_rows(h, metric, q, nullptr, 0, nq, nullptr, g, ng, dim, k, idx_base, top_d, top_i, (float*)workspace, (cudaStream_t)stream);
+}
+
+// ==================================================================================================== the fused search
+constexpr int SEARCH_STAGES = 9;       // S0..S8 of the header comment (S9, the unpacking, is timed with S7)
+constexpr int BRUTE_BATCH = 1024;      // flagged rows handled per round of the brute-force leg
+
+struct SearchLayout {
+    int world, qs, nqp, kp, fb;
+    CoarseLayout C;
+    size_t Q, coarse, L, meta, R, MA, E, Es, OUT, misc, rows, tile, btd, bti, bad, bai, bmd, bmi, total;
+};
+static void search_layout(int world, int nq, int ng, int dim, int k, bool prepared, SearchLayout* S) {
+    S->world = world;
+    S->qs = (nq + world - 1) / world;
+    S->nqp = S->qs * world;
+    S->kp = grl_topk_kprime(k);
+    S->fb = std::min(nq, BRUTE_BATCH);
+    coarse_layout(S->nqp, ng, dim, S->kp, prepared, &S->C);
+    const size_t nqp = S->nqp, kp = S->kp, qs = S->qs;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    S->Q = take(world > 1 ? nqp * dim * 4 : 0);                 // all query rows (gathered / copied + zero padding)
+    S->coarse = take(S->C.total);
+    S->L = take(nqp * kp * 8);                                  // local coarse lists
+    S->meta = take((nqp + 1) * 4);                              // overflow marks [nqp] | max |g|^2 bits
+    S->R = take(world > 1 ? nqp * kp * 8 : 0);                  // all-to-all receive: [world][qs][kp]
+    S->MA = take(world > 1 ? nqp * kp * 8 : 0);                 // merged global lists of all slices (all-gathered)
+    S->E = take(nqp * kp * 4);                                  // re-scored distances (owned candidates, 0 elsewhere)
+    S->Es = take(world > 1 ? qs * kp * 4 : 0);                  // reduce-scattered: exact distances of the own slice
+    S->OUT = take(nqp * (size_t)(k + 1) * 8);                   // result keys + flag word
+    S->misc = take(64);                                         // nflag
+    S->rows = take(nqp * 4);
+    S->tile = take(grl_exact_topk_workspace_bytes(nq, ng, dim));
+    S->btd = take((size_t)S->fb * k * 4);
+    S->bti = take((size_t)S->fb * k * 8);
+    S->bad = take(world > 1 ? (size_t)world * S->fb * k * 4 : 0);
+    S->bai = take(world > 1 ? (size_t)world * S->fb * k * 8 : 0);
+    S->bmd = take(world > 1 ? (size_t)S->fb * k * 4 : 0);
+    S->bmi = take(world > 1 ? (size_t)S->fb * k * 8 : 0);
+    S->total = off;
+}
+
+static int stage_mark(grl_handle* h, cudaStream_t st, int i) {
+    if (!h->stage_prof) return GRL_OK;
+    if (!h->stage_ev) {
+        h->stage_ev = new cudaEvent_t[SEARCH_STAGES + 1];
+        for (int j = 0; j <= SEARCH_STAGES; ++j) GRL_CUDA(h, cudaEventCreate(&h->stage_ev[j]));
+        h->n_stage_ev = SEARCH_STAGES + 1;
+    }
+    GRL_CUDA(h, cudaEventRecord(h->stage_ev[i], st));
+    return GRL_OK;
+}
+
+extern "C" int grl_search_profile(grl_handle* h, int on) {
+    if (!h) return GRL_EINVAL;
+    h->stage_prof = on ? 1 : 0;
+    return GRL_OK;
+}
+extern "C" int grl_search_stage_ms(grl_handle* h, double* ms, int n) {
+    if (!h || !ms || n < SEARCH_STAGES) return set_error(h, GRL_EINVAL, "grl_search_stage_ms: need room for %d stages", SEARCH_STAGES);
+    if (!h->stage_ev) return set_error(h, GRL_EINVAL, "grl_search_stage_ms: no profiled search yet (grl_search_profile)");
+    GRL_CUDA(h, cudaEventSynchronize(h->stage_ev[SEARCH_STAGES]));
+    for (int i = 0; i < SEARCH_STAGES; ++i) {
+        float t = 0.f;
+        GRL_CUDA(h, cudaEventElapsedTime(&t, h->stage_ev[i], h->stage_ev[i + 1]));
+        ms[i] = t;
+    }
+    return GRL_OK;
+}
+
+static int search_impl(grl_handle* h, int world, int rank, int metric, const float* q, int q_rows, const float* g, const void* prepared, int nq,
+                       int ng, int dim, int k, int64_t idx_base, int max_flagged, float* top_d, int64_t* top_i, int32_t* stats, void* workspace,
+                       size_t workspace_bytes, void* stream, const char* who) {
+    if (!h || !q || !g || !top_d || !top_i || !workspace) return set_error(h, GRL_EINVAL, "%s: NULL argument", who);
+    if (nq <= 0 || ng <= 0 || dim <= 0 || (dim & 7) || dim > 32768) return set_error(h, GRL_EINVAL, "%s: need nq,ng > 0, dim %% 8 == 0, dim <= 32768 (dim=%d)", who, dim);
+    if (k <= 0 || k > TOPK_MAXK / 2) return set_error(h, GRL_EINVAL, "%s: need 0 < k <= %d", who, TOPK_MAXK / 2);
+    if (metric != GRL_METRIC_NEG_DOT && metric != GRL_METRIC_L2) return set_error(h, GRL_EINVAL, "%s: unknown metric %d", who, metric);
+    if (idx_base < 0 || idx_base + ng > 0xFFFFFFFFll) return set_error(h, GRL_EINVAL, "%s: global index must fit 32 bits", who);
+    SearchLayout S;
+    search_layout(world, nq, ng, dim, k, prepared != nullptr, &S);
+    if (workspace_bytes < S.total) return set_error(h, GRL_ENOMEM, "%s: workspace %zu < %zu bytes", who, workspace_bytes, S.total);
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return set_error(h, GRL_EINVAL, "%s: workspace must be 256-byte aligned", who);
+    if ((long long)world * S.kp > 16384) return set_error(h, GRL_EINVAL, "%s: world * K' must be <= 16384", who);
+    const int qs = S.qs, nqp = S.nqp, kp = S.kp;
+    const int my_rows = std::max(0, std::min(qs, nq - rank * qs));           // valid rows of this rank's query slice
+    if (q_rows != nq && q_rows != my_rows)
+        return set_error(h, GRL_EINVAL, "%s: q_rows must be nq (%d, all queries) or this rank's slice (%d rows), got %d", who, nq, my_rows, q_rows);
+    const NcclApi* api = nullptr;
+    ncclComm_t comm = nullptr;
+    if (world > 1) {
+        api = nccl_api(h);
+        if (!api) return GRL_ENCCL;
+        comm = (ncclComm_t)h->comm;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* w = (uint8_t*)workspace;
+    uint8_t* cw = w + S.coarse;
+    uint64_t* L = (uint64_t*)(w + S.L);
+    uint32_t* dirty = (uint32_t*)(w + S.meta);
+    uint32_t* gmax2_bits = dirty + nqp;
+    float* E = (float*)(w + S.E);
+    uint64_t* OUT = (uint64_t*)(w + S.OUT);
+    int32_t* nflag = (int32_t*)(w + S.misc);
+    int32_t* rows = (int32_t*)(w + S.rows);
+    const float ce = coarse_error_constant(dim);
+    if (stats) GRL_CUDA(h, cudaMemsetAsync(stats, 0, 8 * sizeof(int32_t), st));
+    GRL_TRY(stage_mark(h, st, 0));
+
+    // ---- S0: all query rows on every rank
+    const float* Q = q;
+    if (world > 1) {
+        float* Qw = (float*)(w + S.Q);
+        if (q_rows == nq) {
+            GRL_CUDA(h, cudaMemcpyAsync(Qw, q, (size_t)nq * dim * 4, cudaMemcpyDeviceToDevice, st));
+            if (nqp > nq) GRL_CUDA(h, cudaMemsetAsync(Qw + (size_t)nq * dim, 0, (size_t)(nqp - nq) * dim * 4, st));
+        } else {
+            float* mine = Qw + (size_t)rank * qs * dim;
+            if (my_rows > 0) GRL_CUDA(h, cudaMemcpyAsync(mine, q, (size_t)my_rows * dim * 4, cudaMemcpyDeviceToDevice, st));
+            if (my_rows < qs) GRL_CUDA(h, cudaMemsetAsync(mine + (size_t)my_rows * dim, 0, (size_t)(qs - my_rows) * dim * 4, st));
+            GRL_NCCL(h, api, api->AllGather(mine, Qw, (size_t)qs * dim, ncclFloat, comm, st));      // in place
+        }
+        Q = Qw;
+    }
+    GRL_TRY(stage_mark(h, st, 1));
+
+    // ---- S1 + S2: conversion and coarse pass over the local shard
+    GRL_CUDA(h, cudaMemsetAsync(dirty, 0, (size_t)(nqp + 1) * 4, st));
+    GRL_TRY(convert_queries(h, st, Q, nqp, dim, cw, S.C));
+    const float* q_n2 = (const float*)(cw + S.C.qf) + nqp;
+    GRL_TRY(stage_mark(h, st, 2));
+    GRL_TRY(coarse_pass(h, st, metric, g, prepared, nqp, ng, dim, kp, idx_base, L, gmax2_bits, dirty, cw, S.C));
+    GRL_TRY(stage_mark(h, st, 3));
+
+    // ---- S3: exchange by query slice, merge, all-gather the merged lists
+    const uint64_t* MA = L;
+    if (world > 1) {
+        uint64_t* R = (uint64_t*)(w + S.R);
+        uint64_t* MAw = (uint64_t*)(w + S.MA);
+        GRL_NCCL(h, api, api->AllReduce(dirty, dirty, (size_t)nqp + 1, ncclUint32, ncclMax, comm, st));
+        const size_t cnt = (size_t)qs * kp;
+        GRL_NCCL(h, api, api->GroupStart());
+        for (int p = 0; p < world; ++p) {
+            GRL_NCCL(h, api, api->Send(L + (size_t)p * cnt, cnt, ncclUint64, p, comm, st));
+            GRL_NCCL(h, api, api->Recv(R + (size_t)p * cnt, cnt, ncclUint64, p, comm, st));
+        }
+        GRL_NCCL(h, api, api->GroupEnd());
+        const int npad = next_pow2(world * kp);
+        GRL_TRY(ensure_dyn_smem(h, (const void*)merge_key_lists_kernel, npad * 8));
+        uint64_t* mine = MAw + (size_t)rank * cnt;
+        merge_key_lists_kernel<<<qs, 256, (size_t)npad * 8, st>>>(R, world, qs, kp, npad, mine);
+        GRL_LAUNCH_CHECK(h);
+        GRL_NCCL(h, api, api->AllGather(mine, MAw, cnt, ncclUint64, comm, st));                      // in place
+        MA = MAw;
+    }
+    GRL_TRY(stage_mark(h, st, 4));
+
+    // ---- S4: re-score the candidates this rank owns
+    {
+        const size_t smem = (size_t)dim * 4;
+        GRL_TRY(ensure_dyn_smem(h, (const void*)rescore_keys_kernel, (int)smem));
+        rescore_keys_kernel<<<nqp, 256, smem, st>>>(metric, Q, q_n2, g, ng, dim, idx_base, MA, kp, k, gmax2_bits, ce, E, stats);
+        GRL_LAUNCH_CHECK(h);
+    }
+    GRL_TRY(stage_mark(h, st, 5));
+
+    // ---- S5: exact distances of the own slice
+    const float* Es = E;
+    if (world > 1) {
+        float* Esw = (float*)(w + S.Es);
+        GRL_NCCL(h, api, api->ReduceScatter(E, Esw, (size_t)qs * kp, ncclFloat, ncclSum, comm, st));
+        Es = Esw;
+    }
+    GRL_TRY(stage_mark(h, st, 6));
+
+    // ---- S6: finalize the own slice
+    {
+        const int npad = next_pow2(kp < 2 ? 2 : kp);
+        const size_t row0 = (size_t)rank * qs;
+        finalize_keys_kernel<<<qs, 256, (size_t)npad * 8, st>>>(metric, q_n2 + row0, MA + row0 * kp, Es, kp, npad, gmax2_bits, ce, k, dirty + row0,
+                                                                world > 1 ? my_rows : nq, OUT + row0 * (k + 1));
+        GRL_LAUNCH_CHECK(h);
+    }
+    GRL_TRY(stage_mark(h, st, 7));
+
+    // ---- S7: results of every slice on every rank, flagged rows
+    if (world > 1) GRL_NCCL(h, api, api->AllGather(OUT + (size_t)rank * qs * (k + 1), OUT, (size_t)qs * (k + 1), ncclUint64, comm, st));
+    compact_flags_kernel<<<1, 1024, 0, st>>>(OUT, nq, k, dirty, rows, nflag, stats);
+    GRL_LAUNCH_CHECK(h);
+    {
+        const long long n = (long long)nq * k;
+        unpack_keys_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(OUT, k + 1, nq, k, top_d, top_i);
+        GRL_LAUNCH_CHECK(h);
+    }
+    GRL_TRY(stage_mark(h, st, 8));
+
+    // ---- S8: brute force for the flagged rows (identical row list on every rank)
+    int todo = max_flagged;
+    const int32_t* gate = nflag;
+    if (max_flagged < 0) {                            // synchronous mode: one 4-byte read tells the host how many rows there are
+        int host_nflag = 0;
+        GRL_CUDA(h, cudaMemcpyAsync(&host_nflag, nflag, 4, cudaMemcpyDeviceToHost, st));
+        GRL_CUDA(h, cudaStreamSynchronize(st));
+        todo = host_nflag;
+        gate = nullptr;
+    } else if (todo > nq) todo = nq;
+    float* btd = (float*)(w + S.btd);
+    int64_t* bti = (int64_t*)(w + S.bti);
+    for (int r0 = 0; r0 < todo; r0 += S.fb) {
+        const int nb = std::min(S.fb, todo - r0);
+        GRL_TRY(exact_topk_rows(h, metric, Q, rows, r0, nb, gate, g, ng, dim, k, idx_base, btd, bti, (float*)(w + S.tile), st));
+        const float* fd = btd;
+        const int64_t* fi = bti;
+        if (world > 1) {
+            float* bad = (float*)(w + S.bad);
+            int64_t* bai = (int64_t*)(w + S.bai);
+            GRL_NCCL(h, api, api->GroupStart());
+            GRL_NCCL(h, api, api->AllGather(btd, bad, (size_t)nb * k, ncclFloat, comm, st));
+            GRL_NCCL(h, api, api->AllGather(bti, bai, (size_t)nb * k, ncclInt64, comm, st));
+            GRL_NCCL(h, api, api->GroupEnd());
+            GRL_TRY(grl_topk_merge(h, bad, bai, world, nb, k, (float*)(w + S.bmd), (int64_t*)(w + S.bmi), st));
+            fd = (const float*)(w + S.bmd);
+            fi = (const int64_t*)(w + S.bmi);
+        }
+        scatter_rows_kernel<<<nb, 128, 0, st>>>(fd, fi, rows, r0, gate, k, top_d, top_i);
+        GRL_LAUNCH_CHECK(h);
+    }
+    GRL_TRY(stage_mark(h, st, 9));
+    return GRL_OK;
+}
+
+extern "C" size_t grl_sharded_topk_workspace_bytes(const grl_handle* h, int nq, int ng_local, int dim, int k, int prepared) {
+    if (!h || nq <= 0 || ng_local <= 0 || dim <= 0 || k <= 0 || k > TOPK_MAXK / 2) return 0;
+    SearchLayout S;
+    search_layout(h->comm ? h->comm_world : 1, nq, ng_local, dim, k, prepared != 0, &S);
+    return S.total;
+}
+
+extern "C" int grl_sharded_topk(grl_handle* h, int metric, const float* q, int q_rows, const float* g_local, const void* prepared, int nq,
+                                int ng_local, int dim, int k, int64_t idx_base, int max_flagged, float* top_d, int64_t* top_i, int32_t* stats,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) return GRL_EINVAL;
+    const int world = h->comm ? h->comm_world : 1, rank = h->comm ? h->comm_rank : 0;
+    return search_impl(h, world, rank, metric, q, q_rows, g_local, prepared, nq, ng_local, dim, k, idx_base, max_flagged, top_d, top_i, stats,
+                       workspace, workspace_bytes, stream, "grl_sharded_topk");
+}
+
+// ---- one shard, end to end (the single-rank form of the same code path; ignores the handle's communicator)
+extern "C" size_t grl_dist_topk_workspace_bytes(int nq, int ng, int dim) {
+    if (nq <= 0 || ng <= 0 || dim <= 0) return 0;
+    SearchLayout S;
+    search_layout(1, nq, ng, dim, TOPK_MAXK / 2, false, &S);     // sized for the largest supported k, unprepared gallery
+    return S.total;
+}
+extern "C" int grl_dist_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k,
+                             int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream) {
+    return search_impl(h, 1, 0, metric, q, nq, g, nullptr, nq, ng, dim, k, idx_base, -1, top_d, top_i, nullptr, workspace, workspace_bytes, stream,
+                       "grl_dist_topk");
+}
+extern "C" int grl_dist_topk_prepared(grl_handle* h, int metric, const float* q, const float* g, const void* prepared, int nq, int ng, int dim,
+                                      int k, int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+    if (!prepared) return set_error(h, GRL_EINVAL, "grl_dist_topk_prepared: NULL argument");
+    return search_impl(h, 1, 0, metric, q, nq, g, prepared, nq, ng, dim, k, idx_base, -1, top_d, top_i, nullptr, workspace, workspace_bytes, stream,
+                       "grl_dist_topk_prepared");
+}

@@ -137,9 +137,10 @@ def argsort_rows(distmat):
 # --------------------------------------------------------------------------------------------
 # Gallery-sharded retrieval (BASELINE.json configs[4]).  The reference has no counterpart: it materialises the whole
 # matrix and argsorts it on the CPU (attevaluator.py:150, eva_functions.py:139).  Gallery rows are split contiguously
-# over the ranks, queries are replicated; every rank searches its shard, one all-gather of [nq, k] candidates over
-# NCCL/NVLink follows, and every rank merges them with ties broken by the lower global gallery index, so the result
-# does not depend on the number of shards.
+# over the ranks; every rank runs the coarse tensor-core pass over its shard, the candidate lists are exchanged by query
+# slice over NCCL/NVLink, and every step that follows (merge, exact re-score, completeness proof) is divided over the
+# ranks as well; ties are broken by the lower global gallery index, so the result does not depend on the number of shards.
+# The protocol lives in the library (grl_sharded_topk); the host only creates the communicator.
 # --------------------------------------------------------------------------------------------
 def shard_bounds(num_gallery, world_size, rank):
     """Contiguous split of gallery rows: returns (first row, number of rows) of `rank`."""
@@ -207,7 +208,7 @@ def retrieve_topk(qf, gf, k, idx_base=0, metric=0):
         top_d = torch.empty((nq, k), dtype=torch.float32, device=qf.device)
         top_i = torch.empty((nq, k), dtype=torch.int64, device=qf.device)
         ws_bytes = lib.grl_dist_topk_workspace_bytes(nq, ng, dim)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qf.device)
+        ws = _search_workspace(qf.device, ws_bytes)      # persistent: no allocation per search
         if prepared is None:
             _lib.check(h, lib.grl_dist_topk(h, metric, qf.data_ptr(), gf.data_ptr(), nq, ng, dim, k, idx_base, top_d.data_ptr(),
                                             top_i.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(qf.device)), "grl_dist_topk")
@@ -233,10 +234,117 @@ def merge_topk(all_d, all_i):
     return out_d, out_i
 
 
+# ---- the search communicator: one NCCL communicator per handle, created by the library (grl_comm_init) from a unique id that
+#      travels over the caller's torch.distributed group (any backend: it is 128 bytes of host data)
+def comm_info(device=None):
+    """(world, rank) of the handle's search communicator; (1, 0) without one."""
+    import ctypes as C
+    lib = _lib.load_library()
+    w, r = C.c_int(), C.c_int()
+    lib.grl_comm_info(_lib.get_handle(device), C.byref(w), C.byref(r))
+    return w.value, r.value
+
+
+def init_search_comm(group=None, device=None):
+    """Create the library's NCCL communicator over the ranks of `group` (default: the world group).  Rank 0 draws the unique id
+    (grl_comm_unique_id), torch.distributed broadcasts it, every rank calls grl_comm_init.  Idempotent per device."""
+    import ctypes as C
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1, 0
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return 1, 0
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if comm_info(dev) == (world, rank):
+        return world, rank
+    lib = _lib.load_library()
+    with torch.cuda.device(dev):
+        h = _lib.get_handle(dev)
+        buf = C.create_string_buffer(_lib.GRL_COMM_ID_BYTES)
+        if rank == 0:
+            _lib.check(h, lib.grl_comm_unique_id(h, buf, _lib.GRL_COMM_ID_BYTES), "grl_comm_unique_id")
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = C.create_string_buffer(box[0], _lib.GRL_COMM_ID_BYTES)
+        _lib.check(h, lib.grl_comm_init(h, ident, _lib.GRL_COMM_ID_BYTES, world, rank), "grl_comm_init")
+    return world, rank
+
+
+def destroy_search_comm(device=None):
+    _lib.load_library().grl_comm_destroy(_lib.get_handle(device))
+
+
+_SEARCH_WS = {}      # device index -> persistent workspace (grown on demand, reused by every search: no allocation per call)
+
+
+def _search_workspace(dev, nbytes):
+    ws = _SEARCH_WS.get(dev.index)
+    if ws is None or ws.numel() < nbytes:
+        raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        shift = (-raw.data_ptr()) % 1024
+        ws = raw[shift:shift + nbytes]
+        _SEARCH_WS[dev.index] = ws
+    return ws
+
+
+def query_slice(num_queries, world_size, rank):
+    """Rows of the query block rank `rank` contributes to a sharded search: (first row, number of rows)."""
+    qs = -(-num_queries // world_size)
+    lo = min(num_queries, rank * qs)
+    return lo, max(0, min(qs, num_queries - rank * qs))
+
+
+def search_stage_ms(device=None):
+    """Per-stage device times of the last profiled grl_sharded_topk call (grl_search_profile): dict name -> ms."""
+    import ctypes as C
+    lib = _lib.load_library()
+    h = _lib.get_handle(device)
+    ms = (C.c_double * _lib.GRL_SEARCH_STAGES)()
+    _lib.check(h, lib.grl_search_stage_ms(h, ms, _lib.GRL_SEARCH_STAGES), "grl_search_stage_ms")
+    names = ("query_allgather", "convert", "coarse_pass", "exchange_merge", "rescore", "reduce_scatter", "finalize",
+             "result_allgather_unpack", "brute_force")
+    return {n: float(v) for n, v in zip(names, ms)}
+
+
+def sharded_topk(qf, gf_local, k, idx_base, nq=None, metric=0, max_flagged=-1, out=None, stats=None):
+    """grl_sharded_topk: one search over a gallery sharded across the ranks of the library's search communicator
+    (init_search_comm), the whole protocol -- coarse tensor-core pass, NCCL exchanges, owned re-scores, completeness proof,
+    brute-force leg -- behind one C call on the current stream.
+
+    qf        all `nq` query rows, or (when `nq` is given and larger than qf.size(0)) this rank's query_slice of them
+    gf_local  this rank's gallery rows [ng_local, dim] or a PreparedGallery of them; idx_base = global index of its first row
+    out       optional (top_d f32 [nq, k], top_i i64 [nq, k]) CUDA tensors to fill;  stats: optional int32[8] CUDA tensor
+    Returns (top_d, top_i): the exact stable top-k of the fixed-order fp32 distances, identical on every rank."""
+    prepared = gf_local if isinstance(gf_local, PreparedGallery) else None
+    if prepared is not None:
+        gf = prepared.gf
+        qf = _pad_queries(qf, gf.size(1))
+    else:
+        qf, gf = _padded_features(qf, gf_local)
+    dev = qf.device
+    q_rows, dim, ng = qf.size(0), qf.size(1), gf.size(0)
+    nq = q_rows if nq is None else int(nq)
+    lib = _lib.load_library()
+    with torch.cuda.device(dev):
+        h = _lib.get_handle(dev)
+        if out is None:
+            out = (torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int64, device=dev))
+        top_d, top_i = out
+        nbytes = lib.grl_sharded_topk_workspace_bytes(h, nq, ng, dim, k, 1 if prepared is not None else 0)
+        if nbytes == 0:
+            raise RuntimeError("grl_sharded_topk: bad sizes nq=%d ng=%d dim=%d k=%d" % (nq, ng, dim, k))
+        ws = _search_workspace(dev, nbytes)
+        _lib.check(h, lib.grl_sharded_topk(h, metric, qf.data_ptr(), q_rows, gf.data_ptr(), None if prepared is None else prepared.buf.data_ptr(),
+                                           nq, ng, dim, k, idx_base, max_flagged, top_d.data_ptr(), top_i.data_ptr(), _lib.ptr(stats),
+                                           ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)), "grl_sharded_topk")
+    return top_d, top_i
+
+
 class CudaSearchStages(object):
-    """The per-rank stages of the two-stage exact search (include/grl_b200.h: grl_coarse_topk, grl_rescore, grl_topk_finalize,
-    grl_exact_topk, grl_topk_merge).  sharded_retrieve takes the stages as an object only so that its collectives can be
-    exercised on CPU with gloo in tests (which plug in a numpy restatement)."""
+    """The per-rank stage entry points of the two-stage exact search (include/grl_b200.h: grl_coarse_topk, grl_rescore,
+    grl_topk_finalize, grl_exact_topk, grl_topk_merge) for hosts that run their own collectives between them
+    (staged_retrieve below).  The product path is grl_sharded_topk, which runs the whole protocol in the library."""
 
     @staticmethod
     def kprime(k):
@@ -253,7 +361,7 @@ class CudaSearchStages(object):
             gmax2 = torch.zeros(1, dtype=torch.float32, device=qf.device)
             dirty = torch.zeros(nq, dtype=torch.int32, device=qf.device)
             ws_bytes = lib.grl_coarse_topk_workspace_bytes(nq, ng, dim)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qf.device)
+            ws = _search_workspace(qf.device, ws_bytes)
             if prepared is None:
                 _lib.check(h, lib.grl_coarse_topk(h, metric, qf.data_ptr(), gf.data_ptr(), nq, ng, dim, kp, idx_base, cd.data_ptr(),
                                                   ci.data_ptr(), gmax2.data_ptr(), dirty.data_ptr(), ws.data_ptr(), ws_bytes,
@@ -307,44 +415,73 @@ class CudaSearchStages(object):
         return top_d, top_i
 
 
-def sharded_retrieve(qf, gf_local, k, idx_base, group=None, metric=0, stages=None):
-    """One search over a gallery sharded across the ranks of `group` (torch.distributed; NCCL over NVLink on B200).
+def staged_retrieve(qf, gf_local, k, idx_base, group=None, metric=0, stages=None):
+    """The sharded search written against torch.distributed, stage by stage -- the protocol of grl_sharded_topk restated on the
+    host: rank r owns query slice r (query_slice) for all list work.
 
-    Every rank ranks its shard by the coarse tensor-core distance and keeps K' candidates per query; one all-gather + merge
-    gives the global coarse K'; every rank re-scores (fixed-order fp32) the candidates whose gallery rows it owns and an
-    all-reduce (sum of disjoint contributions) assembles them; finalisation sorts by exact distance and proves completeness
-    per query.  Queries without a proof (rare: near-duplicate galleries) are searched by brute force per shard and merged.
-    The result is identical on every rank and for every shard count."""
+        coarse K' lists of the local shard for every query
+        -> all-reduce(max) of the overflow marks and of max |g|^2
+        -> exchange by query slice (an all-to-all; spelled as all-gather + slicing here so that gloo can run it) and merge
+           -> the global coarse K' of the own slice -> all-gather of the merged slices
+        -> every rank re-scores the candidates whose gallery rows it owns (0 elsewhere)
+        -> sum over ranks (a reduce-scatter; spelled as all-reduce + slicing here) -> exact distances of the own slice
+        -> finalisation + completeness proof of the own slice -> all-gather of the results and flags
+        -> flagged queries: brute force per shard + all-gather + merge
+
+    `stages` supplies the per-rank computations (CudaSearchStages, or a numpy restatement in the CPU tests, which is how the
+    host-side protocol is exercised over gloo).  The result is identical on every rank and for every shard count."""
     import torch.distributed as dist
-    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    on = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if on else 1
+    rank = dist.get_rank(group) if on else 0
     prepared = gf_local if isinstance(gf_local, PreparedGallery) else None
     if stages is None:
-        if world == 1:
-            return retrieve_topk(qf, gf_local, k, idx_base=idx_base, metric=metric)
         stages = CudaSearchStages
         if prepared is not None:
             gf_local = prepared.gf
             qf = _pad_queries(qf, gf_local.size(1))
         else:
             qf, gf_local = _padded_features(qf, gf_local)
+    nq = qf.size(0)
     kp = stages.kprime(k)
     if prepared is not None:
         cd, ci, gmax2, dirty = stages.coarse(qf, gf_local, kp, idx_base, metric, prepared=prepared)
     else:
         cd, ci, gmax2, dirty = stages.coarse(qf, gf_local, kp, idx_base, metric)
+    lo, n = query_slice(nq, world, rank)
+    spans = [query_slice(nq, world, r) for r in range(world)]
+
+    def gather_rows(mine, width, dtype):
+        """all-gather of per-slice rows [n, width] (ragged last slices padded to the slice size) -> [nq, width]"""
+        qs = spans[0][1]
+        pad = torch.zeros((qs, width), dtype=dtype, device=mine.device)
+        pad[:mine.size(0)] = mine
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        return torch.cat([p[:spans[r][1]] for r, p in enumerate(parts)], 0)
+
     if world > 1:
+        dist.all_reduce(gmax2, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(dirty, op=dist.ReduceOp.MAX, group=group)   # a row whose candidate buffer overflowed on any shard
         all_d = [torch.empty_like(cd) for _ in range(world)]
         all_i = [torch.empty_like(ci) for _ in range(world)]
         dist.all_gather(all_d, cd.contiguous(), group=group)
         dist.all_gather(all_i, ci.contiguous(), group=group)
-        dist.all_reduce(gmax2, op=dist.ReduceOp.MAX, group=group)
-        dist.all_reduce(dirty, op=dist.ReduceOp.MAX, group=group)   # a row whose candidate buffer overflowed on any shard
-        cd, ci = stages.merge(torch.stack(all_d), torch.stack(all_i))
+        md, mi = stages.merge(torch.stack([d[lo:lo + n] for d in all_d]), torch.stack([i[lo:lo + n] for i in all_i])) if n else \
+            (cd[:0], ci[:0])
+        cd, ci = gather_rows(md, kp, cd.dtype), gather_rows(mi, kp, ci.dtype)
     ed = stages.rescore(qf, gf_local, ci, idx_base, metric)
     if world > 1:
         dist.all_reduce(ed, op=dist.ReduceOp.SUM, group=group)       # every candidate is owned by exactly one rank
-    top_d, top_i, flags = stages.finalize(qf, cd, ci, ed, gmax2, dirty, k, metric)
-    rows = torch.nonzero(flags).flatten()                            # identical on every rank (same inputs to finalize)
+    sl = slice(lo, lo + n)
+    if n:
+        top_d, top_i, flags = stages.finalize(qf[sl], cd[sl], ci[sl], ed[sl], gmax2, dirty[sl], k, metric)
+    else:
+        top_d, top_i, flags = cd[:0, :k], ci[:0, :k], dirty[:0]
+    if world > 1:
+        top_d, top_i = gather_rows(top_d, k, top_d.dtype), gather_rows(top_i, k, top_i.dtype)
+        flags = gather_rows(flags.view(-1, 1), 1, flags.dtype).view(-1)
+    rows = torch.nonzero(flags).flatten()                            # identical on every rank
     if rows.numel():
         d_x, i_x = stages.exact(qf[rows].contiguous(), gf_local, k, idx_base, metric)
         if world > 1:
@@ -356,6 +493,60 @@ def sharded_retrieve(qf, gf_local, k, idx_base, group=None, metric=0, stages=Non
         top_d[rows] = d_x
         top_i[rows] = i_x
     return top_d, top_i
+
+
+def sharded_retrieve(qf, gf_local, k, idx_base, group=None, metric=0, stages=None, nq=None, out=None, stats=None):
+    """One search over a gallery sharded across the ranks of `group` (torch.distributed; NCCL over NVLink on B200): the k
+    nearest gallery rows of every query, identical on every rank and for every shard count.
+
+    On the GPU this is ONE library call, grl_sharded_topk (the search communicator over `group` is created on first use);
+    `qf` may hold all queries or, with `nq` given, only this rank's query_slice.  With `stages` given the host-side
+    restatement of the protocol (staged_retrieve) runs instead -- that is how the CPU tests exercise it over gloo."""
+    if stages is not None:
+        return staged_retrieve(qf, gf_local, k, idx_base, group=group, metric=metric, stages=stages)
+    init_search_comm(group)
+    return sharded_topk(qf, gf_local, k, idx_base, nq=nq, metric=metric, out=out, stats=stats)
+
+
+def evaluate_sharded(distmat_local, q_pids, g_pids_local, q_camids, g_camids_local, idx_base, max_rank=100, group=None):
+    """eva_functions.evaluate (eva_functions.py:134-184) over a gallery sharded across the ranks of `group`:
+    `distmat_local` [nq, ng_local] holds this rank's gallery columns (global rows idx_base ...), g_pids_local / g_camids_local
+    their identities; query ids are replicated.  grl_cmc_map_sharded: all-gather of each query's positives, per-shard rank
+    counts, all-reduce(sum).  Returns (all_cmc np.float32[max_rank], mAP) -- on every rank, bit-identical to evaluate() on the
+    concatenated matrix.  max_rank is taken as given (the caller knows the global gallery size)."""
+    init_search_comm(group)
+    dist_l = _as_cuda_f32(distmat_local)
+    dev = dist_l.device
+    nq, ng = dist_l.shape
+    ids = [torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).to(device=dev, dtype=torch.int64).contiguous()
+           for a in (q_pids, g_pids_local, q_camids, g_camids_local)]
+    if ids[0].numel() != nq or ids[1].numel() != ng or ids[2].numel() != nq or ids[3].numel() != ng:
+        raise RuntimeError("evaluate_sharded: id arrays do not match distmat shape %s" % ((nq, ng),))
+    lib = _lib.load_library()
+    with torch.cuda.device(dev):
+        h = _lib.get_handle(dev)
+        hits = torch.empty(max_rank, dtype=torch.int32, device=dev)
+        ap = torch.empty(nq, dtype=torch.float64, device=dev)
+        first = torch.empty(nq, dtype=torch.int32, device=dev)
+        seen = torch.zeros(1, dtype=torch.int32, device=dev)
+        max_pos = 64
+        while True:
+            nbytes = lib.grl_cmc_map_sharded_workspace_bytes(h, nq, max_pos)
+            ws = _search_workspace(dev, nbytes)
+            _lib.check(h, lib.grl_cmc_map_sharded(h, dist_l.data_ptr(), dist_l.stride(0), ids[0].data_ptr(), ids[1].data_ptr(), ids[2].data_ptr(),
+                                                  ids[3].data_ptr(), nq, ng, idx_base, max_rank, max_pos, hits.data_ptr(), ap.data_ptr(),
+                                                  first.data_ptr(), seen.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)),
+                       "grl_cmc_map_sharded")
+            need = int(seen.item())                 # identical on every rank (all-reduced): every rank takes the same branch
+            if need <= max_pos:
+                break
+            max_pos = 1 << (need - 1).bit_length()
+    hits = hits.cpu().numpy()
+    ap = ap.cpu().numpy()
+    valid = ap >= 0
+    num_valid_q = float(valid.sum())
+    assert num_valid_q > 0, "Error: all query identities do not appear in gallery"
+    return hits.astype(np.float32) / num_valid_q, np.mean(ap[valid])
 
 
 class ATTEvaluator(object):

@@ -254,7 +254,9 @@ class GraphedHeadStep(object):
         step.f_uncorr, step.f_corr, step.corr_map, step.dx, step.grads[name]   # static output tensors
 
     The tensors of `sd` are read (and the BN running buffers / num_batches_tracked updated) in place at every replay, so an
-    optimizer that updates the parameters in place composes with it.  The reference has no counterpart (it runs eager)."""
+    optimizer that updates the parameters in place composes with it.  Construction leaves `sd` unchanged: the warm-up step
+    that precedes the capture runs on zero maps, so every BN buffer it touches is saved first and restored before the capture
+    (a loaded checkpoint / resumed run keeps its running statistics).  The reference has no counterpart (it runs eager)."""
 
     def __init__(self, sd, B, T, device=None):
         dev = torch.device(device) if device is not None else next(iter(sd.values())).device
@@ -265,8 +267,13 @@ class GraphedHeadStep(object):
         self._ws = _alloc_ws(workspace_bytes(B, T, True), dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        bn_keys = [p_ + s_ for p_ in head_buffer_names() for s_ in (".running_mean", ".running_var", ".num_batches_tracked")
+                   if p_ + s_ in sd]
         with torch.cuda.stream(side):                    # warm-up outside the capture: attribute calls, tensor-map cache, allocator
+            keep = {k: sd[k].clone() for k in bn_keys}   # the warm-up sees zero maps: its BN statistics must not reach `sd`
             self._run()
+            for k in bn_keys:
+                sd[k].copy_(keep[k])
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()

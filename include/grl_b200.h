@@ -34,6 +34,7 @@ extern "C" {
 #define GRL_ECUDA (-2)    /* CUDA runtime or driver error (message has the cudaError) */
 #define GRL_EARCH (-3)    /* device is not sm_100 */
 #define GRL_ENOMEM (-4)   /* caller-provided workspace too small */
+#define GRL_ENCCL (-5)    /* NCCL missing (dlopen) or a collective failed (message has the ncclResult) */
 
 typedef struct grl_handle grl_handle;
 
@@ -90,6 +91,19 @@ int grl_cmc_map(grl_handle* h, const float* dist, long long ld_dist, const int64
                 const int64_t* q_cam, const int64_t* g_cam, int nq, int ng, int max_rank,
                 int32_t* cmc_hits, double* ap, int32_t* first_hit, void* stream);
 
+/* The same evaluation over a gallery whose rows are sharded over the ranks of the handle's communicator (grl_comm_*; one
+ * rank without): `dist` [nq][ng_local] holds this rank's columns, g_pid / g_cam its rows, idx_base the global index of its
+ * first row (shards are contiguous and in rank order); q_pid / q_cam are replicated.  Two exchanges: an all-gather of each
+ * query's positives (distance, global index; at most max_pos per query and shard) and an all-reduce(sum) of the per-shard
+ * (#kept, #positive) counts of rows ordered before each positive; every rank then holds the same ap / first_hit / cmc_hits,
+ * bit-identical to grl_cmc_map on the concatenated matrix.  max_seen (device int32) returns the largest per-(query, shard)
+ * positive count over all ranks: the result is valid iff max_seen <= max_pos (the caller re-runs with a larger max_pos).  */
+size_t grl_cmc_map_sharded_workspace_bytes(const grl_handle* h, int nq, int max_pos);
+int grl_cmc_map_sharded(grl_handle* h, const float* dist, long long ld_dist, const int64_t* q_pid, const int64_t* g_pid,
+                        const int64_t* q_cam, const int64_t* g_cam, int nq, int ng_local, int64_t idx_base, int max_rank, int max_pos,
+                        int32_t* cmc_hits, double* ap, int32_t* first_hit, int32_t* max_seen, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* np.argsort(distmat, axis=1)                reid/evaluator/eva_functions.py:139
  * Stable (distance, index) row sort, ng <= 16384.  order int32 [nq][ng].                    */
 int grl_argsort_rows(grl_handle* h, const float* dist, long long ld_dist, int nq, int ng, int32_t* order, void* stream);
@@ -117,11 +131,11 @@ int grl_topk_merge(grl_handle* h, const float* all_d, const int64_t* all_i, int 
  *   4. grl_exact_topk    brute force in the same fixed-order arithmetic for the flagged queries (rare).
  * The result is the exact stable top-k of the fixed-order fp32 distances, independent of chunking and of the number of
  * gallery shards.  g [ng][dim] is this rank's shard, idx_base the global index of its first row; top_d/top_i [nq][k] are
- * overwritten.  grl_dist_topk runs 1-4 for one shard and synchronises the stream once (it reads the flag count).
- * For a sharded gallery the caller interleaves the stages with its collectives (grl_b200/evaluator.py: sharded_retrieve):
- * all-gather + grl_topk_merge of the coarse lists, each rank re-scores the candidates it owns (grl_rescore writes 0 for
- * rows of other shards, so the per-rank results combine by a sum), finalize, and the flagged queries go through
- * grl_exact_topk per shard + grl_topk_merge.
+ * overwritten.  grl_dist_topk runs 1-4 for one shard and synchronises the stream once (it reads the flag count); it is the
+ * single-rank form of grl_sharded_topk (below), which runs the whole sharded protocol incl. its NCCL collectives.
+ * The stage entry points remain for hosts that run their own collectives between them: all-gather + grl_topk_merge of the
+ * coarse lists, each rank re-scores the candidates it owns (grl_rescore writes 0 for rows of other shards, so the per-rank
+ * results combine by a sum), finalize, and the flagged queries go through grl_exact_topk per shard + grl_topk_merge.
  * coarse_d holds -q.g (metric 0) or the SQUARED L2 distance (metric 1); gmax2 [1] = max |g|^2 over the shard (combine
  * shards with a max); dirty int32 [nq] = 1 where a per-chunk candidate buffer overflowed (only the first chunk's distance
  * tile is ever stored, so such a row cannot be rescanned: it is flagged and brute-forced; combine shards with a max; may be
@@ -154,6 +168,49 @@ int grl_exact_topk(grl_handle* h, int metric, const float* q, const float* g, in
 size_t grl_dist_topk_workspace_bytes(int nq, int ng, int dim);
 int grl_dist_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k,
                   int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- gallery-sharded retrieval over NCCL (BASELINE.json configs[4]: top-k merged over 1/2/4/8 GPUs) --------------------
+ * No reference counterpart (the reference evaluates on one device: attevaluator.py:125-163, and drives its GPUs from one
+ * process with nn.DataParallel: mars_train.py:80).  One process per GPU; NCCL is resolved at run time (dlopen of
+ * libnccl.so.2 -- inside a PyTorch process that is the instance torch already loaded), so the library has no link-time
+ * dependency on it.
+ * Communicator: rank 0 calls grl_comm_unique_id, the host distributes the GRL_COMM_ID_BYTES bytes by any means, every rank
+ * calls grl_comm_init (ncclCommInitRank; the handle owns the communicator) -- or hands in its own ncclComm_t with
+ * grl_comm_attach (borrowed; NULL detaches).  grl_comm_info reports (1, 0) without a communicator.                        */
+#define GRL_COMM_ID_BYTES 128
+int grl_comm_unique_id(grl_handle* h, void* id_host, size_t id_bytes);
+int grl_comm_init(grl_handle* h, const void* id_host, size_t id_bytes, int world, int rank);
+int grl_comm_attach(grl_handle* h, void* nccl_comm);
+int grl_comm_destroy(grl_handle* h);
+int grl_comm_info(const grl_handle* h, int* world, int* rank);
+
+/* One search over a gallery whose rows are split contiguously over the W ranks of the handle's communicator (W = 1 without
+ * one): the whole protocol behind ONE call, every collective on the caller's stream.
+ *   q         query rows (device, fp32, [q_rows][dim]).  q_rows == nq: all queries (replicated by the caller);
+ *             otherwise this rank's slice, rows [rank*qs, min(nq, (rank+1)*qs)) with qs = ceil(nq / W) -- the ranks then
+ *             all-gather the slices over NVLink instead of each uploading all nq rows over PCIe
+ *   g_local   this rank's gallery rows [ng_local][dim] (fp32; needed for the exact re-score), idx_base = global index of row 0
+ *   prepared  grl_gallery_prepare'd index of g_local, or NULL (the shard is then converted chunk by chunk in every search)
+ *   top_d / top_i [nq][k]: the exact stable top-k of the fixed-order fp32 distances, identical on every rank and for every W
+ *   max_flagged < 0: synchronous -- the stream is synchronised once to read how many queries failed the completeness proof,
+ *             and exactly those go through the brute-force leg.  >= 0: asynchronous (graph-capturable): the brute-force leg is
+ *             launched for max_flagged row slots gated on the device-side count; queries beyond stay as the coarse search
+ *             left them and the caller checks stats[0] <= max_flagged afterwards
+ *   stats     device int32[8] or NULL: [0] queries flagged (proof failed / buffer overflow), [1] rows with an overflow mark,
+ *             [2] candidates re-scored by this rank, [3] candidates this rank skipped (provably outside the top k)
+ * Stages: S0 query all-gather, S1 fp16 conversion, S2 coarse pass (tcgen05 GEMM + candidate filter + list merges) over the
+ * local shard, S3 all-reduce(max) of {overflow marks, max |g|^2} + all-to-all of the K' lists by query slice + merge +
+ * all-gather of the merged slices, S4 owned re-score, S5 reduce-scatter(sum), S6 finalisation + proof of the own slice,
+ * S7 all-gather of the result keys + flag compaction + unpack, S8 brute force (per shard + all-gather + merge).
+ * grl_search_profile(h, 1) records an event at every stage boundary of the following calls; grl_search_stage_ms returns the
+ * nine stage durations of the last one (synchronises on its last event).                                                 */
+size_t grl_sharded_topk_workspace_bytes(const grl_handle* h, int nq, int ng_local, int dim, int k, int prepared);
+int grl_sharded_topk(grl_handle* h, int metric, const float* q, int q_rows, const float* g_local, const void* prepared, int nq,
+                     int ng_local, int dim, int k, int64_t idx_base, int max_flagged, float* top_d, int64_t* top_i, int32_t* stats,
+                     void* workspace, size_t workspace_bytes, void* stream);
+#define GRL_SEARCH_STAGES 9
+int grl_search_profile(grl_handle* h, int on);
+int grl_search_stage_ms(grl_handle* h, double* ms, int n);
 
 /* k-reciprocal re-ranking: re_ranking(q_g_dist, q_q_dist, g_g_dist, k1, k2, lambda_value)
  *                                            reid/evaluator/rerank.py:37-104 (called at attevaluator.py:151-155)

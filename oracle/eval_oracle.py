@@ -212,3 +212,45 @@ def finalize_topk(qf, coarse_d, cand_i, exact_d, gmax2, k, metric=0):
                 ok = ck - emax - np.float32(1e-6) * abs(ck) > u
             flags[r] = 0 if ok else 1
     return top_d, top_i, flags
+
+
+def rescore_cut(coarse_kth, qq, gmax2, dim, metric=0):
+    """rescore_keys_kernel (grl_b200/csrc/search.cu): candidates ranked >= k by the coarse pass whose coarse distance exceeds
+    this value are NOT re-scored -- each of the first k candidates is then strictly closer in exact arithmetic
+    (|coarse - exact| <= E_max for every pair), so such a row cannot be among the k nearest.  float32 arithmetic as on the device."""
+    ce = np.float32(coarse_error_constant(dim))
+    qq, g2, ck = np.float32(qq), np.float32(gmax2), np.float32(coarse_kth)
+    emax = ce * np.sqrt(qq) * np.sqrt(g2) * np.float32(1.00001)
+    if metric == 1:
+        return ck + np.float32(4.0) * emax + np.float32(2e-5) * (qq + g2) + np.float32(4e-12)
+    return ck + np.float32(2.0) * emax + np.float32(2e-6) * np.abs(ck)
+
+
+def two_stage_topk(qf, gf, k, kprime, metric=0, skip=True):
+    """The whole two-stage search restated with numpy for one shard: coarse K' list -> (optionally skipping) re-score ->
+    finalisation + proof -> brute force for flagged rows.  Returns (top_d, top_i, flags, n_rescored)."""
+    qf = np.ascontiguousarray(qf, np.float32)
+    gf = np.ascontiguousarray(gf, np.float32)
+    c = coarse_distance(qf, gf, metric)
+    exact = exact_distance_fixed(qf, gf, metric)
+    cd, ci = topk_stable(c, kprime)
+    nq, kp = ci.shape
+    if kp < kprime:
+        cd = np.concatenate([cd, np.full((nq, kprime - kp), np.inf, np.float32)], 1)
+        ci = np.concatenate([ci, np.full((nq, kprime - kp), -1, np.int64)], 1)
+    ed = np.where(ci >= 0, np.take_along_axis(exact, np.clip(ci, 0, gf.shape[0] - 1), 1), np.float32(0)).astype(np.float32)
+    qq = _fixed_order_reduce(qf * qf)
+    gmax2 = np.float32(_fixed_order_reduce(gf * gf).max())
+    n_rescored = int((ci >= 0).sum())
+    if skip:
+        for r in range(nq):
+            if k - 1 < kprime and ci[r, k - 1] >= 0:
+                cut = rescore_cut(cd[r, k - 1], qq[r], gmax2, qf.shape[1], metric)
+                drop = (np.arange(kprime) >= k) & (cd[r] > cut) & (ci[r] >= 0)
+                ed[r, drop] = np.inf
+                n_rescored -= int(drop.sum())
+    top_d, top_i, flags = finalize_topk(qf, cd, ci, ed, gmax2, k, metric)
+    for r in np.nonzero(flags)[0]:
+        v, i = topk_stable(exact[r:r + 1], k)
+        top_d[r, :v.shape[1]], top_i[r, :i.shape[1]] = v[0], i[0]
+    return top_d, top_i, flags, n_rescored

@@ -346,3 +346,138 @@ def test_prepared_gallery_gives_identical_results(metric):
             parts.append(ev.retrieve_topk(qd, ev.PreparedGallery(gd[lo:lo + n]), k, idx_base=lo, metric=metric))
         dm, im = ev.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
         assert torch.equal(im, i0) and torch.equal(dm, d0)
+
+
+@pytest.mark.parametrize("k", [100, 200, 512])
+def test_sharded_topk_single_rank_stats_and_large_k(k):
+    """grl_sharded_topk without a communicator (one rank): exact results, and on generic data NO query may fall back to brute
+    force for any supported k -- the per-chunk candidate buffer scales with K' (k = 200 -> K' = 512, k = 512 -> K' = 1024;
+    a fixed 512-entry buffer used to overflow there and sent nearly every query to the brute-force leg)."""
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    nq, ng, dim = 48, 40000, 64
+    q, g = _retrieval_inputs(nq, ng, dim, 300 + k, dup_every=0)
+    qd, gd = torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda()
+    stats = torch.zeros(8, dtype=torch.int32, device="cuda")
+    d, i = ev.sharded_topk(qd, gd, k, 0, stats=stats)
+    v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q, g, 0), k)
+    assert np.array_equal(i.cpu().numpy(), i_ref) and np.array_equal(d.cpu().numpy(), v_ref)
+    flagged, dirty, rescored, skipped = [int(v) for v in stats[:4].cpu()]
+    assert flagged == 0 and dirty == 0, (flagged, dirty)
+    kp = ev.CudaSearchStages.kprime(k)
+    assert rescored + skipped == nq * kp and rescored >= nq * k
+    if k == 100:
+        assert skipped > 0                                   # the skip rule does skip work on generic data
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_sharded_topk_async_mode_matches_sync(metric):
+    """max_flagged >= 0: no host synchronisation inside the call (graph-capturable); the brute-force leg runs for a fixed number
+    of row slots gated on the device-side count.  With enough slots the result equals the synchronous one bit for bit; with
+    none, the flagged rows are reported in stats[0] and everything else is already final."""
+    _, ev = _mods()
+    nq, ng, dim, k = 41, 20011, 128, 100
+    q, g = _retrieval_inputs(nq, ng, dim, 11)                   # duplicated rows: some proofs fail
+    qd, gd = torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda()
+    s0 = torch.zeros(8, dtype=torch.int32, device="cuda")
+    d0, i0 = ev.sharded_topk(qd, gd, k, 0, metric=metric, stats=s0)
+    nflag = int(s0[0])
+    assert nflag > 0
+    s1 = torch.zeros(8, dtype=torch.int32, device="cuda")
+    d1, i1 = ev.sharded_topk(qd, gd, k, 0, metric=metric, max_flagged=nq, stats=s1)
+    assert int(s1[0]) == nflag and torch.equal(i1, i0) and torch.equal(d1, d0)
+    s2 = torch.zeros(8, dtype=torch.int32, device="cuda")
+    d2, i2 = ev.sharded_topk(qd, gd, k, 0, metric=metric, max_flagged=0, stats=s2)
+    assert int(s2[0]) == nflag
+    same = (i2 == i0).all(dim=1)
+    assert int((~same).sum()) <= nflag                          # only flagged rows may still differ
+    # the asynchronous form is capturable in a CUDA graph (the synchronous one reads a count on the host)
+    out = (torch.empty_like(d0), torch.empty_like(i0))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ev.sharded_topk(qd, gd, k, 0, metric=metric, max_flagged=nq, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ev.sharded_topk(qd, gd, k, 0, metric=metric, max_flagged=nq, out=out)
+    out[0].zero_(); out[1].zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out[1], i0) and torch.equal(out[0], d0)
+
+
+def test_evaluate_sharded_single_rank_equals_evaluate(golden_dir):
+    """grl_cmc_map_sharded without a communicator == grl_cmc_map, bit for bit (the split into collect / count / reduce keeps
+    the arithmetic, incl. the summation order of the average precision)."""
+    _, ev = _mods()
+    for seed, nq, extra in ((3, 60, 240), (8, 200, 1500)):
+        qf, gf, qp, gp, qc, gc = synth.make_eval_set(nq, extra, 64, seed=seed, num_ids=25, noise=1.5, missing_query_frac=0.05)
+        d = ev.cosin_dist(torch.from_numpy(qf).cuda(), torch.from_numpy(gf).cuda())
+        d[:, ::7] = d[:, 3:4]                                # ties
+        cmc0, map0 = ev.evaluate(d, qp, gp, qc, gc, 50)
+        cmc1, map1 = ev.evaluate_sharded(d, qp, gp, qc, gc, 0, 50)
+        assert np.array_equal(cmc0, cmc1) and map0 == map1
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from grl_b200 import evaluator as ev
+    res = {}
+    for metric, (nq, ng, dim, k, dup) in enumerate(((1101, 30011, 128, 100, 13), (37, 9001, 72, 30, 0))):
+        q, g = _retrieval_inputs(nq, ng, dim, 500 + metric, dup)
+        lo, n = ev.shard_bounds(ng, world, rank)
+        qlo, qn = ev.query_slice(nq, world, rank)
+        gd = torch.from_numpy(g[lo:lo + n]).cuda()
+        stats = torch.zeros(8, dtype=torch.int32, device="cuda")
+        # this rank contributes only its slice of the queries; the library all-gathers them
+        d, i = ev.sharded_retrieve(torch.from_numpy(q[qlo:qlo + qn]).cuda(), gd, k, lo, metric=metric, nq=nq, stats=stats)
+        # ... the same with replicated queries and a prepared gallery
+        d2, i2 = ev.sharded_retrieve(torch.from_numpy(q).cuda(), ev.PreparedGallery(gd), k, lo, metric=metric)
+        assert torch.equal(d, d2) and torch.equal(i, i2)
+        res["d%d" % metric], res["i%d" % metric], res["s%d" % metric] = d.cpu().numpy(), i.cpu().numpy(), stats.cpu().numpy()
+    # sharded CMC / mAP
+    qf, gf, qp, gp, qc, gc = synth.make_eval_set(300, 2500, 64, seed=9, num_ids=25, noise=1.5, missing_query_frac=0.05)
+    ngt = gf.shape[0]
+    lo, n = ev.shard_bounds(ngt, world, rank)
+    dl = ev.cosin_dist(torch.from_numpy(qf).cuda(), torch.from_numpy(gf[lo:lo + n]).cuda())
+    cmc, mAP = ev.evaluate_sharded(dl, qp, gp[lo:lo + n], qc, gc[lo:lo + n], lo, 50)
+    res["cmc"], res["mAP"] = cmc, np.float64(mAP)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), **res)
+    dist.barrier()
+    ev.destroy_search_comm()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL ranks)")
+def test_sharded_search_and_eval_over_nccl_two_ranks(tmp_path):
+    """The real thing: two processes, two GPUs, NCCL.  grl_sharded_topk (query-slice all-gather, all-to-all of the coarse
+    lists, owned re-scores + reduce-scatter, sliced finalisation, result all-gather, brute-force leg) and grl_cmc_map_sharded
+    give, on both ranks, bit for bit what ONE GPU computes for the whole gallery."""
+    import socket
+    import torch.multiprocessing as mp
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(str(tmp_path / "rank0.npz")), np.load(str(tmp_path / "rank1.npz"))
+    for metric, (nq, ng, dim, k, dup) in enumerate(((1101, 30011, 128, 100, 13), (37, 9001, 72, 30, 0))):
+        q, g = _retrieval_inputs(nq, ng, dim, 500 + metric, dup)
+        d, i = ev.retrieve_topk(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda(), k, metric=metric)     # one GPU, whole gallery
+        for r in (r0, r1):
+            assert np.array_equal(r["i%d" % metric], i.cpu().numpy()) and np.array_equal(r["d%d" % metric], d.cpu().numpy())
+        if nq <= 64:
+            v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q, g, metric), k)
+            assert np.array_equal(r0["i%d" % metric], i_ref) and np.array_equal(r0["d%d" % metric], v_ref)
+        if dup:
+            assert int(r0["s%d" % metric][0]) > 0               # the brute-force leg ran over NCCL too
+    qf, gf, qp, gp, qc, gc = synth.make_eval_set(300, 2500, 64, seed=9, num_ids=25, noise=1.5, missing_query_frac=0.05)
+    cmc, mAP = ev.evaluate(ev.cosin_dist(torch.from_numpy(qf).cuda(), torch.from_numpy(gf).cuda()), qp, gp, qc, gc, 50)
+    for r in (r0, r1):
+        assert np.array_equal(r["cmc"], cmc) and float(r["mAP"]) == float(mAP)

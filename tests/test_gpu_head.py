@@ -407,9 +407,9 @@ def test_graphed_head_step_replays_bit_identically():
     gu, gc = gu.cuda(), gc.cuda()
     fresh = lambda: {k: v.cuda().contiguous() for k, v in synth.make_head_params(0).items()}
     sd_e, sd_g = fresh(), fresh()
-    step = head.GraphedHeadStep(sd_g, B, T)               # construction itself runs the step (warm-up + capture)
-    for k, v in fresh().items():
-        sd_g[k].copy_(v)
+    step = head.GraphedHeadStep(sd_g, B, T)               # construction runs a warm-up step on zero maps + the capture ...
+    for k, v in fresh().items():                          # ... and must leave parameters AND BN buffers exactly as loaded
+        assert torch.equal(sd_g[k], v), k
     step.x.copy_(x); step.d_f_uncorr.copy_(gu); step.d_f_corr.copy_(gc)
     ws = None
     for it in range(3):

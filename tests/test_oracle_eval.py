@@ -60,3 +60,27 @@ def test_topk_merge_is_shard_count_invariant():
         vs, is_ = zip(*[eo.topk_stable(d[:, s * w:(s + 1) * w], 10, idx_base=s * w) for s in range(shards)])
         v, i = eo.merge_topk(list(vs), list(is_), 10)
         assert np.array_equal(v, v_ref) and np.array_equal(i, i_ref)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("dup", [False, True])
+def test_two_stage_search_with_skipped_rescores_is_exact(metric, dup):
+    """The re-score skip rule of the fused search (grl_b200/csrc/search.cu: rescore_keys_kernel), restated in numpy: dropping
+    the candidates whose coarse distance exceeds the coarse k-th by more than 2 E_max never changes the exact top-k -- on
+    random data (where it drops a good part of the K' candidates) and on a gallery of near-duplicates (where the proof
+    fails for many queries and the brute-force leg takes over)."""
+    rng = np.random.default_rng(11 + metric)
+    q = rng.standard_normal((24, 64)).astype(np.float32)
+    g = rng.standard_normal((900, 64)).astype(np.float32)
+    if dup:
+        g[100:500] = g[7] + 1e-4 * rng.standard_normal((400, 64)).astype(np.float32)
+        q[:6] = g[7] + 1e-3 * rng.standard_normal((6, 64)).astype(np.float32)
+    k, kp = 10, 64
+    d_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q, g, metric), k)
+    d, i, flags, n_with = eo.two_stage_topk(q, g, k, kp, metric, skip=True)
+    assert np.array_equal(i, i_ref) and np.array_equal(d, d_ref)
+    d2, i2, flags2, n_without = eo.two_stage_topk(q, g, k, kp, metric, skip=False)
+    assert np.array_equal(i2, i_ref) and np.array_equal(flags, flags2)      # skipping never changes a proof either
+    assert n_with < n_without                                               # ... and it does skip work
+    if dup:
+        assert flags[:6].all()
