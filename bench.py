@@ -11,14 +11,19 @@ value = N*B*K / max-over-ranks device time; at N > 1 the replicas average their 
 
 Keys beyond the base contract:
   roofline      dominant kernel = the split-bf16 tcgen05 GEMM (tensor bound): event-timed algorithmic TFLOP/s vs the measured
-                sustained bf16 peak; `traffic` = DRAM bytes per launch from the committed ncu capture of the same step
-  cpu_baseline  the oracle's transcription of the reference head on the host cores (bounded sample: B=4 clips per step)
+                sustained bf16 peak; `traffic` = DRAM bytes per launch from the newest committed ncu capture of the same step
+  hbm_kernels   the HBM-bound glue kernels of the step: live durations (CUPTI via torch.profiler) x DRAM bytes per launch from the
+                committed ncu capture -> achieved GB/s against the measured copy bandwidth
+  cpu_baseline  the oracle's transcription of the reference head on the host cores at the full B=32 (bounded: 2 steps)
+  gpu_comparator  the reference's own torch ops (cuDNN / cuBLAS fp32, TF32 off) on the SAME B200 in the same run
   e2e           the same metric through the nn.Module API with pinned-host inputs and a D2H read of the outputs every step;
                 e2e.graph_replay = the same loop through head.GraphedHeadStep (one CUDA-graph launch per step)
   inference     eval-mode forward (BASELINE.json configs[3]: chunks of 8 clips x 16 frames, and B=32 x T=8)
   eval          MARS-shape evaluation (configs[2]) through the evaluator API, host features in, CMC/mAP out (+ a CPU sample)
   rerank        the same evaluation with k-reciprocal re-ranking (3 distance matrices + re_ranking + CMC/mAP) (+ a CPU sample)
-  retrieval     10k x 1M exact top-100 (configs[4]), gallery sharded over the ranks; its own `roofline` = the coarse search GEMM
+  retrieval     10k x 1M exact top-100 (configs[4]), gallery sharded over the ranks (grl_sharded_topk: one C call per search,
+                NCCL inside); `roofline` = the coarse search GEMM, `stages_ms`, `checksum` (identical for every N), flagged /
+                brute-forced query counts, a clustered-gallery line and a CPU sample
 """
 from __future__ import annotations
 
@@ -82,24 +87,23 @@ def cpu_head_step_fn(B, T):
     return step
 
 
-def cpu_baseline(budget_s=20.0):
+def cpu_baseline(max_steps=2):
+    """The reference head (oracle transcription, same torch CPU ops) at the FULL benchmark batch on the host cores."""
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    B, T = 4, T_HEAD
+    B, T = B_HEAD, T_HEAD
     step = cpu_head_step_fn(B, T)
     step()                                             # warm-up
     t0 = time.perf_counter()
     n = 0
-    while True:
+    for _ in range(max_steps):
         step()
         n += 1
-        if time.perf_counter() - t0 > budget_s or n >= 8:
-            break
     dt = time.perf_counter() - t0
     return dict(value=B * n / dt, unit="clips/s", cores=torch.get_num_threads(), kind="port",
-                sample="%d fwd+bwd steps of B=%d T=%d (fp32, torch CPU ops, train-mode BN) in %.1f s; the full B=32 batch is "
-                       "%dx this sample" % (n, B, T, dt, B_HEAD // B))
+                sample="%d fwd+bwd steps of the full B=%d T=%d batch (fp32, torch CPU ops, train-mode BN) in %.1f s after one warm-up "
+                       "step" % (n, B, T, dt))
 
 
 def run_reference(args):
@@ -109,23 +113,24 @@ def run_reference(args):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    B, T = 4, T_HEAD
+    B, T = int(os.environ.get("GRL_BENCH_REF_B", B_HEAD)), T_HEAD   # our arm's configuration: B=32, T=8 (the env knob is for the CPU test suite)
     step = cpu_head_step_fn(B, T)
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(1):
         step()
-    steps = max(1, min(args.steps, 6))
+    steps = max(1, min(args.steps, 3))                 # ~4 s per step on 16 host cores: bounded so the run ends within a minute
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
     v = B * steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": 1, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "GCE+TRL head fwd+bwd, MARS shape B=32 T=8 2048x16x8 (CPU arm: bounded sample of B=4 clips per step)"},
+            "config": {"workload": "GCE+TRL head fwd+bwd, MARS shape B=%d (8 ids x 4 clips) T=8, layer4 maps 2048x16x8, train-mode BN "
+                                   "(CPU arm: the same batch; %d timed steps after one warm-up step)" % (B, steps)},
             "cpu_baseline": {"value": v, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "B=4 T=8 fwd+bwd per step, oracle transcription of reid/models basebranch.py:56-68 + "
-                                       "grl_model.py:131-180 with the same torch CPU ops"},
+                             "sample": "full B=%d T=8 fwd+bwd per step, oracle transcription of reid/models basebranch.py:56-68 + "
+                                       "grl_model.py:131-180 with the same torch CPU ops" % B},
             "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -287,11 +292,12 @@ def run_ours(args):
     peaks = measured_peaks()
     achieved = g_fl.value / (g_ms.value * 1e-3) / 1e12 if g_ms.value > 0 else 0.0
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01c_gemm_traffic.json")     # written from the committed ncu capture of this command's step
-    if os.path.exists(tpath):
-        with open(tpath) as f:
+    import glob
+    tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json")))    # newest committed ncu capture of this command's step
+    if tfiles:
+        with open(tfiles[-1]) as f:
             tj = json.load(f)
-        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        traffic, traffic_src = tj["dram_bytes_per_launch"], "%s (%s)" % (os.path.basename(tfiles[-1]), tj["source"])
     roofline = {"bound": "tensor", "kernel": "gemm_bf16x3_kernel (split-bf16 tcgen05/TMEM GEMM, TMA-fed)", "achieved": achieved,
                 "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
                 "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the step's GEMM launches)",
@@ -304,6 +310,80 @@ def run_ours(args):
                         % (g_n.value, PROF_STEPS),
                 "gemm_share_of_step": g_ms.value / p0.elapsed_time(p1),
                 "launches_per_step": g_n.value / PROF_STEPS, "avg_launch_ms": g_ms.value / max(1, g_n.value)}
+
+    # ---- the HBM-bound glue kernels: live durations of two more steps (CUPTI activity records via torch.profiler: kernels launched
+    #      by libgrl_b200.so through ctypes are seen like any other) x DRAM bytes per launch from the newest committed ncu capture
+    hbm_kernels = None
+    if rank == 0:
+        try:
+            kfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_kernel_dram_bytes.json")))
+            with open(kfiles[-1]) as f:
+                kbytes = json.load(f)
+            from torch.profiler import ProfilerActivity, profile
+            lib.grl_set_overlap(h, 0)
+            step(); torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for _ in range(2):
+                    step()
+                torch.cuda.synchronize()
+            lib.grl_set_overlap(h, 3)
+            dur = {}
+            for ev in prof.events():
+                nm = ev.name.replace("void ", "").replace("grl::", "").split("(")[0].split("<")[0]
+                if nm in kbytes["kernels"] and ev.device_time > 0:
+                    d_ = dur.setdefault(nm, [0, 0.0])
+                    d_[0] += 1
+                    d_[1] += ev.device_time
+            rows = []
+            for nm, (n_, us_) in dur.items():
+                kb = kbytes["kernels"][nm]
+                if kb.get("bound") != "hbm":
+                    continue
+                gbs = kb["dram_bytes_per_launch"] * n_ / (us_ * 1e-6) / 1e9
+                rows.append({"kernel": nm, "launches_per_step": n_ / 2, "avg_us": us_ / n_, "dram_bytes_per_launch": kb["dram_bytes_per_launch"],
+                             "achieved_gbs": gbs, "frac": gbs / peaks["hbm"]})
+            rows.sort(key=lambda r_: -r_["avg_us"] * r_["launches_per_step"])
+            hbm_kernels = {"peak_gbs": peaks["hbm"], "peak_source": peaks["source"], "bytes_source": os.path.basename(kfiles[-1]) + " (" + kbytes["source"] + ")",
+                           "note": "achieved = DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, committed capture of the same "
+                                   "step) / live kernel duration of this run (CUPTI, single-stream steps)", "kernels": rows[:12]}
+        except Exception as e:                                       # profiling is evidence, never a reason to lose the bench line
+            hbm_kernels = {"unavailable": repr(e)[:200]}
+            lib.grl_set_overlap(h, 3)
+
+    # ---- GPU comparator: the reference head's own torch ops (the oracle's line-by-line transcription:
+    #      F.conv2d 1x1 / F.linear / F.batch_norm + autograd) on the SAME B200 through cuDNN / cuBLAS, true fp32 (TF32 off)
+    gpu_comparator = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import head_oracle as ho
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            leaf = {k_: (v_.clone().requires_grad_(True) if v_.is_floating_point() and "running" not in k_ else v_.clone()) for k_, v_ in sd.items()}
+            xg = x.clone().requires_grad_(True)
+
+            def eager_step():
+                for v_ in leaf.values():
+                    if v_.requires_grad:
+                        v_.grad = None
+                xg.grad = None
+                out_ = ho.ref_forward(leaf, xg, B, T, True)
+                ((out_["f_uncorr"] * gu).sum() + (out_["f_corr"] * gc).sum()).backward()
+            eager_step()
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(3):
+                eager_step()
+            c1.record()
+            torch.cuda.synchronize()
+            cms = c0.elapsed_time(c1) / 3
+            gpu_comparator = {"value": B / cms * 1e3, "unit": "clips/s", "ms_per_step": cms, "kind": "port",
+                              "what": "the reference head's torch ops (oracle transcription of basebranch.py:56-68 + grl_model.py:131-180) "
+                                      "through torch eager on the same B200: cuDNN / cuBLAS fp32, TF32 off, same inputs, 3 timed steps"}
+            del leaf, xg
+            torch.cuda.empty_cache()
+        except Exception as e:
+            gpu_comparator = {"unavailable": repr(e)[:200]}
 
     # ---- forward-only aggregation in eval mode (BASELINE configs[3]: dense / long-tracklet test mode, chunks of 8 clips of T=16
     #      frames as ATTEvaluator.extract_feature feeds them, attevaluator.py:72-77), inputs resident in HBM
@@ -326,9 +406,14 @@ def run_ours(args):
         i1.record()
         torch.cuda.synchronize()
         ims = i0.elapsed_time(i1) / 10
-        infer["B%d_T%d" % (bi, ti_)] = {"ms_per_forward": ims, "clips_per_s": bi / ims * 1e3, "frames_per_s": bi * ti_ / ims * 1e3}
+        if world > 1:                                  # clips are independent in eval mode: every rank runs its own chunk stream
+            tt = torch.tensor([ims], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ims = float(tt.item())
+        infer["B%d_T%d" % (bi, ti_)] = {"ms_per_forward": ims, "clips_per_s": world * bi / ims * 1e3, "frames_per_s": world * bi * ti_ / ims * 1e3}
         del xi, wsi
-    infer["workload"] = "GCE+TRL head forward, eval-mode BN (running statistics), no activations kept"
+    infer["workload"] = ("GCE+TRL head forward, eval-mode BN (running statistics), no activations kept; clips sharded over %d GPU(s) "
+                         "(no collective: eval-mode clips are independent, attevaluator.py:68-98), whole-job rates, max time over ranks" % world)
 
     # ---- end to end through the nn.Module API: pinned host -> device, head fwd+bwd via autograd, outputs read back
     model = head.ResNet50_GRL_Model(base=torch.nn.Identity()).to(dev)
@@ -482,62 +567,124 @@ def run_ours(args):
         del qf_h, gf_h
         torch.cuda.empty_cache()
 
-    # ---- gallery-sharded retrieval (configs[4]): 10k queries x 1M gallery rows x 2048-d, top-100, gallery split over the ranks,
-    #      one NCCL all-gather of the candidates + merge.  Queries come from pinned host memory, results go back to the host.
+    # ---- gallery-sharded retrieval (configs[4]): 10k queries x 1M gallery rows x 2048-d, top-100, gallery split over the ranks.
+    #      One C call per search (grl_sharded_topk, NCCL inside).  Every rank uploads ITS SLICE of the queries from pinned host
+    #      memory (the library all-gathers the slices over NVLink) and reads the full result back to the host.
     retr = None
     if not args.no_eval:
-        NQ, NG, D, KTOP = 10000, 1000000, 2048, 100
-        lo, n = evaluator.shard_bounds(NG, world, rank)
-        gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-        gf = torch.randn((n, D), generator=gen, device=dev)
-        gf /= gf.norm(dim=1, keepdim=True)
-        qf_host = torch.nn.functional.normalize(torch.randn((NQ, D), generator=torch.Generator().manual_seed(7))).pin_memory()
-        out_d, out_i = torch.empty((NQ, KTOP)).pin_memory(), torch.empty((NQ, KTOP), dtype=torch.int64).pin_memory()
-        gallery = evaluator.PreparedGallery(gf)       # the static gallery's search index (fp16 rows + norms), built once, untimed
-
-        def search():
-            d_, i_ = evaluator.sharded_retrieve(qf_host.to(dev, non_blocking=True), gallery, KTOP, lo)
-            out_d.copy_(d_, non_blocking=True)
-            out_i.copy_(i_, non_blocking=True)
-        search()
-        barrier()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        NS = 2
-        r0.record()
-        for _ in range(NS):
-            search()
-        r1.record()
-        barrier()
-        rms = r0.elapsed_time(r1) / NS
-        if world > 1:
-            t = torch.tensor([rms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            rms = float(t.item())
-        # the dominant kernel of the search, event-bracketed launch by launch in one extra (untimed) search
         import ctypes as C2
-        lib.grl_profile_enable(h, 1)
-        search()
-        torch.cuda.synchronize()
-        c_ms, c_fl, c_n = C2.c_double(), C2.c_double(), C2.c_longlong()
-        _lib.check(h, lib.grl_profile_read(h, C2.byref(c_ms), C2.byref(c_fl), C2.byref(c_n)), "grl_profile_read")
-        lib.grl_profile_enable(h, 0)
+        import numpy as np
+        NQ, NG, D, KTOP, BLOCK = 10000, 1000000, 2048, 100, 125000
+        lo, n = evaluator.shard_bounds(NG, world, rank)
+        qlo, qn = evaluator.query_slice(NQ, world, rank)
+        evaluator.init_search_comm()
+        out_d, out_i = torch.empty((NQ, KTOP)).pin_memory(), torch.empty((NQ, KTOP), dtype=torch.int64).pin_memory()
+        dev_out = (torch.empty((NQ, KTOP), device=dev), torch.empty((NQ, KTOP), dtype=torch.int64, device=dev))
+        stats = torch.zeros(8, dtype=torch.int32, device=dev)
+
+        def make_gallery(clustered):
+            """Rows are generated in fixed blocks of 125,000 keyed by the GLOBAL block index, so the gallery -- and with it the
+            checksum of the result -- is the same for every number of shards."""
+            cent = None
+            if clustered:
+                cent = torch.randn((625, D), generator=torch.Generator(device=dev).manual_seed(99), device=dev)
+            parts = []
+            for blk in range(lo // BLOCK, (lo + n - 1) // BLOCK + 1):
+                gblk = torch.randn((BLOCK, D), generator=torch.Generator(device=dev).manual_seed(1000 + blk), device=dev)
+                if clustered:                          # 625 identities x 1,600 near-duplicates: id = global row % 625
+                    ids = (torch.arange(BLOCK, device=dev) + blk * BLOCK) % 625
+                    gblk = cent[ids] + 0.3 * gblk
+                a_, b_ = max(lo, blk * BLOCK) - blk * BLOCK, min(lo + n, (blk + 1) * BLOCK) - blk * BLOCK
+                parts.append(gblk[a_:b_])
+                del gblk
+            gfull = torch.cat(parts) if len(parts) > 1 else parts[0].contiguous()
+            del parts
+            gfull /= gfull.norm(dim=1, keepdim=True)
+            if clustered:
+                qgen = torch.randn((NQ, D), generator=torch.Generator().manual_seed(8))
+                qh = torch.nn.functional.normalize(cent.cpu()[torch.arange(NQ) % 625] + 0.3 * qgen)
+            else:
+                qh = torch.nn.functional.normalize(torch.randn((NQ, D), generator=torch.Generator().manual_seed(7)))
+            return gfull, qh.pin_memory()
+
+        def run_case(clustered, NS):
+            gf, qf_host = make_gallery(clustered)
+            gallery = evaluator.PreparedGallery(gf)    # the static gallery's search index (fp16 rows + norms), built once, untimed
+            q_slice_host = qf_host[qlo:qlo + qn]
+
+            def search():
+                evaluator.sharded_retrieve(q_slice_host.to(dev, non_blocking=True), gallery, KTOP, lo, nq=NQ, out=dev_out, stats=stats)
+                out_d.copy_(dev_out[0], non_blocking=True)
+                out_i.copy_(dev_out[1], non_blocking=True)
+            for _ in range(2):
+                search()
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(NS):
+                search()
+            r1.record()
+            barrier()
+            rms = r0.elapsed_time(r1) / NS
+            if world > 1:
+                t_ = torch.tensor([rms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+                rms = float(t_.item())
+            st_host = [int(v) for v in stats.cpu()[:4]]
+            # one more (untimed) search with an event at every stage boundary and around every coarse GEMM launch
+            lib.grl_search_profile(h, 1)
+            lib.grl_profile_enable(h, 1)
+            search()
+            torch.cuda.synchronize()
+            stages = evaluator.search_stage_ms(dev)
+            c_ms, c_fl, c_n = C2.c_double(), C2.c_double(), C2.c_longlong()
+            _lib.check(h, lib.grl_profile_read(h, C2.byref(c_ms), C2.byref(c_fl), C2.byref(c_n)), "grl_profile_read")
+            lib.grl_profile_enable(h, 0)
+            lib.grl_search_profile(h, 0)
+            if world > 1:                              # the slowest rank per stage
+                t_ = torch.tensor(list(stages.values()) + [c_ms.value], device=dev, dtype=torch.float64)
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+                vals = [float(v) for v in t_.cpu()]
+                stages = dict(zip(stages.keys(), vals[:-1]))
+                gemm_ms_max = vals[-1]
+            else:
+                gemm_ms_max = c_ms.value
+            stages["coarse_gemm_inside_coarse_pass"] = gemm_ms_max
+            ti_dev, td_dev = dev_out[1], dev_out[0]
+            checksum = {"sum_top_i": int(ti_dev.sum().item()), "xor_top_i": int(np.bitwise_xor.reduce(ti_dev.cpu().numpy().reshape(-1))),
+                        "sum_top_d": float(td_dev.double().sum().item())}
+            del gallery, gf
+            torch.cuda.empty_cache()
+            return rms, st_host, stages, (c_ms.value, c_fl.value, c_n.value), checksum
+
+        rms, st_host, stages, (g_ms_, g_fl_, g_n_), checksum = run_case(False, 5)
         peaks_r = measured_peaks()
         alg_tf = 2.0 * NQ * NG * D / (rms * 1e-3) / 1e12
-        gemm_tf = c_fl.value / (c_ms.value * 1e-3) / 1e12 if c_ms.value > 0 else 0.0
-        retr = {"workload": "10k queries x 1M gallery x 2048-d, exact top-100; gallery sharded over %d GPU(s), its fp16 search index "
-                            "prepared once (untimed); per search: queries from pinned host memory -> per-shard coarse fp16 tensor-core "
-                            "pass -> NCCL all-gather + merge of the coarse lists -> owned fixed-order fp32 re-scores (all-reduce) -> "
-                            "completeness proof -> results to the host" % world,
-                "queries_per_s": NQ / (rms * 1e-3), "ms_per_search": rms, "alg_tflops": alg_tf,
-                "roofline": {"bound": "tensor", "kernel": "coarse_gemm_kernel (fp16, one tcgen05 MMA per k-step, 256x256 tiles)",
+        gemm_tf = g_fl_ / (g_ms_ * 1e-3) / 1e12 if g_ms_ > 0 else 0.0
+        retr = {"workload": "10k queries x 1M gallery x 2048-d (i.i.d. unit vectors), exact top-100; gallery sharded over %d GPU(s), its fp16 "
+                            "search index prepared once (untimed); per search: every rank uploads its query slice from pinned host memory -> "
+                            "grl_sharded_topk (NCCL all-gather of the query slices, per-shard coarse fp16 tensor-core pass, all-to-all of the "
+                            "coarse lists by query slice + merge + all-gather, owned fixed-order fp32 re-scores, reduce-scatter, completeness "
+                            "proof per slice, all-gather of the results) -> results to the host on every rank" % world,
+                "queries_per_s": NQ / (rms * 1e-3), "ms_per_search": rms, "timed_searches": 5, "alg_tflops": alg_tf,
+                "stages_ms": stages, "checksum": checksum,
+                "flagged_queries": st_host[0], "overflowed_rows": st_host[1], "candidates_rescored_rank0": st_host[2],
+                "candidates_skipped_rank0": st_host[3],
+                "roofline": {"bound": "tensor", "kernel": "coarse_gemm2_kernel (fp16, tcgen05.mma.cta_group::2, one MMA per k-step, 256x256 tile "
+                                                          "per CTA pair)",
                              "achieved": gemm_tf, "peak": peaks_r["tflops"], "unit": "TFLOP/s per GPU", "frac": gemm_tf / peaks_r["tflops"],
-                             "launches": int(c_n.value), "gemm_share_of_search": c_ms.value / rms if rms > 0 else None,
+                             "launches": int(g_n_), "gemm_share_of_search": g_ms_ / rms if rms > 0 else None,
                              "whole_search_achieved": alg_tf / world, "whole_search_frac": alg_tf / world / peaks_r["tflops"],
                              "note": "achieved = 2*Nq*nc*D per launch / event-timed launch duration over one search (algorithmic == "
                                      "issued: one MMA per product); whole_search_* divides the algorithmic 2*Nq*Ng*D by the full search "
-                                     "time (conversion, list merges, re-score, proof included)"},
-                "h2d_bytes": NQ * D * 4, "d2h_bytes": NQ * KTOP * 12}
-        del gf, gallery
+                                     "time (uploads, conversion, list merges, collectives, re-score, proof, downloads included)"},
+                "h2d_bytes": qn * D * 4, "d2h_bytes": NQ * KTOP * 12}
+        # the same search on a CLUSTERED gallery (625 identities x 1,600 near-duplicates each, the re-ID case): proofs can fail here
+        rms_c, st_c, stages_c, _, checksum_c = run_case(True, 3)
+        retr["clustered"] = {"workload": "same sizes; gallery rows = normalize(centroid[row %% 625] + 0.3 * noise), queries likewise",
+                             "queries_per_s": NQ / (rms_c * 1e-3), "ms_per_search": rms_c, "timed_searches": 3,
+                             "flagged_queries": st_c[0], "overflowed_rows": st_c[1], "brute_forced_queries": st_c[0],
+                             "stages_ms": stages_c, "checksum": checksum_c}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -554,6 +701,22 @@ def run_ours(args):
                                      "sample": "cosin_dist + evaluate, 200 queries x 9,330 gallery rows x 2048-d in %.2f s (the port vectorises the "
                                                "reference's per-query Python list comprehension, eva_functions.py:172, which alone takes "
                                                "31.9 s for the 1,980 queries: SURVEY.md section 6)" % dt_c}
+        if retr is not None:
+            # the reference's way of ranking (attevaluator.py:44-46 + eva_functions.py:139: -qf @ gf.T, then a FULL argsort of every
+            # row) on a BOUNDED sample: 64 queries x one 125,000-row block of the gallery (1/8 of the columns)
+            import numpy as np
+            qs_ = torch.nn.functional.normalize(torch.randn((64, 2048), generator=torch.Generator().manual_seed(7))).numpy()
+            gs_ = torch.randn((125000, 2048), generator=torch.Generator().manual_seed(1000))
+            gs_ = (gs_ / gs_.norm(dim=1, keepdim=True)).numpy()
+            t0 = time.perf_counter()
+            dm_ = -(qs_ @ gs_.T)
+            idx_ = np.argsort(dm_, axis=1)[:, :100]
+            dt_c = time.perf_counter() - t0
+            retr["cpu_baseline"] = {"value": 64 / dt_c, "unit": "queries/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": "64 queries x 125,000 gallery rows x 2048-d (1/8 of the gallery): -q.g^T (BLAS sgemm, all cores) + "
+                                              "np.argsort of every row, top-100 kept, in %.2f s; the full 1M-row gallery costs >= 8x per query" % dt_c,
+                                    "checksum_top1": int(idx_[:, 0].sum())}
+            del qs_, gs_, dm_
         if rerank_line is not None:
             # the reference's re_ranking (oracle restatement, bit-identical to it) on a BOUNDED sample: 200 queries + 1,000 gallery rows;
             # its dense N x N stages grow with N^2, so the full 11,310-row problem is ~90x this time
@@ -580,6 +743,10 @@ def run_ours(args):
                            "alg_tflop_per_step": ALG_FLOPS_PER_CLIP_FWD_BWD * B / 1e12},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "inference": infer,
                 "alg_tflops": ALG_FLOPS_PER_CLIP_FWD_BWD * B / (ms_per_step * 1e-3) / 1e12}
+        if hbm_kernels is not None:
+            line["hbm_kernels"] = hbm_kernels
+        if gpu_comparator is not None:
+            line["gpu_comparator"] = gpu_comparator
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if eval_line is not None:

@@ -80,7 +80,6 @@ __global__ void f16_rows_kernel(const float* __restrict__ x, long long rows, int
 }
 
 // ------------------------------------------------------------------ streaming top-K' lists (packed keys)
-constexpr int TOPK_SMALL = 32;                  // candidate counts up to this are merged by one warp per row
 
 __global__ void fill_keys_kernel(uint64_t* keys, long long n) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -96,150 +95,158 @@ __global__ void topk_filter_init_kernel(float* thresh, int* cnt, int nq, int cap
 
 __device__ __forceinline__ float thresh_of(uint64_t kth) { return kth == KEY_EMPTY ? CUDART_INF_F : key_value(kth); }
 
-// One column chunk folded into the running lists, fed by the distance GEMM's candidate filter.  One block per query row:
-//   cnt <= TOPK_SMALL : handled by list_update_small_kernel (or nothing to do)
-//   cnt <= cap        : sort the candidates alone, then merge them into the sorted list by rank
-//   cnt  > cap        : the candidate buffer overflowed.  First chunk (its tile IS stored): rescan the tile row; any other
-//                       chunk: the row's list can no longer be trusted -> dirty (finalisation sends it to brute force)
-// and publish the new K'-th best distance as the row's filter threshold.
-__global__ void __launch_bounds__(TOPK_THREADS) list_update_kernel(const float* __restrict__ dist, long long ld, int ncols, int k, int64_t idx_base,
-                                                                   uint64_t* __restrict__ list, float* __restrict__ thresh_out,
-                                                                   const unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt, int cap,
-                                                                   uint32_t* __restrict__ dirty) {
+// Rows whose candidate count exceeds what one warp sorts in registers (possible only when the buffer is larger than
+// LIST_WARP_MAX, i.e. K' >= 512): one block per row sorts the candidates alone in shared memory, then merges them into the
+// sorted list by rank.  Defined after the warp kernel's constants.
+__global__ void __launch_bounds__(TOPK_THREADS) list_update_kernel(int k, int min_cnt, uint64_t* __restrict__ list, float* __restrict__ thresh_out,
+                                                                   const unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt, int cap) {
     __shared__ uint64_t keys[TOPK_BUF];
-    __shared__ int count;
-    __shared__ uint64_t thresh;
     const int row = blockIdx.x;
     const int cnt = cand_cnt[row];
-    if (cnt <= TOPK_SMALL) return;
+    if (cnt <= min_cnt || cnt > cap) return;          // the warp kernel's share / overflow (marked dirty there)
     uint64_t* lrow = list + (long long)row * k;
-    if (cnt <= cap) {
-        // a list key moves down by the number of candidates below it, a candidate lands at its rank plus the number of list
-        // keys below it (keys are unique: the index is part of the key)
-        uint64_t* cs = keys;                        // [npc] sorted candidates (cap <= TOPK_BUF / 2)
-        uint64_t* ls = keys + TOPK_BUF / 2;         // [k]   the running list (k <= TOPK_MAXK <= TOPK_BUF / 2)
-        int npc = 2;
-        while (npc < cnt) npc <<= 1;
-        for (int i = threadIdx.x; i < npc; i += blockDim.x) cs[i] = i < cnt ? cand[(long long)row * cap + i] : KEY_EMPTY;
-        for (int i = threadIdx.x; i < k; i += blockDim.x) ls[i] = lrow[i];
-        block_bitonic_sort(cs, npc);
-        for (int i = threadIdx.x; i < k + cnt; i += blockDim.x) {
-            uint64_t key;
-            int pos;
-            if (i < k) {
-                key = ls[i];
-                int lo = 0, hi = cnt;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid] < key) lo = mid + 1; else hi = mid; }
-                pos = i + lo;
-                if (lo == 0) pos = (pos == k - 1) ? pos : -1 - pos;      // unmoved: nothing to write unless it defines the threshold
-            } else {
-                key = cs[i - k];
-                int lo = 0, hi = k;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (ls[mid] < key) lo = mid + 1; else hi = mid; }
-                pos = (i - k) + lo;
-            }
-            if (pos >= 0 && pos < k) {
-                lrow[pos] = key;
-                if (pos == k - 1) thresh_out[row] = thresh_of(key);
-            }
+    uint64_t* cs = keys;                              // [npc] sorted candidates (cap <= TOPK_BUF / 2)
+    uint64_t* ls = keys + TOPK_BUF / 2;               // [k]   the running list (k <= TOPK_MAXK <= TOPK_BUF / 2)
+    int npc = 2;
+    while (npc < cnt) npc <<= 1;
+    for (int i = threadIdx.x; i < npc; i += blockDim.x) cs[i] = i < cnt ? cand[(long long)row * cap + i] : KEY_EMPTY;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) ls[i] = lrow[i];
+    block_bitonic_sort(cs, npc);
+    for (int i = threadIdx.x; i < k + cnt; i += blockDim.x) {
+        uint64_t key;
+        int pos;
+        if (i < k) {
+            key = ls[i];
+            int lo = 0, hi = cnt;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid] < key) lo = mid + 1; else hi = mid; }
+            pos = i + lo;
+            if (lo == 0) pos = (pos == k - 1) ? pos : -1 - pos;      // unmoved: nothing to write unless it defines the threshold
+        } else {
+            key = cs[i - k];
+            int lo = 0, hi = k;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ls[mid] < key) lo = mid + 1; else hi = mid; }
+            pos = (i - k) + lo;
         }
-        if (threadIdx.x == 0) cand_cnt[row] = 0;
-        return;
-    }
-    if (dist == nullptr) {
-        if (threadIdx.x == 0) { dirty[row] = 1u; thresh_out[row] = -CUDART_INF_F; cand_cnt[row] = 0; }
-        return;
-    }
-    const float* drow = dist + (long long)row * ld;
-    if (lrow[0] == KEY_EMPTY && ncols <= TOPK_BUF) {
-        // bootstrap (empty list, first chunk): one sort of the tile row, sized to the row
-        int npad = 2;
-        while (npad < ncols) npad <<= 1;
-        for (int i = threadIdx.x; i < npad; i += blockDim.x) keys[i] = i < ncols ? make_key(drow[i], (uint32_t)(idx_base + i)) : KEY_EMPTY;
-        block_bitonic_sort(keys, npad);
-        for (int i = threadIdx.x; i < k; i += blockDim.x) lrow[i] = i < npad ? keys[i] : KEY_EMPTY;
-        if (threadIdx.x == 0) {
-            thresh_out[row] = thresh_of((k - 1 < npad) ? keys[k - 1] : KEY_EMPTY);
-            cand_cnt[row] = 0;
-        }
-        return;
-    }
-    for (int i = threadIdx.x; i < TOPK_BUF; i += blockDim.x) keys[i] = i < k ? lrow[i] : KEY_EMPTY;
-    if (threadIdx.x == 0) count = k;
-    __syncthreads();
-    if (threadIdx.x == 0) thresh = keys[k - 1];
-    __syncthreads();
-    const int stage_cap = k <= 256 ? TOPK_WAVE : TOPK_BUF - TOPK_WAVE;
-    for (int c0 = 0; c0 < ncols; c0 += TOPK_WAVE) {
-        const uint64_t th = thresh;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int c = c0 + u * TOPK_THREADS + threadIdx.x;
-            if (c < ncols) {
-                const uint64_t key = make_key(drow[c], (uint32_t)(idx_base + c));
-                if (key < th) keys[atomicAdd(&count, 1)] = key;
-            }
-        }
-        __syncthreads();
-        const bool last = c0 + TOPK_WAVE >= ncols;
-        const int n = count;                         // one snapshot per thread, then a barrier: the flush decision is block-uniform
-        __syncthreads();
-        if (n > stage_cap || (last && n > k)) {
-            int npad = 2;
-            while (npad < n) npad <<= 1;
-            for (int i = n + threadIdx.x; i < npad; i += blockDim.x) keys[i] = KEY_EMPTY;
-            block_bitonic_sort(keys, npad);
-            if (threadIdx.x == 0) { count = k; thresh = keys[k - 1]; }
-            __syncthreads();
+        if (pos >= 0 && pos < k) {
+            lrow[pos] = key;
+            if (pos == k - 1) thresh_out[row] = thresh_of(key);
         }
     }
-    for (int i = threadIdx.x; i < k; i += blockDim.x) lrow[i] = keys[i];
-    if (threadIdx.x == 0) { thresh_out[row] = thresh_of(keys[k - 1]); cand_cnt[row] = 0; }
+    if (threadIdx.x == 0) cand_cnt[row] = 0;
 }
 
-// The common case once the thresholds have tightened: a handful of candidates per row and chunk.  One WARP per row, no block
-// barriers: the candidates are sorted across the lanes with a shuffle network and merged into the (sorted) running list by
-// rank, so the cost is one pass over the list instead of a block-wide sort.
-__global__ void __launch_bounds__(256) list_update_small_kernel(int nq, int k, uint64_t* __restrict__ list, float* __restrict__ thresh_out,
-                                                                const unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt, int cap) {
-    extern __shared__ uint64_t small_keys[];          // [8 warps][k]
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int row = blockIdx.x * 8 + warp;
-    if (row >= nq) return;
-    const int cnt = cand_cnt[row];
-    if (cnt == 0 || cnt > TOPK_SMALL) return;
-    uint64_t* sl = small_keys + (size_t)warp * k;
-    uint64_t* lrow = list + (long long)row * k;
-    for (int t = lane; t < k; t += 32) sl[t] = lrow[t];
-    uint64_t c = lane < cnt ? cand[(long long)row * cap + lane] : KEY_EMPTY;
+// ---- one WARP per row: the candidates are sorted in REGISTERS (NK keys per lane, element e = lane * NK + r; compare-exchange
+// partners at distance < NK live in the same lane, the others one shuffle away), written to shared memory and merged into the
+// sorted running list by rank -- every list key moves down by the number of candidates below it, every candidate lands at its
+// own rank plus the number of list keys below it (keys are unique: the index is part of the key).  No block barrier anywhere.
+template <int NK>
+__device__ __forceinline__ void warp_sort_keys(uint64_t (&v)[NK], int lane) {
+    constexpr int N = 32 * NK;
 #pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {      // bitonic sort across the lanes, ascending
+    for (int size = 2; size <= N; size <<= 1) {
 #pragma unroll
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            const uint64_t o = __shfl_xor_sync(0xffffffffu, c, stride);
-            const bool up = (lane & size) == 0;
-            const bool lower = (lane & stride) == 0;
-            c = ((c < o) == (up == lower)) ? c : o;
+            if (stride < NK) {
+#pragma unroll
+                for (int r = 0; r < NK; ++r) {
+                    if ((r & stride) == 0) {
+                        const int e = lane * NK + r;
+                        const bool up = (size == N) || ((e & size) == 0);
+                        const uint64_t a = v[r], b = v[r | stride];
+                        const bool sw = (a > b) == up;
+                        v[r] = sw ? b : a;
+                        v[r | stride] = sw ? a : b;
+                    }
+                }
+            } else {
+                const int lstride = stride / NK;
+                const bool lower = (lane & lstride) == 0;
+#pragma unroll
+                for (int r = 0; r < NK; ++r) {
+                    const int e = lane * NK + r;
+                    const bool up = (size == N) || ((e & size) == 0);
+                    const uint64_t o = __shfl_xor_sync(0xffffffffu, v[r], lstride);
+                    v[r] = ((v[r] < o) == (up == lower)) ? v[r] : o;
+                }
+            }
         }
     }
+}
+
+// Sorts this row's `cnt` candidates (from the candidate buffer, or -- first chunk -- straight from the stored tile row) and
+// merges them into the list.  sl: the warp's copy of the list [k], cs: the warp's sorted candidates [32 * NK].
+template <int NK>
+__device__ __forceinline__ void warp_merge_row(int cnt, const unsigned long long* __restrict__ crow, const float* __restrict__ drow,
+                                               int64_t idx_base, uint64_t* __restrict__ lrow, int k, uint64_t* sl, uint64_t* cs,
+                                               float* __restrict__ thresh_row, int lane) {
+    uint64_t v[NK];
+#pragma unroll
+    for (int r = 0; r < NK; ++r) {
+        const int e = lane * NK + r;
+        uint64_t key = KEY_EMPTY;
+        if (e < cnt) key = drow ? make_key(drow[e], (uint32_t)(idx_base + e)) : crow[e];
+        v[r] = key;
+    }
+    warp_sort_keys<NK>(v, lane);
+#pragma unroll
+    for (int r = 0; r < NK; ++r) cs[lane * NK + r] = v[r];
     __syncwarp();
-    if (lane < cnt) {                                 // candidates: rank among the list keys
-        int lo = 0, hi = k;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sl[mid] < c) lo = mid + 1; else hi = mid; }
-        const int pos = lo + lane;
-        if (pos < k) {
-            lrow[pos] = c;
-            if (pos == k - 1) thresh_out[row] = key_value(c);
+#pragma unroll
+    for (int r = 0; r < NK; ++r) {                    // candidates: rank among the list keys
+        const int e = lane * NK + r;
+        if (e < cnt) {
+            int lo = 0, hi = k;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sl[mid] < v[r]) lo = mid + 1; else hi = mid; }
+            const int pos = lo + e;
+            if (pos < k) {
+                lrow[pos] = v[r];
+                if (pos == k - 1) *thresh_row = key_value(v[r]);
+            }
         }
     }
     for (int t = lane; t < k; t += 32) {              // list keys: shifted down by the number of candidates below them
         const uint64_t key = sl[t];
-        int below = 0;
-        for (int j = 0; j < cnt; ++j) below += (__shfl_sync(0xffffffffu, c, j) < key) ? 1 : 0;
-        const int pos = t + below;
-        if (below > 0 && pos < k) lrow[pos] = key;
-        if (pos == k - 1) thresh_out[row] = thresh_of(key);
+        int lo = 0, hi = cnt;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid] < key) lo = mid + 1; else hi = mid; }
+        const int pos = t + lo;
+        if (lo > 0 && pos < k) lrow[pos] = key;
+        if (pos == k - 1) *thresh_row = thresh_of(key);
     }
+}
+
+constexpr int LIST_WARPS = 4;          // rows per block of list_update_warp_kernel
+constexpr int LIST_WARP_MAX = 512;     // candidates one warp sorts in registers (16 keys per lane)
+
+// `dist` != NULL: first chunk -- every row takes all `ncols` (<= LIST_WARP_MAX) columns of its stored tile row.  Otherwise rows
+// with 1..LIST_WARP_MAX buffered candidates are merged here; more than `cap`: the buffer overflowed and the row's list can no
+// longer be trusted -> dirty (finalisation sends it to brute force); in between (cap > LIST_WARP_MAX): list_update_kernel.
+__global__ void __launch_bounds__(LIST_WARPS * 32) list_update_warp_kernel(int nq, int k, const float* __restrict__ dist, long long ld, int ncols,
+                                                                           int64_t idx_base, uint64_t* __restrict__ list, float* __restrict__ thresh_out,
+                                                                           const unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt,
+                                                                           int cap, uint32_t* __restrict__ dirty) {
+    extern __shared__ uint64_t warp_keys[];           // [LIST_WARPS][k + LIST_WARP_MAX]
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int row = blockIdx.x * LIST_WARPS + warp;
+    if (row >= nq) return;
+    int cnt = dist ? ncols : cand_cnt[row];
+    if (cnt == 0) return;
+    if (!dist && cnt > cap) {
+        if (lane == 0) { dirty[row] = 1u; thresh_out[row] = -CUDART_INF_F; cand_cnt[row] = 0; }
+        return;
+    }
+    if (cnt > LIST_WARP_MAX) return;                  // list_update_kernel's share
+    uint64_t* sl = warp_keys + (size_t)warp * (k + LIST_WARP_MAX);
+    uint64_t* cs = sl + k;
+    uint64_t* lrow = list + (long long)row * k;
+    for (int t = lane; t < k; t += 32) sl[t] = lrow[t];
+    __syncwarp();
+    const unsigned long long* crow = cand + (long long)row * cap;
+    const float* drow = dist ? dist + (long long)row * ld : nullptr;
+    float* th = thresh_out + row;
+    if (cnt <= 32) warp_merge_row<1>(cnt, crow, drow, idx_base, lrow, k, sl, cs, th, lane);
+    else if (cnt <= 128) warp_merge_row<4>(cnt, crow, drow, idx_base, lrow, k, sl, cs, th, lane);
+    else if (cnt <= 256) warp_merge_row<8>(cnt, crow, drow, idx_base, lrow, k, sl, cs, th, lane);
+    else warp_merge_row<16>(cnt, crow, drow, idx_base, lrow, k, sl, cs, th, lane);
     if (lane == 0) cand_cnt[row] = 0;
 }
 
@@ -541,10 +548,10 @@ using namespace grl;
 static int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 // Column chunks of one coarse pass.  The first chunk has no thresholds yet: its tile IS stored and every row is rescanned, so it
-// is kept small (TOPK_FIRST_CHUNK columns, one 1024-key sort per row).  Afterwards the K'-th best of n_seen columns lets
+// is kept small (TOPK_FIRST_CHUNK columns: what one warp sorts in registers).  Afterwards the K'-th best of n_seen columns lets
 // ~K' * nc / n_seen candidates per row through, so chunks grow with n_seen (at most doubling the columns seen) up to the
 // steady-state size, whose 256 x 256 tiles fill whole waves of the persistent grid; their tiles are never stored.
-constexpr int TOPK_FIRST_CHUNK = 1024;
+constexpr int TOPK_FIRST_CHUNK = LIST_WARP_MAX;
 // candidates per query row and column chunk: a chunk at most doubles the columns seen, so ~K' candidates per row are expected;
 // the buffer holds twice that (an overflow outside the first chunk marks the row dirty -> brute force)
 static int cand_cap(int kprime) { return std::max(512, 2 * kprime); }
@@ -659,7 +666,8 @@ static int coarse_pass(grl_handle* h, cudaStream_t st, int metric, const float* 
     unsigned long long* cand = (unsigned long long*)(w + L.cand);
     const PreparedLayout P = prepared_layout(ng, dim);
     const uint8_t* pb = (const uint8_t*)prepared;
-    GRL_TRY(ensure_dyn_smem(h, (const void*)list_update_small_kernel, 8 * kprime * 8));
+    const size_t list_smem = (size_t)LIST_WARPS * (kprime + LIST_WARP_MAX) * 8;
+    GRL_TRY(ensure_dyn_smem(h, (const void*)list_update_warp_kernel, (int)list_smem));
     topk_filter_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(thresh, cand_cnt, nq, L.cap);
     GRL_LAUNCH_CHECK(h);
     {
@@ -667,6 +675,7 @@ static int coarse_pass(grl_handle* h, cudaStream_t st, int metric, const float* 
         fill_keys_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(list, n);
         GRL_LAUNCH_CHECK(h);
     }
+    int c_merge = 0;                                  // columns seen at the last merge
     for (int c0 = 0; c0 < ng;) {
         const int nc = topk_next_chunk(c0, ng, L.chunk);
         const bool first = c0 == 0;
@@ -689,11 +698,27 @@ static int coarse_pass(grl_handle* h, cudaStream_t st, int metric, const float* 
         // the epilogue keeps only distances that can still enter a row's list (v <= current K'-th best) as candidates
         e.tk_cand = cand; e.tk_cnt = cand_cnt; e.tk_thresh = thresh; e.tk_cap = L.cap; e.tk_idx_base = idx_base + c0;
         GRL_TRY(coarse_gemm_launch(h, st, nq, nc, dim, q16, dim, g16c, dim, e));
-        list_update_small_kernel<<<(nq + 7) / 8, 256, (size_t)8 * kprime * 8, st>>>(nq, kprime, list, thresh, cand, cand_cnt, L.cap);
-        GRL_LAUNCH_CHECK(h);
-        list_update_kernel<<<nq, TOPK_THREADS, 0, st>>>(first ? tile : nullptr, L.first, nc, kprime, idx_base + c0, list, thresh, cand, cand_cnt,
-                                                        L.cap, dirty);
-        GRL_LAUNCH_CHECK(h);
+        // Lazy merging: candidates may stay in the row buffers over several chunks (the filter threshold then dates from the
+        // last merge at c_merge columns, so ~K' * cols / c_merge candidates per row arrive over `cols` further columns).
+        // Merge when the buffers could overflow during the next chunk (1.6x the expectation + 48 of slack), and at the end.
+        const int c_end = c0 + nc;
+        const bool last = c_end >= ng;
+        bool merge = first || last;
+        if (!merge) {
+            const int nc_next = topk_next_chunk(c_end, ng, L.chunk);
+            const double pending = (double)kprime * (double)(c_end - c_merge + nc_next) / (double)c_merge;
+            merge = 1.6 * pending + 48.0 > (double)L.cap;
+        }
+        if (merge) {
+            list_update_warp_kernel<<<(nq + LIST_WARPS - 1) / LIST_WARPS, LIST_WARPS * 32, list_smem, st>>>(
+                nq, kprime, first ? tile : nullptr, L.first, nc, idx_base + c0, list, thresh, cand, cand_cnt, L.cap, dirty);
+            GRL_LAUNCH_CHECK(h);
+            if (L.cap > LIST_WARP_MAX && !first) {    // K' >= 512: a row can hold more candidates than one warp sorts
+                list_update_kernel<<<nq, TOPK_THREADS, 0, st>>>(kprime, LIST_WARP_MAX, list, thresh, cand, cand_cnt, L.cap);
+                GRL_LAUNCH_CHECK(h);
+            }
+            c_merge = c_end;
+        }
         c0 += nc;
     }
     if (prepared) {   // the prepared index carries the shard's largest squared norm

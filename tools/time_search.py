@@ -11,7 +11,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from grl_b200 import _lib, evaluator as ev  # noqa: E402
 
 NQ, D, K = 10000, 2048, 100
-sizes = [int(a) for a in sys.argv[1:]] or [1000000, 500000, 250000, 125000]
+ONCE = "--once" in sys.argv            # one warm-up + one profiled search per size (for ncu launch lists)
+sizes = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [1000000, 500000, 250000, 125000]
 dev = torch.device("cuda", 0)
 lib = _lib.load_library()
 h = _lib.get_handle(dev)
@@ -22,16 +23,16 @@ for ng in sizes:
     g = torch.randn((ng, D), generator=torch.Generator(device=dev).manual_seed(1000), device=dev)
     g /= g.norm(dim=1, keepdim=True)
     pg = ev.PreparedGallery(g)
-    for _ in range(2):
+    for _ in range(1 if ONCE else 2):
         ev.sharded_topk(q, pg, K, 0, out=out, stats=stats)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(5):
+    for _ in range(0 if ONCE else 5):
         ev.sharded_topk(q, pg, K, 0, out=out, stats=stats)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
+    ms = e0.elapsed_time(e1) / 5 if not ONCE else 0.0
     lib.grl_search_profile(h, 1)
     lib.grl_profile_enable(h, 1)
     ev.sharded_topk(q, pg, K, 0, out=out, stats=stats)
