@@ -540,6 +540,34 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src_d, const int64
     for (int t = threadIdx.x; t < k; t += blockDim.x) { dst_d[dst + t] = src_d[(long long)r * k + t]; dst_i[dst + t] = src_i[(long long)r * k + t]; }
 }
 
+// dst[r] = src[rows[r]] (float4 granularity), r < nrows
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ rows, int nrows, int dim, float* __restrict__ dst) {
+    const int nv = dim >> 2;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)nrows * nv) return;
+    const long long r = i / nv;
+    const int j = (int)(i - r * nv);
+    reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src + (long long)rows[r] * dim) + j);
+}
+// result keys of the second chance -> rows[r] of the outputs, for the rows that now carry a proof
+__global__ void scatter_keys_kernel(const uint64_t* __restrict__ out2, const int32_t* __restrict__ rows, int k, float* __restrict__ top_d,
+                                    int64_t* __restrict__ top_i) {
+    const int r = blockIdx.x;
+    const uint64_t* orow = out2 + (long long)r * (k + 1);
+    if (orow[k]) return;                              // still flagged: the brute force writes this row
+    const long long dst = (long long)rows[r] * k;
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const uint64_t key = orow[t];
+        if (key == KEY_EMPTY) { top_d[dst + t] = CUDART_INF_F; top_i[dst + t] = -1; }
+        else { top_d[dst + t] = key_value(key); top_i[dst + t] = (int64_t)key_index(key); }
+    }
+}
+// rows2[i] (an index into `rows`) -> the original row id
+__global__ void remap_rows_kernel(int32_t* __restrict__ rows2, const int32_t* __restrict__ n, const int32_t* __restrict__ rows) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < *n) rows2[i] = rows[rows2[i]];
+}
+
 }  // namespace grl
 
 using namespace grl;
@@ -587,19 +615,22 @@ static float coarse_error_constant(int dim) {   // CE of the header comment
 
 // ---- workspace of one coarse pass (nq query rows against a shard of ng rows)
 struct CoarseLayout {
-    int chunk, first, cap;
+    int chunk, chunk_alloc, first, cap;
     size_t q16, g16, qf, gf, tile, thresh, cnt, cand, total;
 };
 static void coarse_layout(int nq, int ng, int dim, int kprime, bool prepared, CoarseLayout* L) {
     L->chunk = topk_chunk_max(nq, ng, 148);
+    // the conversion buffers of an unprepared shard are sized for the largest chunk any query count can pick, so that a layout
+    // computed for fewer rows (the second chance over the flagged queries) always fits the reservation made for all of them
+    L->chunk_alloc = (int)std::min<long long>(16384, ((long long)ng + 7) / 8 * 8);
     L->first = ng < TOPK_FIRST_CHUNK ? (ng + 7) / 8 * 8 : TOPK_FIRST_CHUNK;
     L->cap = cand_cap(kprime);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
     L->q16 = take((size_t)nq * dim * 2);
-    L->g16 = take(prepared ? 0 : (size_t)L->chunk * dim * 2);
+    L->g16 = take(prepared ? 0 : (size_t)L->chunk_alloc * dim * 2);
     L->qf = take((size_t)nq * 4 * 2);                 // inv_scale | sqnorm
-    L->gf = take(prepared ? 0 : (size_t)L->chunk * 4 * 2);
+    L->gf = take(prepared ? 0 : (size_t)L->chunk_alloc * 4 * 2);
     L->tile = take((size_t)nq * L->first * 4);        // coarse distances of the first chunk only
     L->thresh = take((size_t)nq * 4);
     L->cnt = take((size_t)nq * 4);
@@ -659,7 +690,7 @@ static int coarse_pass(grl_handle* h, cudaStream_t st, int metric, const float* 
     float* q_inv = (float*)(w + L.qf);
     float* q_n2 = q_inv + nq;
     float* g_inv = (float*)(w + L.gf);
-    float* g_n2 = g_inv + L.chunk;
+    float* g_n2 = g_inv + L.chunk_alloc;
     float* tile = (float*)(w + L.tile);
     float* thresh = (float*)(w + L.thresh);
     int* cand_cnt = (int*)(w + L.cnt);
@@ -851,22 +882,20 @@ extern "C" int grl_exact_topk(grl_handle* h, int metric, const float* q, const f
 constexpr int SEARCH_STAGES = 9;       // S0..S8 of the header comment (S9, the unpacking, is timed with S7)
 constexpr int BRUTE_BATCH = 1024;      // flagged rows handled per round of the brute-force leg
 
-struct SearchLayout {
-    int world, qs, nqp, kp, fb;
+// Buffers of one pass of the protocol (stages S1..S7) over `nqp` (padded) query rows with lists of kp keys.
+struct CoreLayout {
+    int nqp, qs, kp;
     CoarseLayout C;
-    size_t Q, coarse, L, meta, R, MA, E, Es, OUT, misc, rows, tile, btd, bti, bad, bai, bmd, bmi, total;
+    size_t coarse, L, meta, R, MA, E, Es, OUT, total;
 };
-static void search_layout(int world, int nq, int ng, int dim, int k, bool prepared, SearchLayout* S) {
-    S->world = world;
+static void core_layout(int world, int nq, int ng, int dim, int k, int kp, bool prepared, CoreLayout* S) {
     S->qs = (nq + world - 1) / world;
     S->nqp = S->qs * world;
-    S->kp = grl_topk_kprime(k);
-    S->fb = std::min(nq, BRUTE_BATCH);
-    coarse_layout(S->nqp, ng, dim, S->kp, prepared, &S->C);
-    const size_t nqp = S->nqp, kp = S->kp, qs = S->qs;
+    S->kp = kp;
+    coarse_layout(S->nqp, ng, dim, kp, prepared, &S->C);
+    const size_t nqp = S->nqp, qs = S->qs;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
-    S->Q = take(world > 1 ? nqp * dim * 4 : 0);                 // all query rows (gathered / copied + zero padding)
     S->coarse = take(S->C.total);
     S->L = take(nqp * kp * 8);                                  // local coarse lists
     S->meta = take((nqp + 1) * 4);                              // overflow marks [nqp] | max |g|^2 bits
@@ -875,8 +904,32 @@ static void search_layout(int world, int nq, int ng, int dim, int k, bool prepar
     S->E = take(nqp * kp * 4);                                  // re-scored distances (owned candidates, 0 elsewhere)
     S->Es = take(world > 1 ? qs * kp * 4 : 0);                  // reduce-scattered: exact distances of the own slice
     S->OUT = take(nqp * (size_t)(k + 1) * 8);                   // result keys + flag word
-    S->misc = take(64);                                         // nflag
-    S->rows = take(nqp * 4);
+    S->total = off;
+}
+
+struct SearchLayout {
+    int world, fb;
+    CoreLayout P1, P2;                                          // first pass (K' of k), second chance (K' = TOPK_MAXK)
+    size_t Q, core1, Q2, core2, misc, rows, rows2, tile, btd, bti, bad, bai, bmd, bmi, total;
+};
+static void search_layout(int world, int nq, int ng, int dim, int k, bool prepared, SearchLayout* S) {
+    S->world = world;
+    S->fb = std::min(nq, BRUTE_BATCH);
+    const int kp = grl_topk_kprime(k);
+    core_layout(world, nq, ng, dim, k, kp, prepared, &S->P1);
+    const bool second = kp < TOPK_MAXK;
+    if (second) core_layout(world, nq, ng, dim, k, TOPK_MAXK, prepared, &S->P2);
+    else memset(&S->P2, 0, sizeof(S->P2));
+    const size_t nqp = S->P1.nqp;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    S->Q = take(world > 1 ? nqp * dim * 4 : 0);                 // all query rows (gathered / copied + zero padding)
+    S->core1 = take(S->P1.total);
+    S->Q2 = take(second ? nqp * dim * 4 : 0);                   // flagged query rows, gathered for the second chance
+    S->core2 = take(S->P2.total);
+    S->misc = take(64);                                         // nflag | nflag2
+    S->rows = take(nqp * 4);                                    // flagged rows after the first pass
+    S->rows2 = take(nqp * 4);                                   // flagged rows after the second chance (original row ids)
     S->tile = take(grl_exact_topk_workspace_bytes(nq, ng, dim));
     S->btd = take((size_t)S->fb * k * 4);
     S->bti = take((size_t)S->fb * k * 8);
@@ -915,68 +968,30 @@ extern "C" int grl_search_stage_ms(grl_handle* h, double* ms, int n) {
     return GRL_OK;
 }
 
-static int search_impl(grl_handle* h, int world, int rank, int metric, const float* q, int q_rows, const float* g, const void* prepared, int nq,
-                       int ng, int dim, int k, int64_t idx_base, int max_flagged, float* top_d, int64_t* top_i, int32_t* stats, void* workspace,
-                       size_t workspace_bytes, void* stream, const char* who) {
-    if (!h || !q || !g || !top_d || !top_i || !workspace) return set_error(h, GRL_EINVAL, "%s: NULL argument", who);
-    if (nq <= 0 || ng <= 0 || dim <= 0 || (dim & 7) || dim > 32768) return set_error(h, GRL_EINVAL, "%s: need nq,ng > 0, dim %% 8 == 0, dim <= 32768 (dim=%d)", who, dim);
-    if (k <= 0 || k > TOPK_MAXK / 2) return set_error(h, GRL_EINVAL, "%s: need 0 < k <= %d", who, TOPK_MAXK / 2);
-    if (metric != GRL_METRIC_NEG_DOT && metric != GRL_METRIC_L2) return set_error(h, GRL_EINVAL, "%s: unknown metric %d", who, metric);
-    if (idx_base < 0 || idx_base + ng > 0xFFFFFFFFll) return set_error(h, GRL_EINVAL, "%s: global index must fit 32 bits", who);
-    SearchLayout S;
-    search_layout(world, nq, ng, dim, k, prepared != nullptr, &S);
-    if (workspace_bytes < S.total) return set_error(h, GRL_ENOMEM, "%s: workspace %zu < %zu bytes", who, workspace_bytes, S.total);
-    if (reinterpret_cast<uintptr_t>(workspace) & 255) return set_error(h, GRL_EINVAL, "%s: workspace must be 256-byte aligned", who);
-    if ((long long)world * S.kp > 16384) return set_error(h, GRL_EINVAL, "%s: world * K' must be <= 16384", who);
+// Stages S1..S7 for `nq` query rows Q (all of them on every rank; rows nq..nqp-1 are zero padding): leaves the result keys of
+// every row + the flag word in OUT [nqp][k+1] on every rank and the (all-reduced) overflow marks in the pass's meta buffer.
+// mark_stages: record the per-stage events of the handle (first pass only).
+static int search_core(grl_handle* h, const NcclApi* api, ncclComm_t comm, int world, int rank, cudaStream_t st, int metric, const float* Q,
+                       int nq, const float* g, const void* prepared, int ng, int dim, int k, int64_t idx_base, uint8_t* w, const CoreLayout& S,
+                       int32_t* stats, bool mark_stages) {
     const int qs = S.qs, nqp = S.nqp, kp = S.kp;
-    const int my_rows = std::max(0, std::min(qs, nq - rank * qs));           // valid rows of this rank's query slice
-    if (q_rows != nq && q_rows != my_rows)
-        return set_error(h, GRL_EINVAL, "%s: q_rows must be nq (%d, all queries) or this rank's slice (%d rows), got %d", who, nq, my_rows, q_rows);
-    const NcclApi* api = nullptr;
-    ncclComm_t comm = nullptr;
-    if (world > 1) {
-        api = nccl_api(h);
-        if (!api) return GRL_ENCCL;
-        comm = (ncclComm_t)h->comm;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    uint8_t* w = (uint8_t*)workspace;
+    const int my_rows = std::max(0, std::min(qs, nq - rank * qs));
     uint8_t* cw = w + S.coarse;
     uint64_t* L = (uint64_t*)(w + S.L);
     uint32_t* dirty = (uint32_t*)(w + S.meta);
     uint32_t* gmax2_bits = dirty + nqp;
     float* E = (float*)(w + S.E);
     uint64_t* OUT = (uint64_t*)(w + S.OUT);
-    int32_t* nflag = (int32_t*)(w + S.misc);
-    int32_t* rows = (int32_t*)(w + S.rows);
     const float ce = coarse_error_constant(dim);
-    if (stats) GRL_CUDA(h, cudaMemsetAsync(stats, 0, 8 * sizeof(int32_t), st));
-    GRL_TRY(stage_mark(h, st, 0));
-
-    // ---- S0: all query rows on every rank
-    const float* Q = q;
-    if (world > 1) {
-        float* Qw = (float*)(w + S.Q);
-        if (q_rows == nq) {
-            GRL_CUDA(h, cudaMemcpyAsync(Qw, q, (size_t)nq * dim * 4, cudaMemcpyDeviceToDevice, st));
-            if (nqp > nq) GRL_CUDA(h, cudaMemsetAsync(Qw + (size_t)nq * dim, 0, (size_t)(nqp - nq) * dim * 4, st));
-        } else {
-            float* mine = Qw + (size_t)rank * qs * dim;
-            if (my_rows > 0) GRL_CUDA(h, cudaMemcpyAsync(mine, q, (size_t)my_rows * dim * 4, cudaMemcpyDeviceToDevice, st));
-            if (my_rows < qs) GRL_CUDA(h, cudaMemsetAsync(mine + (size_t)my_rows * dim, 0, (size_t)(qs - my_rows) * dim * 4, st));
-            GRL_NCCL(h, api, api->AllGather(mine, Qw, (size_t)qs * dim, ncclFloat, comm, st));      // in place
-        }
-        Q = Qw;
-    }
-    GRL_TRY(stage_mark(h, st, 1));
+    auto mark = [&](int i) { return mark_stages ? stage_mark(h, st, i) : GRL_OK; };
 
     // ---- S1 + S2: conversion and coarse pass over the local shard
     GRL_CUDA(h, cudaMemsetAsync(dirty, 0, (size_t)(nqp + 1) * 4, st));
     GRL_TRY(convert_queries(h, st, Q, nqp, dim, cw, S.C));
     const float* q_n2 = (const float*)(cw + S.C.qf) + nqp;
-    GRL_TRY(stage_mark(h, st, 2));
+    GRL_TRY(mark(2));
     GRL_TRY(coarse_pass(h, st, metric, g, prepared, nqp, ng, dim, kp, idx_base, L, gmax2_bits, dirty, cw, S.C));
-    GRL_TRY(stage_mark(h, st, 3));
+    GRL_TRY(mark(3));
 
     // ---- S3: exchange by query slice, merge, all-gather the merged lists
     const uint64_t* MA = L;
@@ -999,7 +1014,7 @@ static int search_impl(grl_handle* h, int world, int rank, int metric, const flo
         GRL_NCCL(h, api, api->AllGather(mine, MAw, cnt, ncclUint64, comm, st));                      // in place
         MA = MAw;
     }
-    GRL_TRY(stage_mark(h, st, 4));
+    GRL_TRY(mark(4));
 
     // ---- S4: re-score the candidates this rank owns
     {
@@ -1008,7 +1023,7 @@ static int search_impl(grl_handle* h, int world, int rank, int metric, const flo
         rescore_keys_kernel<<<nqp, 256, smem, st>>>(metric, Q, q_n2, g, ng, dim, idx_base, MA, kp, k, gmax2_bits, ce, E, stats);
         GRL_LAUNCH_CHECK(h);
     }
-    GRL_TRY(stage_mark(h, st, 5));
+    GRL_TRY(mark(5));
 
     // ---- S5: exact distances of the own slice
     const float* Es = E;
@@ -1017,7 +1032,7 @@ static int search_impl(grl_handle* h, int world, int rank, int metric, const flo
         GRL_NCCL(h, api, api->ReduceScatter(E, Esw, (size_t)qs * kp, ncclFloat, ncclSum, comm, st));
         Es = Esw;
     }
-    GRL_TRY(stage_mark(h, st, 6));
+    GRL_TRY(mark(6));
 
     // ---- S6: finalize the own slice
     {
@@ -1027,10 +1042,67 @@ static int search_impl(grl_handle* h, int world, int rank, int metric, const flo
                                                                 world > 1 ? my_rows : nq, OUT + row0 * (k + 1));
         GRL_LAUNCH_CHECK(h);
     }
-    GRL_TRY(stage_mark(h, st, 7));
+    GRL_TRY(mark(7));
 
-    // ---- S7: results of every slice on every rank, flagged rows
+    // ---- S7 (first half): results of every slice on every rank
     if (world > 1) GRL_NCCL(h, api, api->AllGather(OUT + (size_t)rank * qs * (k + 1), OUT, (size_t)qs * (k + 1), ncclUint64, comm, st));
+    return GRL_OK;
+}
+
+static int search_impl(grl_handle* h, int world, int rank, int metric, const float* q, int q_rows, const float* g, const void* prepared, int nq,
+                       int ng, int dim, int k, int64_t idx_base, int max_flagged, float* top_d, int64_t* top_i, int32_t* stats, void* workspace,
+                       size_t workspace_bytes, void* stream, const char* who) {
+    if (!h || !q || !g || !top_d || !top_i || !workspace) return set_error(h, GRL_EINVAL, "%s: NULL argument", who);
+    if (nq <= 0 || ng <= 0 || dim <= 0 || (dim & 7) || dim > 32768) return set_error(h, GRL_EINVAL, "%s: need nq,ng > 0, dim %% 8 == 0, dim <= 32768 (dim=%d)", who, dim);
+    if (k <= 0 || k > TOPK_MAXK / 2) return set_error(h, GRL_EINVAL, "%s: need 0 < k <= %d", who, TOPK_MAXK / 2);
+    if (metric != GRL_METRIC_NEG_DOT && metric != GRL_METRIC_L2) return set_error(h, GRL_EINVAL, "%s: unknown metric %d", who, metric);
+    if (idx_base < 0 || idx_base + ng > 0xFFFFFFFFll) return set_error(h, GRL_EINVAL, "%s: global index must fit 32 bits", who);
+    SearchLayout S;
+    search_layout(world, nq, ng, dim, k, prepared != nullptr, &S);
+    if (workspace_bytes < S.total) return set_error(h, GRL_ENOMEM, "%s: workspace %zu < %zu bytes", who, workspace_bytes, S.total);
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return set_error(h, GRL_EINVAL, "%s: workspace must be 256-byte aligned", who);
+    if ((long long)world * TOPK_MAXK > 16384) return set_error(h, GRL_EINVAL, "%s: world * K' must be <= 16384", who);
+    const int qs = S.P1.qs, nqp = S.P1.nqp;
+    const int my_rows = std::max(0, std::min(qs, nq - rank * qs));           // valid rows of this rank's query slice
+    if (q_rows != nq && q_rows != my_rows)
+        return set_error(h, GRL_EINVAL, "%s: q_rows must be nq (%d, all queries) or this rank's slice (%d rows), got %d", who, nq, my_rows, q_rows);
+    const NcclApi* api = nullptr;
+    ncclComm_t comm = nullptr;
+    if (world > 1) {
+        api = nccl_api(h);
+        if (!api) return GRL_ENCCL;
+        comm = (ncclComm_t)h->comm;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* w = (uint8_t*)workspace;
+    int32_t* nflag = (int32_t*)(w + S.misc);
+    int32_t* nflag2 = nflag + 1;
+    int32_t* rows = (int32_t*)(w + S.rows);
+    if (stats) GRL_CUDA(h, cudaMemsetAsync(stats, 0, 8 * sizeof(int32_t), st));
+    GRL_TRY(stage_mark(h, st, 0));
+
+    // ---- S0: all query rows on every rank
+    const float* Q = q;
+    if (world > 1) {
+        float* Qw = (float*)(w + S.Q);
+        if (q_rows == nq) {
+            GRL_CUDA(h, cudaMemcpyAsync(Qw, q, (size_t)nq * dim * 4, cudaMemcpyDeviceToDevice, st));
+            if (nqp > nq) GRL_CUDA(h, cudaMemsetAsync(Qw + (size_t)nq * dim, 0, (size_t)(nqp - nq) * dim * 4, st));
+        } else {
+            float* mine = Qw + (size_t)rank * qs * dim;
+            if (my_rows > 0) GRL_CUDA(h, cudaMemcpyAsync(mine, q, (size_t)my_rows * dim * 4, cudaMemcpyDeviceToDevice, st));
+            if (my_rows < qs) GRL_CUDA(h, cudaMemsetAsync(mine + (size_t)my_rows * dim, 0, (size_t)(qs - my_rows) * dim * 4, st));
+            GRL_NCCL(h, api, api->AllGather(mine, Qw, (size_t)qs * dim, ncclFloat, comm, st));      // in place
+        }
+        Q = Qw;
+    }
+    GRL_TRY(stage_mark(h, st, 1));
+
+    // ---- S1..S7: the first pass
+    uint8_t* w1 = w + S.core1;
+    GRL_TRY(search_core(h, api, comm, world, rank, st, metric, Q, nq, g, prepared, ng, dim, k, idx_base, w1, S.P1, stats, true));
+    uint64_t* OUT = (uint64_t*)(w1 + S.P1.OUT);
+    const uint32_t* dirty = (const uint32_t*)(w1 + S.P1.meta);
     compact_flags_kernel<<<1, 1024, 0, st>>>(OUT, nq, k, dirty, rows, nflag, stats);
     GRL_LAUNCH_CHECK(h);
     {
@@ -1040,21 +1112,59 @@ static int search_impl(grl_handle* h, int world, int rank, int metric, const flo
     }
     GRL_TRY(stage_mark(h, st, 8));
 
-    // ---- S8: brute force for the flagged rows (identical row list on every rank)
+    // ---- S8: queries without a proof (identical row list on every rank)
     int todo = max_flagged;
     const int32_t* gate = nflag;
+    const int32_t* brute_rows = rows;
     if (max_flagged < 0) {                            // synchronous mode: one 4-byte read tells the host how many rows there are
         int host_nflag = 0;
         GRL_CUDA(h, cudaMemcpyAsync(&host_nflag, nflag, 4, cudaMemcpyDeviceToHost, st));
         GRL_CUDA(h, cudaStreamSynchronize(st));
         todo = host_nflag;
         gate = nullptr;
+        if (todo > 0 && S.P2.total > 0) {
+            // Second chance: the same protocol over the flagged rows with the longest lists (K' = TOPK_MAXK).  A proof fails
+            // when more than K' - k gallery rows sit within the coarse error of the k-th neighbour (clusters of near-duplicates,
+            // the re-ID case); four times the list usually reaches past the cluster, at a fraction of the brute-force cost.
+            float* Q2 = (float*)(w + S.Q2);
+            CoreLayout P2;
+            core_layout(world, todo, ng, dim, k, TOPK_MAXK, prepared != nullptr, &P2);   // offsets for `todo` rows (<= the reserved size)
+            const long long n4 = (long long)todo * (dim >> 2);
+            gather_rows_kernel<<<(int)((n4 + 255) / 256), 256, 0, st>>>(Q, rows, todo, dim, Q2);
+            GRL_LAUNCH_CHECK(h);
+            if (P2.nqp > todo) GRL_CUDA(h, cudaMemsetAsync(Q2 + (size_t)todo * dim, 0, (size_t)(P2.nqp - todo) * dim * 4, st));
+            uint8_t* w2 = w + S.core2;
+            GRL_TRY(search_core(h, api, comm, world, rank, st, metric, Q2, todo, g, prepared, ng, dim, k, idx_base, w2, P2, nullptr, false));
+            uint64_t* OUT2 = (uint64_t*)(w2 + P2.OUT);
+            int32_t* rows2 = (int32_t*)(w + S.rows2);
+            // rows proven now: scatter their results; rows still flagged: compacted (as ORIGINAL row ids) for the brute force
+            scatter_keys_kernel<<<todo, 128, 0, st>>>(OUT2, rows, k, top_d, top_i);
+            GRL_LAUNCH_CHECK(h);
+            compact_flags_kernel<<<1, 1024, 0, st>>>(OUT2, todo, k, nullptr, rows2, nflag2, nullptr);
+            GRL_LAUNCH_CHECK(h);
+            remap_rows_kernel<<<(todo + 255) / 256, 256, 0, st>>>(rows2, nflag2, rows);
+            GRL_LAUNCH_CHECK(h);
+            int host_nflag2 = 0;
+            GRL_CUDA(h, cudaMemcpyAsync(&host_nflag2, nflag2, 4, cudaMemcpyDeviceToHost, st));
+            GRL_CUDA(h, cudaStreamSynchronize(st));
+            if (stats) {
+                const int32_t v[2] = {todo - host_nflag2, host_nflag2};       // [4] proven by the second chance, [5] brute-forced
+                GRL_CUDA(h, cudaMemcpyAsync(stats + 4, v, 8, cudaMemcpyHostToDevice, st));
+                GRL_CUDA(h, cudaStreamSynchronize(st));                       // `v` lives on this stack frame
+            }
+            todo = host_nflag2;
+            brute_rows = rows2;
+        } else if (stats && todo > 0) {
+            const int32_t v[2] = {0, todo};
+            GRL_CUDA(h, cudaMemcpyAsync(stats + 4, v, 8, cudaMemcpyHostToDevice, st));
+            GRL_CUDA(h, cudaStreamSynchronize(st));
+        }
     } else if (todo > nq) todo = nq;
     float* btd = (float*)(w + S.btd);
     int64_t* bti = (int64_t*)(w + S.bti);
     for (int r0 = 0; r0 < todo; r0 += S.fb) {
         const int nb = std::min(S.fb, todo - r0);
-        GRL_TRY(exact_topk_rows(h, metric, Q, rows, r0, nb, gate, g, ng, dim, k, idx_base, btd, bti, (float*)(w + S.tile), st));
+        GRL_TRY(exact_topk_rows(h, metric, Q, brute_rows, r0, nb, gate, g, ng, dim, k, idx_base, btd, bti, (float*)(w + S.tile), st));
         const float* fd = btd;
         const int64_t* fi = bti;
         if (world > 1) {
@@ -1068,7 +1178,7 @@ static int search_impl(grl_handle* h, int world, int rank, int metric, const flo
             fd = (const float*)(w + S.bmd);
             fi = (const int64_t*)(w + S.bmi);
         }
-        scatter_rows_kernel<<<nb, 128, 0, st>>>(fd, fi, rows, r0, gate, k, top_d, top_i);
+        scatter_rows_kernel<<<nb, 128, 0, st>>>(fd, fi, brute_rows, r0, gate, k, top_d, top_i);
         GRL_LAUNCH_CHECK(h);
     }
     GRL_TRY(stage_mark(h, st, 9));

@@ -197,11 +197,14 @@ int grl_comm_info(const grl_handle* h, int* world, int* rank);
  *             launched for max_flagged row slots gated on the device-side count; queries beyond stay as the coarse search
  *             left them and the caller checks stats[0] <= max_flagged afterwards
  *   stats     device int32[8] or NULL: [0] queries flagged (proof failed / buffer overflow), [1] rows with an overflow mark,
- *             [2] candidates re-scored by this rank, [3] candidates this rank skipped (provably outside the top k)
+ *             [2] candidates re-scored by this rank, [3] candidates this rank skipped (provably outside the top k) -- both of
+ *             the first pass --, [4] flagged queries proven by the second chance, [5] queries that went to brute force
  * Stages: S0 query all-gather, S1 fp16 conversion, S2 coarse pass (tcgen05 GEMM + candidate filter + list merges) over the
  * local shard, S3 all-reduce(max) of {overflow marks, max |g|^2} + all-to-all of the K' lists by query slice + merge +
  * all-gather of the merged slices, S4 owned re-score, S5 reduce-scatter(sum), S6 finalisation + proof of the own slice,
- * S7 all-gather of the result keys + flag compaction + unpack, S8 brute force (per shard + all-gather + merge).
+ * S7 all-gather of the result keys + flag compaction + unpack, S8 the queries without a proof: (synchronous mode) a second
+ * chance -- S1..S7 again over those rows with the longest lists, K' = 1024, which reaches past a cluster of near-duplicates at
+ * a fraction of the brute-force cost -- then brute force (per shard + all-gather + merge) for what is still unproven.
  * grl_search_profile(h, 1) records an event at every stage boundary of the following calls; grl_search_stage_ms returns the
  * nine stage durations of the last one (synchronises on its last event).                                                 */
 size_t grl_sharded_topk_workspace_bytes(const grl_handle* h, int nq, int ng_local, int dim, int k, int prepared);

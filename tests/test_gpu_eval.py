@@ -481,3 +481,37 @@ def test_sharded_search_and_eval_over_nccl_two_ranks(tmp_path):
     cmc, mAP = ev.evaluate(ev.cosin_dist(torch.from_numpy(qf).cuda(), torch.from_numpy(gf).cuda()), qp, gp, qc, gc, 50)
     for r in (r0, r1):
         assert np.array_equal(r["cmc"], cmc) and float(r["mAP"]) == float(mAP)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_second_chance_proves_clustered_queries(metric):
+    """A gallery with clusters of ~600 near-duplicates (the re-ID case): with K' = 256 the completeness proof fails for the
+    queries inside a cluster (more than K' - k rows within the coarse error of the k-th neighbour); the second chance
+    (the same protocol over those queries with K' = 1024) reaches past the cluster and proves them -- no brute force -- and the
+    result stays bit-identical to the oracle.  Exact duplicates beyond K' = 1024 still end in the brute-force leg."""
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    rng = np.random.default_rng(71)
+    nq, ng, dim, k = 40, 12000, 128, 100
+    q, g = _retrieval_inputs(nq, ng, dim, 72, dup_every=0)
+    for c in range(3):                                          # three clusters of 600 rows, spread over the gallery
+        centre = g[17 + c]
+        rows = np.arange(100 + c, 100 + c + 600 * 19, 19)
+        g[rows] = centre + 2e-4 * rng.standard_normal((600, dim)).astype(np.float32)
+        q[c * 5:(c + 1) * 5] = centre + 1e-3 * rng.standard_normal((5, dim)).astype(np.float32)
+    g /= np.linalg.norm(g, axis=1, keepdims=True)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    stats = torch.zeros(8, dtype=torch.int32, device="cuda")
+    d, i = ev.sharded_topk(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda(), k, 0, metric=metric, stats=stats)
+    v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q, g, metric), k)
+    assert np.array_equal(i.cpu().numpy(), i_ref) and np.array_equal(d.cpu().numpy(), v_ref)
+    flagged, _, _, _, second, brute = [int(v) for v in stats[:6].cpu()]
+    assert flagged >= 15 and second >= 15 and brute == flagged - second and brute <= 2, (flagged, second, brute)
+    # 1,540 exact duplicates: more than the longest list holds -> those queries do need the brute force
+    q2, g2 = _retrieval_inputs(nq, 20011, dim, 11)
+    q2[0] = g2[5] + 1e-3 * q2[0]
+    q2[0] /= np.linalg.norm(q2[0])
+    d2, i2 = ev.sharded_topk(torch.from_numpy(q2).cuda(), torch.from_numpy(g2).cuda(), k, 0, metric=metric, stats=stats)
+    v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q2, g2, metric), k)
+    assert np.array_equal(i2.cpu().numpy(), i_ref) and np.array_equal(d2.cpu().numpy(), v_ref)
+    assert int(stats[5]) >= 1
