@@ -241,7 +241,8 @@ int coarse_gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, cons
     const bool aligned = !epi.C || ((reinterpret_cast<uintptr_t>(epi.C) & 15) == 0 && (epi.ldc & 3) == 0);
     const bool aligned_cols = (!epi.col_scale || (reinterpret_cast<uintptr_t>(epi.col_scale) & 15) == 0) &&
                               (!epi.col_norm || (reinterpret_cast<uintptr_t>(epi.col_norm) & 15) == 0);
-    if (M < 1024 || N < 1024 || !aligned || !aligned_cols) return gemm_launch_f16(h, st, M, N, K, A, lda, B, ldb, epi, 0);
+    // (the first chunks of a search are 512 columns wide: still 2 column tiles x M/256 row tiles for the 256 x 256 kernel)
+    if (M < 1024 || N < 512 || !aligned || !aligned_cols) return gemm_launch_f16(h, st, M, N, K, A, lda, B, ldb, epi, 0);
     CoarseGemmParams p;
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = N; p.K = K;

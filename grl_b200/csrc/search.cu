@@ -1204,9 +1204,13 @@ extern "C" int grl_sharded_topk(grl_handle* h, int metric, const float* q, int q
 // ---- one shard, end to end (the single-rank form of the same code path; ignores the handle's communicator)
 extern "C" size_t grl_dist_topk_workspace_bytes(int nq, int ng, int dim) {
     if (nq <= 0 || ng <= 0 || dim <= 0) return 0;
-    SearchLayout S;
-    search_layout(1, nq, ng, dim, TOPK_MAXK / 2, false, &S);     // sized for the largest supported k, unprepared gallery
-    return S.total;
+    size_t need = 0;
+    for (int k : {128, 256, TOPK_MAXK / 2}) {                   // one k per list length K' = 256 / 512 / 1024: sized for any supported k
+        SearchLayout S;
+        search_layout(1, nq, ng, dim, k, false, &S);              // unprepared gallery (the larger layout)
+        need = std::max(need, S.total);
+    }
+    return need;
 }
 extern "C" int grl_dist_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k,
                              int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream) {
