@@ -84,6 +84,10 @@ int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, 
 int gemm_launch_f16(grl_handle* h, cudaStream_t st, int M, int N, int K, const __half* A, long long lda, const __half* B,
                     long long ldb, GemmEpi epi, int bn);
 
+// D[z] = A[z] * B[z]^T with ONE fp16 plane per operand, any majors, batches (single MMA per k-step).
+int gemm_launch_x1(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, const __half* A, long long lda, long long a_bstride,
+                   int a_mn, const __half* B, long long ldb, long long b_bstride, int b_mn, GemmEpi epi);
+
 // The same contraction on 256 x 256 tiles (coarse_gemm.cuh) when the problem is large enough, else gemm_launch_f16.
 int coarse_gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, const __half* A, long long lda, const __half* B,
                        long long ldb, GemmEpi epi);

@@ -2,6 +2,7 @@
 // the fp32 -> bf16 hi/lo split kernels, handle lifecycle and the grl_gemm_bf16x3 C entry point.
 #include "api.h"
 #include "coarse_gemm.cuh"
+#include "gemm_pair.cuh"
 
 #include <utility>
 #include <vector>
@@ -174,6 +175,47 @@ static int launch_variant(grl_handle* h, cudaStream_t st, const GemmParams& p, i
     return GRL_OK;
 }
 
+template <bool A_MN, bool B_MN>
+static int launch_pair_variant(grl_handle* h, cudaStream_t st, const GemmParams& p, int grid) {
+    auto kern = gemm_pair_bf16x3_kernel<A_MN, B_MN>;
+    GRL_TRY(ensure_dyn_smem(h, (const void*)kern, GP_SMEM_BYTES));
+    grl_prof_rec rec;
+    if (h->prof_on) {
+        GRL_CUDA(h, cudaEventCreate(&rec.e0));
+        GRL_CUDA(h, cudaEventCreate(&rec.e1));
+        rec.flops = 2.0 * p.M * (double)p.N * p.K * p.batch;
+        GRL_CUDA(h, cudaEventRecord(rec.e0, st));
+    }
+    kern<<<grid, GEMM_THREADS, GP_SMEM_BYTES, st>>>(p);
+    GRL_LAUNCH_CHECK(h);
+    if (h->prof_on) {
+        GRL_CUDA(h, cudaEventRecord(rec.e1, st));
+        h->prof->recs.push_back(rec);
+    }
+    return GRL_OK;
+}
+
+// The CTA-pair kernel (gemm_pair.cuh): 256 x 256 tiles, each CTA loads 128-row boxes of A and of B.
+static int gemm_launch_pair(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, const Operand& A, const Operand& B, GemmEpi epi) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K; p.batch = batch;
+    p.num_m_tiles = (M + GP_BM - 1) / GP_BM;
+    p.num_n_tiles = (N + GP_BN - 1) / GP_BN;
+    p.group_m = p.num_m_tiles > 16 ? 8 : p.num_m_tiles;
+    p.epi = epi;
+    GRL_TRY(make_tmap(h, &p.ta_hi, A.hi, A.ld, A.bstride, A.mn_major, M, K, batch, 128));
+    GRL_TRY(make_tmap(h, &p.ta_lo, A.lo, A.ld, A.bstride, A.mn_major, M, K, batch, 128));
+    GRL_TRY(make_tmap(h, &p.tb_hi, B.hi, B.ld, B.bstride, B.mn_major, N, K, batch, 128));
+    GRL_TRY(make_tmap(h, &p.tb_lo, B.lo, B.ld, B.bstride, B.mn_major, N, K, batch, 128));
+    const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles * batch;
+    const long long pairs = tiles < (long long)(h->num_sms / 2) ? tiles : (long long)(h->num_sms / 2);
+    const int grid = (int)(2 * pairs);
+    if (A.mn_major) return launch_pair_variant<true, true>(h, st, p, grid);
+    if (B.mn_major) return launch_pair_variant<false, true>(h, st, p, grid);
+    return launch_pair_variant<false, false>(h, st, p, grid);
+}
+
 int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, const Operand& A, const Operand& B,
                 GemmEpi epi, int bn) {
     if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return set_error(h, GRL_EINVAL, "gemm: empty problem %dx%dx%d", M, N, K);
@@ -185,6 +227,8 @@ int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, 
         bn = (N > 128 && t256 >= (long long)h->num_sms * 3 / 4) ? 256 : 128;
     }
     if (bn != 128 && bn != 256) return set_error(h, GRL_EINVAL, "gemm: bn must be 0, 128 or 256");
+    // 256-wide tiles go to the CTA-pair kernel (two SMs per 256 x 256 tile) unless grl_set_overlap bit 4 asks for the single-CTA one
+    if (bn == 256 && M > GEMM_BM && (h->overlap & 16) == 0) return gemm_launch_pair(h, st, M, N, K, batch, A, B, epi);
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = N; p.K = K; p.batch = batch;
@@ -208,6 +252,38 @@ int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, 
     if (A.mn_major) return launch_variant<128, true, true>(h, st, p, grid);
     if (B.mn_major) return launch_variant<128, false, true>(h, st, p, grid);
     return launch_variant<128, false, false>(h, st, p, grid);
+}
+
+// D[z] = A[z] * B[z]^T with ONE fp16 plane per operand and any operand majors (one MMA per k-step): the weight / input
+// gradients of the TRL attention convs f1 / f2, whose single-pass fp16 form stays inside every gradient gate.
+int gemm_launch_x1(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, const __half* A, long long lda, long long a_bstride,
+                   int a_mn, const __half* B, long long ldb, long long b_bstride, int b_mn, GemmEpi epi) {
+    if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return set_error(h, GRL_EINVAL, "gemm_x1: empty problem %dx%dx%d", M, N, K);
+    if (a_mn && !b_mn) return set_error(h, GRL_EINVAL, "gemm_x1: MN-major A with K-major B is not instantiated");
+    if ((a_mn || b_mn) && (K % GEMM_BK)) return set_error(h, GRL_EINVAL, "gemm_x1: MN-major operands need K %% 64 == 0");
+    const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    const long long t256 = (long long)m_tiles * ((N + 255) / 256) * batch;
+    const int bn = (N > 128 && t256 >= (long long)h->num_sms * 3 / 4) ? 256 : 128;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = K; p.batch = batch;
+    p.num_m_tiles = m_tiles;
+    p.num_n_tiles = (N + bn - 1) / bn;
+    p.group_m = p.num_m_tiles > 32 ? 16 : p.num_m_tiles;
+    p.epi = epi;
+    GRL_TRY(make_tmap(h, &p.ta_hi, A, lda, a_bstride, a_mn, M, K, batch, GEMM_BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
+    GRL_TRY(make_tmap(h, &p.tb_hi, B, ldb, b_bstride, b_mn, N, K, batch, bn, CU_TENSOR_MAP_DATA_TYPE_FLOAT16));
+    p.ta_lo = p.ta_hi; p.tb_lo = p.tb_hi;
+    const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles * batch;
+    const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    if (bn == 256) {
+        if (a_mn) return launch_variant<256, true, true, 1>(h, st, p, grid);
+        if (b_mn) return launch_variant<256, false, true, 1>(h, st, p, grid);
+        return launch_variant<256, false, false, 1>(h, st, p, grid);
+    }
+    if (a_mn) return launch_variant<128, true, true, 1>(h, st, p, grid);
+    if (b_mn) return launch_variant<128, false, true, 1>(h, st, p, grid);
+    return launch_variant<128, false, false, 1>(h, st, p, grid);
 }
 
 // D = A * B^T with ONE fp16 plane per operand (K-major both, no batch): the coarse pass of the retrieval search.
@@ -339,7 +415,7 @@ extern "C" void grl_destroy(grl_handle* h) {
 
 extern "C" int grl_set_overlap(grl_handle* h, int on) {
     if (!h) return GRL_EINVAL;
-    h->overlap = on & 15;
+    h->overlap = on & 31;
     return GRL_OK;
 }
 

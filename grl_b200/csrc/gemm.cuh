@@ -42,6 +42,8 @@ struct GemmEpi {
     long long stat_bstride;
     // ---- transforms: v = alpha*acc; v *= row_scale[m]; v += col_bias[n] + grp_bias[m/grp_rows][n]; relu ----
     float alpha;
+    const float* dscale_a;    // device scalars (or NULL) multiplied into alpha: the de-scaling factors of fp16 operands whose
+    const float* dscale_b;    // power-of-two scale was chosen on the device (gemm_launch_x1)
     const float* row_scale;
     long long rs_bstride;
     const float* col_bias;
@@ -90,6 +92,166 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int t
     const int gsize = min(p.group_m, p.num_m_tiles - mg * p.group_m);
     n_tile = rr / gsize;
     m_tile = mg * p.group_m + (rr - n_tile * gsize);
+}
+
+// Per-row state of one epilogue thread for one output tile (thread == output row): loaded BEFORE the accumulator is waited for.
+struct EpiRow {
+    int grow;
+    bool row_ok;
+    float rscale, rnorm, rthresh;
+    const float* gb_row;
+    const float* sub_row;
+    float* c_row;
+};
+// m_tile counts 128-row tiles (the unit of the statistic / `sub` layouts), row_in_tile = TMEM lane of this thread.
+__device__ __forceinline__ EpiRow epi_row_setup(const GemmParams& p, int z, int m_tile, int row_in_tile) {
+    const GemmEpi& e = p.epi;
+    EpiRow r;
+    r.grow = m_tile * GEMM_BM + row_in_tile;
+    r.row_ok = r.grow < p.M;
+    r.rscale = 1.f; r.rnorm = 0.f; r.rthresh = 0.f;
+    if (r.row_ok) {
+        if (e.row_scale) r.rscale = e.row_scale[z * e.rs_bstride + r.grow];
+        if (e.mode != 0) r.rnorm = e.row_norm[r.grow];
+        if (e.tk_cand)      // a row whose list already overflowed is rescanned by the consumer anyway: stop appending
+            r.rthresh = (e.tk_cnt[r.grow] > e.tk_cap) ? -__int_as_float(0x7f800000) : e.tk_thresh[r.grow];
+    }
+    if (e.dscale_a) r.rscale *= __ldg(e.dscale_a);
+    if (e.dscale_b) r.rscale *= __ldg(e.dscale_b);
+    r.gb_row = e.grp_bias ? e.grp_bias + (long long)(r.grow / e.grp_rows) * e.ld_gb : nullptr;
+    r.sub_row = nullptr;
+    if (e.sub) r.sub_row = e.sub + ((long long)m_tile * e.sub_tile_rows + e.sub_row_off[z] + row_in_tile) * e.ld_sub + e.sub_col_off[z];
+    r.c_row = e.C ? e.C + z * e.c_bstride + (long long)r.grow * e.ldc : nullptr;
+    return r;
+}
+
+// Drains one 128 x BN accumulator (TMEM address t_acc: lane quadrant and first column included) through the fused epilogue.
+template <int BN>
+__device__ __forceinline__ void epi_tile(const GemmParams& p, const EpiRow& R, int z, int m_tile, int n0, uint32_t t_acc, int quad, int lane) {
+    const GemmEpi& e = p.epi;
+    const int grow = R.grow;
+    const bool row_ok = R.row_ok;
+    const float rscale = R.rscale, rnorm = R.rnorm, rthresh = R.rthresh;
+    const float* gb_row = R.gb_row;
+    const float* sub_row = R.sub_row;
+    float* c_row = R.c_row;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;                   // warp-uniform
+        float v[32];
+        tmem_ld_32x32(t_acc + uint32_t(c * 32), v);
+        tmem_ld_wait();
+        const bool full_chunk = col0 + 32 <= p.N;
+        if (e.col_scale) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= (full_chunk || col0 + j < p.N) ? __ldg(e.col_scale + col0 + j) : 0.f;
+        }
+        if (e.mode != 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float cn = (col0 + j < p.N) ? e.col_norm[col0 + j] : 0.f;
+                const float sq = fmaxf(rnorm + cn - 2.f * (v[j] * rscale), 1e-12f);
+                v[j] = (e.mode == 1) ? sqrtf(sq) : sq;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= e.alpha * rscale;
+            if (e.col_bias) {
+                const float* cb = e.col_bias + z * e.cb_bstride + col0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (full_chunk || col0 + j < p.N) v[j] += __ldg(cb + j);
+            }
+            if (gb_row && row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (full_chunk || col0 + j < p.N) v[j] += __ldg(gb_row + col0 + j);
+            }
+            if (e.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+        }
+        // ---- top-k candidates (small problems only; the large-problem kernel is coarse_gemm.cuh) ----
+        if (e.tk_cand && row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (v[j] <= rthresh && (full_chunk || col0 + j < p.N)) {
+                    const int pos = atomicAdd(e.tk_cnt + grow, 1);
+                    if (pos < e.tk_cap)
+                        e.tk_cand[(long long)grow * e.tk_cap + pos] = make_key(v[j], (uint32_t)(e.tk_idx_base + col0 + j));
+                }
+            }
+        }
+        // ---- stores of v ----
+        if (row_ok) {
+            if (c_row) {
+                float* dst = c_row + col0;
+                if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                    float4* d4 = reinterpret_cast<float4*>(dst);
+                    if (e.accumulate) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 o = d4[j];
+                            v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.N) {
+                            if (e.accumulate) v[j] += dst[j];
+                            dst[j] = v[j];
+                        }
+                }
+            }
+            if (e.Phi && full_chunk) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(v[2 * j], h0, l0); split_bf16(v[2 * j + 1], h1, l1);
+                    hi[j] = pack_bf16(h0, h1); lo[j] = pack_bf16(l0, l1);
+                }
+                const long long off = z * e.p_bstride + (long long)grow * e.ldp + col0;
+                uint4* ph = reinterpret_cast<uint4*>(e.Phi + off);
+                uint4* pl = reinterpret_cast<uint4*>(e.Plo + off);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    ph[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                    pl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
+            }
+        }
+        // ---- column reductions (BN statistics / squared-difference pooling) ----
+        if (e.col_sum || e.col_sq) {
+            if (sub_row) {
+                const float4* s4 = reinterpret_cast<const float4*>(sub_row + col0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 s = __ldg(s4 + j);
+                    v[4 * j] -= s.x; v[4 * j + 1] -= s.y; v[4 * j + 2] -= s.z; v[4 * j + 3] -= s.w;
+                }
+            }
+            if (!row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            const long long sidx = z * e.stat_bstride + (long long)(m_tile * 4 + quad) * p.N + col0 + lane;
+            if (e.col_sq) {
+                float w[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w[j] = v[j] * v[j];
+                const float s2 = warp_transpose_sum32(w);
+                if (col0 + lane < p.N) e.col_sq[sidx] = s2;
+            }
+            if (e.col_sum) {
+                const float s1 = warp_transpose_sum32(v);
+                if (col0 + lane < p.N) e.col_sum[sidx] = s1;
+            }
+        }
+    }
 }
 
 // PLANES = 3: split-bf16 (hi and lo planes, three MMAs per k-step).  PLANES = 1: one fp16 plane per operand, one MMA per
@@ -245,139 +407,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
             const int n0 = n_tile * BN;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int grow = m0 + row_in_tile;
-            const bool row_ok = grow < p.M;
-            float rscale = 1.f, rnorm = 0.f, rthresh = 0.f;
-            if (row_ok) {
-                if (e.row_scale) rscale = e.row_scale[z * e.rs_bstride + grow];
-                if (e.mode != 0) rnorm = e.row_norm[grow];
-                if (e.tk_cand)      // a row whose list already overflowed is rescanned by the consumer anyway: stop appending
-                    rthresh = (e.tk_cnt[grow] > e.tk_cap) ? -__int_as_float(0x7f800000) : e.tk_thresh[grow];
-            }
-            const float* gb_row = e.grp_bias ? e.grp_bias + (long long)(grow / e.grp_rows) * e.ld_gb : nullptr;
-            const float* sub_row = nullptr;
-            if (e.sub) sub_row = e.sub + ((long long)m_tile * e.sub_tile_rows + e.sub_row_off[z] + row_in_tile) * e.ld_sub + e.sub_col_off[z];
-            float* c_row = e.C ? e.C + z * e.c_bstride + (long long)grow * e.ldc : nullptr;
-
+            const EpiRow R = epi_row_setup(p, z, m_tile, row_in_tile);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int col0 = n0 + c * 32;
-                if (col0 >= p.N) break;                   // warp-uniform
-                float v[32];
-                tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN + c * 32), v);
-                tmem_ld_wait();
-                const bool full_chunk = col0 + 32 <= p.N;
-                if (e.col_scale) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] *= (full_chunk || col0 + j < p.N) ? __ldg(e.col_scale + col0 + j) : 0.f;
-                }
-                if (e.mode != 0) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float cn = (col0 + j < p.N) ? e.col_norm[col0 + j] : 0.f;
-                        const float sq = fmaxf(rnorm + cn - 2.f * (v[j] * rscale), 1e-12f);
-                        v[j] = (e.mode == 1) ? sqrtf(sq) : sq;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] *= e.alpha * rscale;
-                    if (e.col_bias) {
-                        const float* cb = e.col_bias + z * e.cb_bstride + col0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (full_chunk || col0 + j < p.N) v[j] += __ldg(cb + j);
-                    }
-                    if (gb_row && row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (full_chunk || col0 + j < p.N) v[j] += __ldg(gb_row + col0 + j);
-                    }
-                    if (e.relu) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                    }
-                }
-                // ---- top-k candidates (small problems only; the large-problem kernel is coarse_gemm.cuh) ----
-                if (e.tk_cand && row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (v[j] <= rthresh && (full_chunk || col0 + j < p.N)) {
-                            const int pos = atomicAdd(e.tk_cnt + grow, 1);
-                            if (pos < e.tk_cap)
-                                e.tk_cand[(long long)grow * e.tk_cap + pos] = make_key(v[j], (uint32_t)(e.tk_idx_base + col0 + j));
-                        }
-                    }
-                }
-                // ---- stores of v ----
-                if (row_ok) {
-                    if (c_row) {
-                        float* dst = c_row + col0;
-                        if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                            float4* d4 = reinterpret_cast<float4*>(dst);
-                            if (e.accumulate) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    float4 o = d4[j];
-                                    v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
-                                }
-                            }
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < p.N) {
-                                    if (e.accumulate) v[j] += dst[j];
-                                    dst[j] = v[j];
-                                }
-                        }
-                    }
-                    if (e.Phi && full_chunk) {
-                        uint32_t hi[16], lo[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(v[2 * j], h0, l0); split_bf16(v[2 * j + 1], h1, l1);
-                            hi[j] = pack_bf16(h0, h1); lo[j] = pack_bf16(l0, l1);
-                        }
-                        const long long off = z * e.p_bstride + (long long)grow * e.ldp + col0;
-                        uint4* ph = reinterpret_cast<uint4*>(e.Phi + off);
-                        uint4* pl = reinterpret_cast<uint4*>(e.Plo + off);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            ph[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            pl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-                        }
-                    }
-                }
-                // ---- column reductions (BN statistics / squared-difference pooling) ----
-                if (e.col_sum || e.col_sq) {
-                    if (sub_row) {
-                        const float4* s4 = reinterpret_cast<const float4*>(sub_row + col0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 s = __ldg(s4 + j);
-                            v[4 * j] -= s.x; v[4 * j + 1] -= s.y; v[4 * j + 2] -= s.z; v[4 * j + 3] -= s.w;
-                        }
-                    }
-                    if (!row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                    }
-                    const long long sidx = z * e.stat_bstride + (long long)(m_tile * 4 + quad) * p.N + col0 + lane;
-                    if (e.col_sq) {
-                        float w[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) w[j] = v[j] * v[j];
-                        const float s2 = warp_transpose_sum32(w);
-                        if (col0 + lane < p.N) e.col_sq[sidx] = s2;
-                    }
-                    if (e.col_sum) {
-                        const float s1 = warp_transpose_sum32(v);
-                        if (col0 + lane < p.N) e.col_sum[sidx] = s1;
-                    }
-                }
-            }
+            epi_tile<BN>(p, R, z, m_tile, n0, tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN), quad, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);

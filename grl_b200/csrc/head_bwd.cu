@@ -12,6 +12,8 @@
 // Buffers live in the caller's workspace (head_common.cuh); `dxu` is used as dZ[T][2][R][C].
 #include <stddef.h>
 
+#include <algorithm>
+
 #include "head_common.cuh"
 
 namespace grl {
@@ -137,6 +139,53 @@ __global__ void dgc_kernel(const float* __restrict__ dfc, const float* __restric
     const float a0 = se_a[(((size_t)t * 2 + 0) * B + b) * HC + c];
     const float a1 = se_a[(((size_t)(T - 1 - t) * 2 + 1) * B + b) * HC + c];
     dgc[idx] = dfc[idx] * (2.f + a0 + a1);
+}
+
+// ------------------------------------------------------------------ bf16 hi/lo planes -> ONE fp16 plane with a device-chosen scale
+// The weight / input gradients of the attention convs f1 / f2 run as single-pass fp16 GEMMs (gemm_launch_x1): emulated on the
+// fp64 plan, rounding the operands of exactly those contractions to fp16 leaves every head output and gradient where the
+// three-MMA split-bf16 form puts them (tools/exp_f1f2_precision.py; the FORWARD f1 / f2 must stay split-bf16).  fp16 needs a
+// scale: each tensor gets one power of two that maps its largest magnitude into [2^14, 2^15) -- 28 binades of full precision
+// below the maximum -- found by a pass over the hi plane; the reciprocal is handed to the GEMM epilogue as a device scalar.
+__global__ void __launch_bounds__(256) absmax_bf16_kernel(const __nv_bfloat16* __restrict__ x, size_t n8, unsigned int* __restrict__ out_bits) {
+    unsigned int m = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + i);
+        const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { m = max(m, w[j] & 0x7FFFu); m = max(m, (w[j] >> 16) & 0x7FFFu); }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane_id() == 0 && m) atomicMax(out_bits, m << 16);       // bf16 bits << 16 == the float's bits: orders like the magnitude
+}
+// scal[0] = amax bits (in), scal[1] = 1 / scale (out).  NaN / inf maxima fall back to scale 1.
+__global__ void __launch_bounds__(256) planes_to_f16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, size_t n8,
+                                                            float* __restrict__ scal, __half* __restrict__ out) {
+    const unsigned int mb = __float_as_uint(scal[0]);
+    int e = (int)((mb >> 23) & 0xff) - 127;
+    if (mb == 0 || ((mb >> 23) & 0xff) == 0xff) e = 14;
+    const float s = ldexpf(1.f, 14 - e);
+    if (blockIdx.x == 0 && threadIdx.x == 0) scal[1] = ldexpf(1.f, e - 14);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        float v[8];
+        load8_planes(hi + i * 8, lo + i * 8, v);
+        __half2 h2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h2[j] = __floats2half2_rn(v[2 * j] * s, v[2 * j + 1] * s);
+        *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(h2);
+    }
+}
+// planes [n] -> fp16 plane `out` + scal[slot] (amax, 1/scale); everything on `st`
+static int planes_to_f16(grl_handle* h, cudaStream_t st, const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t n, float* scal, __half* out) {
+    const size_t n8 = n / 8;
+    const int blocks = (int)std::min<size_t>((n8 + 255) / 256, (size_t)h->num_sms * 16);
+    GRL_CUDA(h, cudaMemsetAsync(scal, 0, 8, st));
+    absmax_bf16_kernel<<<blocks, 256, 0, st>>>(hi, n8, reinterpret_cast<unsigned int*>(scal));
+    GRL_LAUNCH_CHECK(h);
+    planes_to_f16_kernel<<<blocks, 256, 0, st>>>(hi, lo, n8, scal, out);
+    GRL_LAUNCH_CHECK(h);
+    return GRL_OK;
 }
 
 // ------------------------------------------------------------------ f1/f2 squared-difference backward for one step
@@ -752,17 +801,24 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
                                                                WS_F32(w, dbf1_part) + (size_t)i * 2 * B * HC,
                                                                WS_F32(w, dbf2_part) + (size_t)i * 2 * B * HC);
         GRL_LAUNCH_CHECK(h);
+        // single-pass fp16 operands of this step: dF1 and the memory slot M_i (one scale per tensor, chosen on the device)
+        float* scal = WS_F32(w, f16_scal);
+        __half* df1_16 = reinterpret_cast<__half*>(WS_BF(w, df1_16));
+        __half* mem_16 = reinterpret_cast<__half*>(WS_BF(w, mem_16));
+        GRL_TRY(planes_to_f16(h, sd, WS_BF(w, df1_hi), WS_BF(w, df1_lo), (size_t)2 * R * HC, scal + 0, df1_16));
+        GRL_TRY(planes_to_f16(h, sd, mem_hi, mem_lo, (size_t)2 * R * HC, scal + 2, mem_16));
         {   // f1 wgrad: gw_f1[z] (+)= dF1^T M
             GemmEpi e = epi_default();
             e.C = WS_F32(w, gw_f1); e.ldc = HC; e.c_bstride = (long long)HC * HC; e.accumulate = acc;
-            Operand a{WS_BF(w, df1_hi), WS_BF(w, df1_lo), HC, (long long)R * HC, 1}, b{mem_hi, mem_lo, HC, (long long)R * HC, 1};
-            GRL_TRY(gemm_launch(h, sd, HC, HC, R, 2, a, b, e, 0));
+            e.dscale_a = scal + 1; e.dscale_b = scal + 3;
+            GRL_TRY(gemm_launch_x1(h, sd, HC, HC, R, 2, df1_16, HC, (long long)R * HC, 1, mem_16, HC, (long long)R * HC, 1, e));
         }
         {   // f1 dgrad: dmem[i] = dF1 Wf1   (the other half of dM for step i-1 is dZ of step i)
             GemmEpi e = epi_default();
             e.C = dmem_all + (size_t)i * slotM; e.ldc = HC; e.c_bstride = (long long)R * HC;
-            Operand a{WS_BF(w, df1_hi), WS_BF(w, df1_lo), HC, (long long)R * HC, 0}, b{WS_BF(w, wf1_hi), WS_BF(w, wf1_lo), HC, (long long)HC * HC, 1};
-            GRL_TRY(gemm_launch(h, sd, R, HC, HC, 2, a, b, e, 0));
+            e.dscale_a = scal + 1; e.dscale_b = scal + 5;
+            GRL_TRY(gemm_launch_x1(h, sd, R, HC, HC, 2, df1_16, HC, (long long)R * HC, 0, reinterpret_cast<const __half*>(WS_BF(w, wf1_16)), HC,
+                                   (long long)HC * HC, 1, e));
         }
         if (two) GRL_TRY(ev_record(h, EV_DMEM(i), sd));
         return GRL_OK;
@@ -771,6 +827,9 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
     // ---------------- BPTT over the memory updates ----------------
     bcast_rows_kernel<<<dim3(HC / 64, B, 2), 256, 0, st>>>(d_f_uncorr, 1.f / HS, R, dmem_all + (size_t)T * slotM);   // d f_uncorr = mean_s(M_fwd) + mean_s(M_bwd)
     GRL_LAUNCH_CHECK(h);
+    // the f1 weights as one fp16 plane (input gradient of f1: dM += dF1 Wf1), converted once per backward on the side stream
+    GRL_TRY(planes_to_f16(h, sd, WS_BF(w, wf1_hi), WS_BF(w, wf1_lo), (size_t)2 * HC * HC, WS_F32(w, f16_scal) + 4,
+                          reinterpret_cast<__half*>(WS_BF(w, wf1_16))));
     GRL_TRY(f1_path(T - 1));
     for (int i = T - 1; i >= 0; --i) {
         const int first = (i == T - 1) ? 1 : 0;
@@ -859,18 +918,26 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
         small_colsum_kernel<<<dim3(HC / 256, 1), 256, 0, sd>>>(WS_F32(w, dbf2_part) + (size_t)d * B * HC, 0, (long long)2 * B * HC, HC, T, B,
                                                                g->f2_b[d], 0, HC);
         GRL_LAUNCH_CHECK(h);
-        {   // f2 wgrad over all frames: d Wf2[d] = dF2[:, d]^T Xc     (K = P)
+        {   // f2 wgrad over all frames: d Wf2[d] = dF2[:, d]^T Xc     (K = P); single-pass fp16 operands (converted below, d == 0)
+            if (d == 0) {
+                float* scal = WS_F32(w, f16_scal);
+                GRL_TRY(planes_to_f16(h, sd, WS_BF(w, df2_hi), WS_BF(w, df2_lo), (size_t)P * 2 * HC, scal + 6, reinterpret_cast<__half*>(WS_BF(w, df2_16))));
+                GRL_TRY(planes_to_f16(h, sd, WS_BF(w, xc_hi), WS_BF(w, xc_lo), (size_t)P * HC, scal + 8, reinterpret_cast<__half*>(WS_BF(w, xc_16))));
+                GRL_TRY(planes_to_f16(h, sd, WS_BF(w, wf2_hi), WS_BF(w, wf2_lo), (size_t)2 * HC * HC, scal + 10, reinterpret_cast<__half*>(WS_BF(w, wf2_16))));
+            }
             GemmEpi e = epi_default();
             e.C = g->f2_w[d]; e.ldc = HC;
-            Operand a{WS_BF(w, df2_hi) + (size_t)d * HC, WS_BF(w, df2_lo) + (size_t)d * HC, 2 * HC, 0, 1}, b{WS_BF(w, xc_hi), WS_BF(w, xc_lo), HC, 0, 1};
-            GRL_TRY(gemm_launch(h, sd, HC, HC, P, 1, a, b, e, 0));
+            e.dscale_a = WS_F32(w, f16_scal) + 7; e.dscale_b = WS_F32(w, f16_scal) + 9;
+            GRL_TRY(gemm_launch_x1(h, sd, HC, HC, P, 1, reinterpret_cast<const __half*>(WS_BF(w, df2_16)) + (size_t)d * HC, 2 * HC, 0, 1,
+                                   reinterpret_cast<const __half*>(WS_BF(w, xc_16)), HC, 0, 1, e));
         }
     }
     {   // f2 dgrad, both directions in one contraction (K = 4096): dxc = dF2cat Wf2cat
         GemmEpi e = epi_default();
         e.C = WS_F32(w, dxc); e.ldc = HC;
-        Operand a{WS_BF(w, df2_hi), WS_BF(w, df2_lo), 2 * HC, 0, 0}, b{WS_BF(w, wf2_hi), WS_BF(w, wf2_lo), HC, 0, 1};
-        GRL_TRY(gemm_launch(h, sd, P, HC, 2 * HC, 1, a, b, e, 0));
+        e.dscale_a = WS_F32(w, f16_scal) + 7; e.dscale_b = WS_F32(w, f16_scal) + 11;
+        GRL_TRY(gemm_launch_x1(h, sd, P, HC, 2 * HC, 1, reinterpret_cast<const __half*>(WS_BF(w, df2_16)), 2 * HC, 0, 0,
+                               reinterpret_cast<const __half*>(WS_BF(w, wf2_16)), HC, 0, 1, e));
     }
     if (two) GRL_TRY(stream_wait(h, sd, st, 1));
     return GRL_OK;

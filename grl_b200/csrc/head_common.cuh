@@ -65,7 +65,10 @@ constexpr float BN_MOM = 0.1f;
     X(dm, 4, BW * P) X(dy3, 4, BW * P) X(dy2_hi, 2, BW * P * HMID) X(dy2_lo, 2, BW * P * HMID)     \
     X(g2, 4, BW * 16 * HMID * HG) X(dz1, 4, BW * P * HG) X(dy1_hi, 2, BW * P * HG) X(dy1_lo, 2, BW * P * HG) \
     X(dbias1_part, 4, BW * N * HG) X(dbias1, 4, BW * B * HG) X(du, 4, BW * B * HG) X(dg, 4, BW * B * HC) \
-    X(gsmall, 4, BW * 8192)
+    X(gsmall, 4, BW * 8192)                                                                        \
+    /* --- single-plane fp16 operands of the f1 / f2 gradient GEMMs (one MMA per k-step) + their device-side scales --- */ \
+    X(df1_16, 2, BW * 2 * R * HC) X(mem_16, 2, BW * 2 * R * HC) X(df2_16, 2, BW * P * 2 * HC) X(xc_16, 2, BW * P * HC) \
+    X(wf1_16, 2, BW * 2 * HC * HC) X(wf2_16, 2, BW * 2 * HC * HC) X(f16_scal, 4, BW * 64)
 
 struct HeadWs {
     int B, T, N, P, R, save, SL, SLM, SLZ;

@@ -245,6 +245,20 @@ def plan_gce_backward(p, ctx, dXu, dXc, dm_extra=None):
     return dX, G
 
 
+# The six contractions of the f1 / f2 attention convs (forward, input gradient, weight gradient) go through this hook so that
+# tools/exp_f1f2_precision.py can emulate reduced-precision tensor-core variants of exactly those GEMMs ("Numerics").
+MM_F12 = [torch.matmul]
+
+
+def _mm12(a, b, role="fwd"):
+    """role: "fwd" (F = X W^T), "dgrad" (dX = dF W), "wgrad" (dW = dF^T X); a hook may take (a, b) or (a, b, role)."""
+    f = MM_F12[0]
+    try:
+        return f(a, b, role)
+    except TypeError:
+        return f(a, b)
+
+
 def _rows(b, t, tau):
     """Row indices (in [P]) of frame tau of every clip, ordered (b, s)."""
     base = (torch.arange(b)[:, None] * t + tau) * S + torch.arange(S)[None, :]
@@ -261,7 +275,7 @@ def plan_trl_forward(p, Xu, Xc, b, t, training, update=True):
     F2 = []
     for d, (direction, atte) in enumerate(DIRS):
         Wf2 = p[TP + direction + "_f2.0.weight"].view(C, C)
-        F2.append(torch.relu(Xc @ Wf2.t() + p[TP + direction + "_f2.0.bias"]))   # F2: not recurrent
+        F2.append(torch.relu(_mm12(Xc, Wf2.t()) + p[TP + direction + "_f2.0.bias"]))   # F2: not recurrent
     for d, (direction, atte) in enumerate(DIRS):
         mp = TP + "uncorr_memo_" + direction
         Wf1 = p[TP + direction + "_f1.0.weight"].view(C, C)
@@ -275,7 +289,7 @@ def plan_trl_forward(p, Xu, Xc, b, t, training, update=True):
         for i in range(t):
             tau = i if d == 0 else t - 1 - i
             r = _rows(b, t, tau)
-            F1 = torch.relu(M @ Wf1.t() + bf1)                       # K10
+            F1 = torch.relu(_mm12(M, Wf1.t()) + bf1)                       # K10
             E = F1 - F2[d][r]
             q = (E * E).view(b, S, C).mean(1)                        # K11
             h = torch.relu(q @ L1.t())                               # K12
@@ -352,13 +366,13 @@ def plan_trl_backward(p, ctx, d_f_uncorr, d_f_corr):
             dE = (2.0 / S) * dq[:, None, :].expand(b, S, C).reshape(b * S, C) * st["E"]
             dF1 = dE * (st["F1"] > 0)
             dF2[r] = -dE * (F2[d][r] > 0)
-            acc["Wf1"] = acc["Wf1"] + dF1.t() @ st["M"]
+            acc["Wf1"] = acc["Wf1"] + _mm12(dF1.t(), st["M"], "wgrad")
             acc["bf1"] = acc["bf1"] + dF1.sum(0)
-            dM = dZ + dF1 @ Wf1
+            dM = dZ + _mm12(dF1, Wf1, "dgrad")
         dXu += (dM / t).view(b, 1, S, C).expand(b, t, S, C).reshape(P, C)
-        G[TP + direction + "_f2.0.weight"] = (dF2.t() @ Xc).view(C, C, 1, 1)
+        G[TP + direction + "_f2.0.weight"] = _mm12(dF2.t(), Xc, "wgrad").view(C, C, 1, 1)
         G[TP + direction + "_f2.0.bias"] = dF2.sum(0)
-        dXc += dF2 @ Wf2
+        dXc += _mm12(dF2, Wf2, "dgrad")
         G[TP + direction + "_f1.0.weight"] = acc["Wf1"].view(C, C, 1, 1)
         G[TP + direction + "_f1.0.bias"] = acc["bf1"]
         G[TP + "channel_atte_" + atte + "_corr.0.weight"] = acc["L1"]
