@@ -88,8 +88,10 @@ __global__ void __launch_bounds__(256) bcast_rows_kernel(const float* __restrict
 struct SePtrsB { const float* l1[2]; const float* l2[2]; };
 __global__ void __launch_bounds__(256) se_bwd_kernel(const float* __restrict__ dfc, const float* __restrict__ gc, const float* __restrict__ se_a,
                                                      const float* __restrict__ se_h, SePtrsB sp, int B, int T, float* __restrict__ se_ds,
-                                                     float* __restrict__ se_dh, float* __restrict__ se_dq) {
+                                                     float* __restrict__ se_dh, float* __restrict__ se_dq, const float* __restrict__ se_q,
+                                                     unsigned int* __restrict__ df_bound_bits) {
     __shared__ float ds[HC];
+    __shared__ float wmax[8];
     __shared__ float part[2][HSE];
     __shared__ float dh[HSE];
     const int b = blockIdx.x, d = blockIdx.y, i = blockIdx.z;
@@ -120,12 +122,25 @@ __global__ void __launch_bounds__(256) se_bwd_kernel(const float* __restrict__ d
         se_dh[slot * HSE + threadIdx.x] = v;
     }
     __syncthreads();
+    float bound = 0.f;
     for (int c = threadIdx.x; c < HC; c += 256) {
         const float* w = sp.l1[d] + c;
         float acc = 0.f;
 #pragma unroll 8
         for (int j = 0; j < HSE; ++j) acc += dh[j] * __ldg(w + (size_t)j * HC);
         se_dq[slot * HC + c] = acc;
+        // |dF1|, |dF2| = (2/S) |dq| |E| <= 2 |dq| sqrt(q / S)  (sum_s E^2 = S q): an upper bound of every entry trl_bwd_f1_kernel
+        // writes, from which it picks the power-of-two scale of its fp16 outputs -- no pass over the outputs themselves
+        bound = fmaxf(bound, 2.02f * fabsf(acc) * sqrtf(fmaxf(se_q[slot * HC + c], 0.f) * (1.f / HS)));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, off));
+    if (lane_id() == 0) wmax[threadIdx.x >> 5] = bound;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = 0.f;
+        for (int i = 0; i < 8; ++i) m = fmaxf(m, wmax[i]);
+        if (m == m && m > 0.f) atomicMax(df_bound_bits, __float_as_uint(m));      // non-negative floats order like their bits
     }
 }
 
@@ -191,14 +206,20 @@ static int planes_to_f16(grl_handle* h, cudaStream_t st, const __nv_bfloat16* hi
 // ------------------------------------------------------------------ f1/f2 squared-difference backward for one step
 // grid (C/64, B, 2).  E = F1 - F2[tau];  dE = (2/S) dq E;  dF1 = dE [F1>0];  dF2[tau] = -dE [F2>0]
 __global__ void __launch_bounds__(256) trl_bwd_f1_kernel(const float* __restrict__ f1, const float* __restrict__ f2, const float* __restrict__ dq,
-                                                         int B, int T, int R, int tau0, int tau1, __nv_bfloat16* __restrict__ df1_hi,
-                                                         __nv_bfloat16* __restrict__ df1_lo, __nv_bfloat16* __restrict__ df2_hi,
-                                                         __nv_bfloat16* __restrict__ df2_lo, float* __restrict__ dbf1_part,
+                                                         int B, int T, int R, int tau0, int tau1, float* __restrict__ scal,
+                                                         __half* __restrict__ df1_16, __half* __restrict__ df2_16, float* __restrict__ dbf1_part,
                                                          float* __restrict__ dbf2_part) {
     __shared__ float red[32 * 65];
     const int z = blockIdx.z, b = blockIdx.y, c0 = blockIdx.x * 64;
     const int tau = z ? tau1 : tau0;
     const Tile t;
+    // the outputs are ONE fp16 plane each (single-pass gradient GEMMs): power-of-two scale from se_bwd_kernel's bound on |dF|,
+    // scal[0] = bound bits (in), scal[1] = 1 / scale (out, the same value from every launch of one backward)
+    const unsigned int mb = __float_as_uint(scal[0]);
+    int ex = (int)((mb >> 23) & 0xff) - 127;
+    if (mb == 0 || ((mb >> 23) & 0xff) == 0xff) ex = 14;
+    const float sc = ldexpf(1.f, 14 - ex);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) scal[1] = ldexpf(1.f, ex - 14);
     float q[8], s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     load8(dq + ((size_t)z * B + b) * HC + c0 + t.cg * 8, q);
 #pragma unroll
@@ -218,8 +239,8 @@ __global__ void __launch_bounds__(256) trl_bwd_f1_kernel(const float* __restrict
             g2[i] = f[i] > 0.f ? -de : 0.f;
             s1[i] += g1[i]; s2[i] += g2[i];
         }
-        store8_planes(df1_hi + off1, df1_lo + off1, g1);
-        store8_planes(df2_hi + off2, df2_lo + off2, g2);
+        store8_f16(df1_16 + off1, g1, sc);
+        store8_f16(df2_16 + off2, g2, sc);
     }
     tile_colsum(s1, red, dbf1_part + ((size_t)z * B + b) * HC + c0, t);
     tile_colsum(s2, red, dbf2_part + ((size_t)z * B + b) * HC + c0, t);
@@ -775,8 +796,10 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
     // ---------------- squeeze-excite backward for every step (independent of the recurrence) ----------------
     {
         SePtrsB sp; sp.l1[0] = p->se1_w[0]; sp.l1[1] = p->se1_w[1]; sp.l2[0] = p->se2_w[0]; sp.l2[1] = p->se2_w[1];
+        GRL_CUDA(h, cudaMemsetAsync(WS_F32(w, f16_scal), 0, 8, st));      // [0] bound of |dF1|, |dF2| (bits), [1] 1 / their scale
         se_bwd_kernel<<<dim3(B, 2, T), 256, 0, st>>>(d_f_corr, WS_F32(w, gc), WS_F32(w, se_a), WS_F32(w, se_h), sp, B, T, WS_F32(w, se_ds),
-                                                     WS_F32(w, se_dh), WS_F32(w, se_dq));
+                                                     WS_F32(w, se_dh), WS_F32(w, se_dq), WS_F32(w, se_q),
+                                                     reinterpret_cast<unsigned int*>(WS_F32(w, f16_scal)));
         GRL_LAUNCH_CHECK(h);
         dgc_kernel<<<(unsigned)(((size_t)N * HC + 255) / 256), 256, 0, st>>>(d_f_corr, WS_F32(w, se_a), B, T, WS_F32(w, dgc));
         GRL_LAUNCH_CHECK(h);
@@ -794,23 +817,21 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
     auto f1_path = [&](int i) -> int {
         const int acc = (i == T - 1) ? 0 : 1;
         const int tau0 = i, tau1 = T - 1 - i;
-        const __nv_bfloat16 *mem_hi = WS_BF(w, mem_hi) + (size_t)i * slotM, *mem_lo = WS_BF(w, mem_lo) + (size_t)i * slotM;
+        // dF1 / dF2[tau] come out as ONE fp16 plane each (scale from se_bwd_kernel's bound); the memory slot M_i was written as an
+        // fp16 plane by the forward: the single-pass operands of this step's gradient GEMMs
+        float* scal = WS_F32(w, f16_scal);
+        __half* df1_16 = reinterpret_cast<__half*>(WS_BF(w, df1_16));
+        const __half* mem_16 = reinterpret_cast<const __half*>(WS_BF(w, mem_16)) + (size_t)i * slotM;
         trl_bwd_f1_kernel<<<dim3(HC / 64, B, 2), 256, 0, sd>>>(WS_F32(w, f1) + (size_t)i * slotM, WS_F32(w, f2),
-                                                               WS_F32(w, se_dq) + (size_t)i * 2 * B * HC, B, T, R, tau0, tau1, WS_BF(w, df1_hi),
-                                                               WS_BF(w, df1_lo), WS_BF(w, df2_hi), WS_BF(w, df2_lo),
+                                                               WS_F32(w, se_dq) + (size_t)i * 2 * B * HC, B, T, R, tau0, tau1, scal, df1_16,
+                                                               reinterpret_cast<__half*>(WS_BF(w, df2_16)),
                                                                WS_F32(w, dbf1_part) + (size_t)i * 2 * B * HC,
                                                                WS_F32(w, dbf2_part) + (size_t)i * 2 * B * HC);
         GRL_LAUNCH_CHECK(h);
-        // single-pass fp16 operands of this step: dF1 and the memory slot M_i (one scale per tensor, chosen on the device)
-        float* scal = WS_F32(w, f16_scal);
-        __half* df1_16 = reinterpret_cast<__half*>(WS_BF(w, df1_16));
-        __half* mem_16 = reinterpret_cast<__half*>(WS_BF(w, mem_16));
-        GRL_TRY(planes_to_f16(h, sd, WS_BF(w, df1_hi), WS_BF(w, df1_lo), (size_t)2 * R * HC, scal + 0, df1_16));
-        GRL_TRY(planes_to_f16(h, sd, mem_hi, mem_lo, (size_t)2 * R * HC, scal + 2, mem_16));
         {   // f1 wgrad: gw_f1[z] (+)= dF1^T M
             GemmEpi e = epi_default();
             e.C = WS_F32(w, gw_f1); e.ldc = HC; e.c_bstride = (long long)HC * HC; e.accumulate = acc;
-            e.dscale_a = scal + 1; e.dscale_b = scal + 3;
+            e.dscale_a = scal + 1;                       // the memory planes are unscaled fp16
             GRL_TRY(gemm_launch_x1(h, sd, HC, HC, R, 2, df1_16, HC, (long long)R * HC, 1, mem_16, HC, (long long)R * HC, 1, e));
         }
         {   // f1 dgrad: dmem[i] = dF1 Wf1   (the other half of dM for step i-1 is dZ of step i)
@@ -921,13 +942,12 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
         {   // f2 wgrad over all frames: d Wf2[d] = dF2[:, d]^T Xc     (K = P); single-pass fp16 operands (converted below, d == 0)
             if (d == 0) {
                 float* scal = WS_F32(w, f16_scal);
-                GRL_TRY(planes_to_f16(h, sd, WS_BF(w, df2_hi), WS_BF(w, df2_lo), (size_t)P * 2 * HC, scal + 6, reinterpret_cast<__half*>(WS_BF(w, df2_16))));
                 GRL_TRY(planes_to_f16(h, sd, WS_BF(w, xc_hi), WS_BF(w, xc_lo), (size_t)P * HC, scal + 8, reinterpret_cast<__half*>(WS_BF(w, xc_16))));
                 GRL_TRY(planes_to_f16(h, sd, WS_BF(w, wf2_hi), WS_BF(w, wf2_lo), (size_t)2 * HC * HC, scal + 10, reinterpret_cast<__half*>(WS_BF(w, wf2_16))));
             }
             GemmEpi e = epi_default();
             e.C = g->f2_w[d]; e.ldc = HC;
-            e.dscale_a = WS_F32(w, f16_scal) + 7; e.dscale_b = WS_F32(w, f16_scal) + 9;
+            e.dscale_a = WS_F32(w, f16_scal) + 1; e.dscale_b = WS_F32(w, f16_scal) + 9;
             GRL_TRY(gemm_launch_x1(h, sd, HC, HC, P, 1, reinterpret_cast<const __half*>(WS_BF(w, df2_16)) + (size_t)d * HC, 2 * HC, 0, 1,
                                    reinterpret_cast<const __half*>(WS_BF(w, xc_16)), HC, 0, 1, e));
         }
@@ -935,7 +955,7 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
     {   // f2 dgrad, both directions in one contraction (K = 4096): dxc = dF2cat Wf2cat
         GemmEpi e = epi_default();
         e.C = WS_F32(w, dxc); e.ldc = HC;
-        e.dscale_a = WS_F32(w, f16_scal) + 7; e.dscale_b = WS_F32(w, f16_scal) + 11;
+        e.dscale_a = WS_F32(w, f16_scal) + 1; e.dscale_b = WS_F32(w, f16_scal) + 11;
         GRL_TRY(gemm_launch_x1(h, sd, P, HC, 2 * HC, 1, reinterpret_cast<const __half*>(WS_BF(w, df2_16)), 2 * HC, 0, 0,
                                reinterpret_cast<const __half*>(WS_BF(w, wf2_16)), HC, 0, 1, e));
     }

@@ -54,8 +54,7 @@ constexpr float BN_MOM = 0.1f;
     X(dmem, 4, BW * (T + 1) * 2 * R * HC) X(dh3_hi, 2, BW * T * 2 * R * HC) X(dh3_lo, 2, BW * T * 2 * R * HC) \
     X(dh2p, 4, BW * 2 * R * HB) X(dh2_hi, 2, BW * T * 2 * R * HB) X(dh2_lo, 2, BW * T * 2 * R * HB) \
     X(dh1p, 4, BW * 2 * R * HB) X(dh1_hi, 2, BW * T * 2 * R * HB) X(dh1_lo, 2, BW * T * 2 * R * HB) \
-    X(dzc, 4, BW * 2 * R * HC) X(df1_hi, 2, BW * 2 * R * HC) X(df1_lo, 2, BW * 2 * R * HC)         \
-    X(df2_hi, 2, BW * P * 2 * HC) X(df2_lo, 2, BW * P * 2 * HC)                                    \
+    X(dzc, 4, BW * 2 * R * HC)                                                                      \
     X(dxu, 4, BW * 2 * P * HC) X(dxc, 4, BW * P * HC) X(dgc, 4, BW * N * HC)                       \
     X(kcoef, 4, BW * 2 * 3 * HC) X(se_ds, 4, BW * T * 2 * B * HC) X(se_dh, 4, BW * T * 2 * B * HSE) X(se_dq, 4, BW * T * 2 * B * HC) \
     X(dbf1_part, 4, BW * T * 2 * B * HC) X(dbf2_part, 4, BW * T * 2 * B * HC)                      \
@@ -67,7 +66,7 @@ constexpr float BN_MOM = 0.1f;
     X(dbias1_part, 4, BW * N * HG) X(dbias1, 4, BW * B * HG) X(du, 4, BW * B * HG) X(dg, 4, BW * B * HC) \
     X(gsmall, 4, BW * 8192)                                                                        \
     /* --- single-plane fp16 operands of the f1 / f2 gradient GEMMs (one MMA per k-step) + their device-side scales --- */ \
-    X(df1_16, 2, BW * 2 * R * HC) X(mem_16, 2, BW * 2 * R * HC) X(df2_16, 2, BW * P * 2 * HC) X(xc_16, 2, BW * P * HC) \
+    X(df1_16, 2, BW * 2 * R * HC) X(mem_16, 2, BW * SLM * 2 * R * HC) X(df2_16, 2, BW * P * 2 * HC) X(xc_16, 2, BW * P * HC) \
     X(wf1_16, 2, BW * 2 * HC * HC) X(wf2_16, 2, BW * 2 * HC * HC) X(f16_scal, 4, BW * 64)
 
 struct HeadWs {
@@ -167,6 +166,15 @@ __device__ __forceinline__ void tile_colsum(const float* acc, float* red, float*
         for (int r = 0; r < 32; ++r) s += red[r * 65 + threadIdx.x];
         out[threadIdx.x] = s;
     }
+}
+
+// one fp16 plane (single-pass operands of the f1 / f2 gradient GEMMs); saturating, so a diverged activation cannot become inf
+__device__ __forceinline__ void store8_f16(__half* p, const float* v, float scale = 1.f) {
+    __half2 h2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        h2[j] = __floats2half2_rn(fminf(fmaxf(v[2 * j] * scale, -65504.f), 65504.f), fminf(fmaxf(v[2 * j + 1] * scale, -65504.f), 65504.f));
+    *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(h2);
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }

@@ -325,7 +325,8 @@ __global__ void __launch_bounds__(256) gap_planes_kernel(const __nv_bfloat16* __
 // ------------------------------------------------------------------ K8: M0 = mean_t Xu, Z0 = M0 + Xu[tau0(d)]   grid (C/64, B)
 __global__ void __launch_bounds__(256) trl_init_kernel(const __nv_bfloat16* __restrict__ uh, const __nv_bfloat16* __restrict__ ul, int T, int R,
                                                        __nv_bfloat16* __restrict__ mem_hi, __nv_bfloat16* __restrict__ mem_lo,
-                                                       __nv_bfloat16* __restrict__ z_hi, __nv_bfloat16* __restrict__ z_lo) {
+                                                       __nv_bfloat16* __restrict__ z_hi, __nv_bfloat16* __restrict__ z_lo,
+                                                       __half* __restrict__ mem16) {
     const int b = blockIdx.y, c0 = blockIdx.x * 64;
     const Tile t;
     float acc[4][8], first[4][8], last[4][8];
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(256) trl_init_kernel(const __nv_bfloat16* __re
         for (int i = 0; i < 8; ++i) { m0[i] = acc[k][i] * inv; zf[i] = m0[i] + first[k][i]; zb[i] = m0[i] + last[k][i]; }
         store8_planes(mem_hi + off, mem_lo + off, m0);
         store8_planes(mem_hi + dstride + off, mem_lo + dstride + off, m0);
+        if (mem16) { store8_f16(mem16 + off, m0); store8_f16(mem16 + dstride + off, m0); }   // the f1 weight-gradient operand (training)
         store8_planes(z_hi + off, z_lo + off, zf);
         store8_planes(z_hi + dstride + off, z_lo + dstride + off, zb);
     }
@@ -437,7 +439,8 @@ __global__ void __launch_bounds__(256) memo_update_kernel(const float* __restric
                                                           const __nv_bfloat16* __restrict__ uh, const __nv_bfloat16* __restrict__ ul, int T, int R,
                                                           int has_next, int tau_next0, int tau_next1,
                                                           __nv_bfloat16* __restrict__ mem_hi, __nv_bfloat16* __restrict__ mem_lo,
-                                                          __nv_bfloat16* __restrict__ zn_hi, __nv_bfloat16* __restrict__ zn_lo) {
+                                                          __nv_bfloat16* __restrict__ zn_hi, __nv_bfloat16* __restrict__ zn_lo,
+                                                          __half* __restrict__ mem16) {
     const int z = blockIdx.z, b = blockIdx.y, c0 = blockIdx.x * 64;
     const Tile t;
     const float* st = stat3 + (size_t)z * 4 * HC;
@@ -454,6 +457,7 @@ __global__ void __launch_bounds__(256) memo_update_kernel(const float* __restric
 #pragma unroll
         for (int i = 0; i < 8; ++i) mn[i] = fmaxf(a[i] * h[i] + c[i] + zz[i], 0.f);
         store8_planes(mem_hi + off, mem_lo + off, mn);
+        if (mem16) store8_f16(mem16 + off, mn);
         if (has_next) {
             const size_t xoff = (((size_t)b * T + tau) * HS + s) * HC + c0 + t.cg * 8;
             float xu[8];
@@ -649,8 +653,10 @@ static int trl_forward_part(grl_handle* h, cudaStream_t st, const grl_head_param
         GRL_TRY(gemm_launch(h, sd, P, 2 * HC, HC, 1, a, b, e, 0));
     }
     const size_t slotM = (size_t)2 * R * HC;     // elements per mem / z slot (both directions)
+    // training keeps every memory slot also as ONE fp16 plane: the operand of the single-pass f1 weight-gradient GEMM (head_bwd.cu)
+    __half* mem16 = w.save ? reinterpret_cast<__half*>(WS_BF(w, mem_16)) : nullptr;
     trl_init_kernel<<<dim3(HC / 64, B), 256, 0, st>>>(WS_BF(w, xu_hi), WS_BF(w, xu_lo), T, R, WS_BF(w, mem_hi), WS_BF(w, mem_lo),
-                                                      WS_BF(w, z_hi), WS_BF(w, z_lo));
+                                                      WS_BF(w, z_hi), WS_BF(w, z_lo), mem16);
     GRL_LAUNCH_CHECK(h);
     if (two) GRL_TRY(ev_record(h, EV_M(0), st));
     const int save = w.save;
@@ -721,7 +727,8 @@ static int trl_forward_part(grl_handle* h, cudaStream_t st, const grl_head_param
         memo_update_kernel<<<dim3(HC / 64, B, 2), 256, 0, st>>>(h3, s3, zh, zl, WS_BF(w, xu_hi), WS_BF(w, xu_lo), T, R, has_next, i + 1,
                                                                 T - 2 - i, WS_BF(w, mem_hi) + ms_next * slotM, WS_BF(w, mem_lo) + ms_next * slotM,
                                                                 WS_BF(w, z_hi) + (has_next ? zs_next : zs) * slotM,
-                                                                WS_BF(w, z_lo) + (has_next ? zs_next : zs) * slotM);
+                                                                WS_BF(w, z_lo) + (has_next ? zs_next : zs) * slotM,
+                                                                mem16 ? mem16 + ms_next * slotM : nullptr);
         GRL_LAUNCH_CHECK(h);
         if (two) GRL_TRY(ev_record(h, EV_M(i + 1), st));
     }

@@ -259,6 +259,18 @@ def _mm12(a, b, role="fwd"):
         return f(a, b)
 
 
+# ... and the contractions of the memory block (conv1/2/3 of BasicBlock) through this one
+MM_BLK = [torch.matmul]
+
+
+def _mmblk(a, b, role="fwd"):
+    f = MM_BLK[0]
+    try:
+        return f(a, b, role)
+    except TypeError:
+        return f(a, b)
+
+
 def _rows(b, t, tau):
     """Row indices (in [P]) of frame tau of every clip, ordered (b, s)."""
     base = (torch.arange(b)[:, None] * t + tau) * S + torch.arange(S)[None, :]
@@ -296,13 +308,13 @@ def plan_trl_forward(p, Xu, Xc, b, t, training, update=True):
             a = torch.sigmoid(h @ L2.t())
             out[d][:, tau] = (1 + a) * Gc[:, tau]                    # K13 via F4
             Z = M + Xu[r]                                            # K14
-            H1 = Z @ Wc1.t()
+            H1 = _mmblk(Z, Wc1.t())
             a1, c1, mu1, rs1 = _bn_coeffs(p, mp + ".bn1", H1, training, update)
             H1p = torch.relu(a1 * H1 + c1)
-            H2 = H1p @ Wc2.t()
+            H2 = _mmblk(H1p, Wc2.t())
             a2, c2, mu2, rs2 = _bn_coeffs(p, mp + ".bn2", H2, training, update)
             H2p = torch.relu(a2 * H2 + c2)
-            H3 = H2p @ Wc3.t()
+            H3 = _mmblk(H2p, Wc3.t())
             a3, c3, mu3, rs3 = _bn_coeffs(p, mp + ".bn3", H3, training, update)
             Mn = torch.relu(a3 * H3 + c3 + Z)
             ctx["steps"][d].append(dict(tau=tau, M=M, F1=F1, E=E, q=q, h=h, a=a, Z=Z, H1=H1, mu1=mu1, rs1=rs1,
@@ -345,16 +357,16 @@ def plan_trl_backward(p, ctx, d_f_uncorr, d_f_corr):
             dPre = dM * (st["Mn"] > 0)
             dH3, dg, db = _bn_bwd(dPre, st["H3"], st["mu3"], st["rs3"], p[mp + ".bn3.weight"], tr)
             acc["g3"] = acc["g3"] + dg; acc["b3"] = acc["b3"] + db
-            acc["Wc3"] = acc["Wc3"] + dH3.t() @ st["H2p"]
-            dA2 = (dH3 @ Wc3) * (st["H2p"] > 0)
+            acc["Wc3"] = acc["Wc3"] + _mmblk(dH3.t(), st["H2p"], "wgrad")
+            dA2 = _mmblk(dH3, Wc3, "dgrad") * (st["H2p"] > 0)
             dH2, dg, db = _bn_bwd(dA2, st["H2"], st["mu2"], st["rs2"], p[mp + ".bn2.weight"], tr)
             acc["g2"] = acc["g2"] + dg; acc["b2"] = acc["b2"] + db
-            acc["Wc2"] = acc["Wc2"] + dH2.t() @ st["H1p"]
-            dA1 = (dH2 @ Wc2) * (st["H1p"] > 0)
+            acc["Wc2"] = acc["Wc2"] + _mmblk(dH2.t(), st["H1p"], "wgrad")
+            dA1 = _mmblk(dH2, Wc2, "dgrad") * (st["H1p"] > 0)
             dH1, dg, db = _bn_bwd(dA1, st["H1"], st["mu1"], st["rs1"], p[mp + ".bn1.weight"], tr)
             acc["g1"] = acc["g1"] + dg; acc["b1"] = acc["b1"] + db
-            acc["Wc1"] = acc["Wc1"] + dH1.t() @ st["Z"]
-            dZ = dH1 @ Wc1 + dPre
+            acc["Wc1"] = acc["Wc1"] + _mmblk(dH1.t(), st["Z"], "wgrad")
+            dZ = _mmblk(dH1, Wc1, "dgrad") + dPre
             dXu[r] += dZ
             # reciprocal-attention path
             da = d_f_corr[:, st["tau"]] * Gc[:, st["tau"]]

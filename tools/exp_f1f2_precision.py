@@ -60,8 +60,9 @@ VARIANTS = {
 }
 
 
-def run(mm):
+def run(mm, blk=torch.matmul):
     ho.MM_F12[0] = mm
+    ho.MM_BLK[0] = blk
     p = synth.make_head_params(0, dtype=torch.float64)
     x = synth.make_head_input(B, T, dtype=torch.float64)
     gu, gc = synth.make_head_grads(B, T)
@@ -71,9 +72,20 @@ def run(mm):
 rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-300))
 ref = run(torch.matmul)
 print("B=%d T=%d; error vs the unmodified fp64 plan (gates: outputs 1e-4, gradients 1e-3)" % (B, T))
-for name, mm in VARIANTS.items():
+for name, mm in VARIANTS.items() if "--all" in sys.argv else []:
     o = run(mm)
     worst = sorted(((rel(o["grads"][k], ref["grads"][k]), k) for k in ref["grads"] if float(ref["grads"][k].norm()) > 1e-9), reverse=True)
     print("%-30s f_corr %.1e  dx %.1e  worst gradients: %s" %
           (name, rel(o["f_corr"], ref["f_corr"]), rel(o["dx"], ref["dx"]), ", ".join("%s %.1e" % (k.split("block.")[-1], e) for e, k in worst[:4])), flush=True)
+# ---- the memory block (conv1/2/3 of BasicBlock): f1/f2 as adopted (forward x3, gradients fp16 x1) + block variants
+adopted = VARIANTS["fwd x3, dgrad+wgrad fp16 x1"]
+print("memory block variants (f1/f2 as adopted):")
+for name, blk in (("block fwd exact, dgrad+wgrad fp16 x1", mixed(torch.matmul, f16mm, f16mm)), ("block all x3", mixed(x3, x3, x3)), ("block fwd x3, dgrad+wgrad fp16 x1", mixed(x3, f16mm, f16mm)),
+                  ("block fwd x3, wgrad fp16 x1", mixed(x3, x3, f16mm)), ("block all fp16 x1", mixed(f16mm, f16mm, f16mm))):
+    o = run(adopted, blk)
+    worst = sorted(((rel(o["grads"][k], ref["grads"][k]), k) for k in ref["grads"] if float(ref["grads"][k].norm()) > 1e-9), reverse=True)
+    print("%-38s f_uncorr %.1e f_corr %.1e  dx %.1e  worst gradients: %s" %
+          (name, rel(o["f_uncorr"], ref["f_uncorr"]), rel(o["f_corr"], ref["f_corr"]), rel(o["dx"], ref["dx"]),
+           ", ".join("%s %.1e" % (k.split("block.")[-1], e) for e, k in worst[:4])), flush=True)
 ho.MM_F12[0] = torch.matmul
+ho.MM_BLK[0] = torch.matmul
