@@ -175,9 +175,10 @@ static int launch_variant(grl_handle* h, cudaStream_t st, const GemmParams& p, i
     return GRL_OK;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int PLANES = 3>
 static int launch_pair_variant(grl_handle* h, cudaStream_t st, const GemmParams& p, int grid) {
-    auto kern = gemm_pair_bf16x3_kernel<A_MN, B_MN>;
+    auto kern = gemm_pair_bf16x3_kernel<A_MN, B_MN, PLANES>;
+    constexpr int GP_SMEM_BYTES = GpCfg<PLANES>::SMEM_BYTES;
     GRL_TRY(ensure_dyn_smem(h, (const void*)kern, GP_SMEM_BYTES));
     grl_prof_rec rec;
     if (h->prof_on) {
@@ -195,8 +196,13 @@ static int launch_pair_variant(grl_handle* h, cudaStream_t st, const GemmParams&
     return GRL_OK;
 }
 
-// The CTA-pair kernel (gemm_pair.cuh): 256 x 256 tiles, each CTA loads 128-row boxes of A and of B.
-static int gemm_launch_pair(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, const Operand& A, const Operand& B, GemmEpi epi) {
+// The CTA-pair kernel (gemm_pair.cuh): 256 x 256 tiles, each CTA loads 128-row boxes of A and of B.  a_lo == NULL: one fp16
+// plane per operand (single MMA per k-step), else bf16 hi/lo planes.
+static int gemm_launch_pair(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, const void* a_hi, const void* a_lo, long long lda,
+                            long long a_bstride, int a_mn, const void* b_hi, const void* b_lo, long long ldb, long long b_bstride, int b_mn,
+                            GemmEpi epi) {
+    const bool x1 = a_lo == nullptr;
+    const CUtensorMapDataType dt = x1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = N; p.K = K; p.batch = batch;
@@ -204,16 +210,33 @@ static int gemm_launch_pair(grl_handle* h, cudaStream_t st, int M, int N, int K,
     p.num_n_tiles = (N + GP_BN - 1) / GP_BN;
     p.group_m = p.num_m_tiles > 16 ? 8 : p.num_m_tiles;
     p.epi = epi;
-    GRL_TRY(make_tmap(h, &p.ta_hi, A.hi, A.ld, A.bstride, A.mn_major, M, K, batch, 128));
-    GRL_TRY(make_tmap(h, &p.ta_lo, A.lo, A.ld, A.bstride, A.mn_major, M, K, batch, 128));
-    GRL_TRY(make_tmap(h, &p.tb_hi, B.hi, B.ld, B.bstride, B.mn_major, N, K, batch, 128));
-    GRL_TRY(make_tmap(h, &p.tb_lo, B.lo, B.ld, B.bstride, B.mn_major, N, K, batch, 128));
+    GRL_TRY(make_tmap(h, &p.ta_hi, a_hi, lda, a_bstride, a_mn, M, K, batch, 128, dt));
+    GRL_TRY(make_tmap(h, &p.tb_hi, b_hi, ldb, b_bstride, b_mn, N, K, batch, 128, dt));
+    if (x1) { p.ta_lo = p.ta_hi; p.tb_lo = p.tb_hi; }
+    else {
+        GRL_TRY(make_tmap(h, &p.ta_lo, a_lo, lda, a_bstride, a_mn, M, K, batch, 128, dt));
+        GRL_TRY(make_tmap(h, &p.tb_lo, b_lo, ldb, b_bstride, b_mn, N, K, batch, 128, dt));
+    }
     const long long tiles = (long long)p.num_m_tiles * p.num_n_tiles * batch;
     const long long pairs = tiles < (long long)(h->num_sms / 2) ? tiles : (long long)(h->num_sms / 2);
     const int grid = (int)(2 * pairs);
-    if (A.mn_major) return launch_pair_variant<true, true>(h, st, p, grid);
-    if (B.mn_major) return launch_pair_variant<false, true>(h, st, p, grid);
+    if (x1) {
+        if (a_mn) return launch_pair_variant<true, true, 1>(h, st, p, grid);
+        if (b_mn) return launch_pair_variant<false, true, 1>(h, st, p, grid);
+        return launch_pair_variant<false, false, 1>(h, st, p, grid);
+    }
+    if (a_mn) return launch_pair_variant<true, true>(h, st, p, grid);
+    if (b_mn) return launch_pair_variant<false, true>(h, st, p, grid);
     return launch_pair_variant<false, false>(h, st, p, grid);
+}
+
+// Pairs pay off when the k-loop is long enough to amortise the cross-CTA handshakes and there is at least a wave of 256 x 256
+// tiles (measured: the K = 512 / one-wave GEMMs of the memory block run a few percent faster on the single-CTA kernel).
+static bool use_pair_kernel(const grl_handle* h, int M, int N, int K, int batch) {
+    if ((h->overlap & 16) != 0 || M <= GEMM_BM) return false;
+    if ((h->overlap & 64) != 0) return true;                                              // debug bit 6: pairs for every 256-wide tile
+    const long long tiles = (long long)((M + GP_BM - 1) / GP_BM) * ((N + GP_BN - 1) / GP_BN) * batch;
+    return K >= 1024 && tiles >= (long long)(h->num_sms / 2);
 }
 
 int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, const Operand& A, const Operand& B,
@@ -228,7 +251,8 @@ int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, 
     }
     if (bn != 128 && bn != 256) return set_error(h, GRL_EINVAL, "gemm: bn must be 0, 128 or 256");
     // 256-wide tiles go to the CTA-pair kernel (two SMs per 256 x 256 tile) unless grl_set_overlap bit 4 asks for the single-CTA one
-    if (bn == 256 && M > GEMM_BM && (h->overlap & 16) == 0) return gemm_launch_pair(h, st, M, N, K, batch, A, B, epi);
+    if (bn == 256 && use_pair_kernel(h, M, N, K, batch))
+        return gemm_launch_pair(h, st, M, N, K, batch, A.hi, A.lo, A.ld, A.bstride, A.mn_major, B.hi, B.lo, B.ld, B.bstride, B.mn_major, epi);
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = N; p.K = K; p.batch = batch;
@@ -264,6 +288,8 @@ int gemm_launch_x1(grl_handle* h, cudaStream_t st, int M, int N, int K, int batc
     const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
     const long long t256 = (long long)m_tiles * ((N + 255) / 256) * batch;
     const int bn = (N > 128 && t256 >= (long long)h->num_sms * 3 / 4) ? 256 : 128;
+    if (bn == 256 && (h->overlap & 32) == 0 && use_pair_kernel(h, M, N, K, batch))      // debug bit 5: single-CTA kernel for the fp16 GEMMs
+        return gemm_launch_pair(h, st, M, N, K, batch, A, nullptr, lda, a_bstride, a_mn, B, nullptr, ldb, b_bstride, b_mn, epi);
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.M = M; p.N = N; p.K = K; p.batch = batch;
@@ -415,7 +441,7 @@ extern "C" void grl_destroy(grl_handle* h) {
 
 extern "C" int grl_set_overlap(grl_handle* h, int on) {
     if (!h) return GRL_EINVAL;
-    h->overlap = on & 31;
+    h->overlap = on & 127;
     return GRL_OK;
 }
 

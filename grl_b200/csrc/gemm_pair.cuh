@@ -16,16 +16,23 @@
 
 namespace grl {
 
-constexpr int GP_STAGES = 3;
-constexpr int GP_PLANE = 128 * GEMM_BK * 2;                 // one plane of one operand half: 128 rows x 64 k x bf16 = 16 KB
-constexpr int GP_STAGE_BYTES = 4 * GP_PLANE;                // A_hi | B_hi | A_lo | B_lo = 64 KB
-constexpr int GP_SMEM_BYTES = GP_STAGES * GP_STAGE_BYTES + 1024 + 256;
+constexpr int GP_PLANE = 128 * GEMM_BK * 2;                 // one plane of one operand half: 128 rows x 64 k x 2 bytes = 16 KB
 constexpr int GP_BM = 256, GP_BN = 256;
+// PLANES = 3: split-bf16 (A_hi | B_hi | A_lo | B_lo = 64 KB per stage, 3 stages); PLANES = 1: one fp16 plane per operand, one MMA
+// per k-step (32 KB per stage, 6 stages) -- the single-pass gradient GEMMs of the attention convs
+template <int PLANES>
+struct GpCfg {
+    static constexpr int STAGES = PLANES == 1 ? 6 : 3;
+    static constexpr int STAGE_BYTES = (PLANES == 1 ? 2 : 4) * GP_PLANE;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
 
 // tile index -> (batch, 256-row tile, 256-column tile); same grouped rasterisation as gemm.cuh with p.num_m_tiles counted in
 // 256-row tiles (the host passes pair params: num_m_tiles = ceil(M / 256))
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int PLANES = 3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gemm_pair_bf16x3_kernel(const __grid_constant__ GemmParams p) {
+    constexpr int GP_STAGES = GpCfg<PLANES>::STAGES;
+    constexpr int GP_STAGE_BYTES = GpCfg<PLANES>::STAGE_BYTES;
     extern __shared__ uint8_t gp_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gp_smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GP_STAGES * GP_STAGE_BYTES);
@@ -75,7 +82,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
                     uint8_t* sB_hi = sA_hi + GP_PLANE;
                     uint8_t* sA_lo = sB_hi + GP_PLANE;
                     uint8_t* sB_lo = sA_lo + GP_PLANE;
-                    if (leader) mbar_arrive_expect_tx(&full_hi[stage], 4 * GP_PLANE);          // both CTAs' hi boxes land on this barrier
+                    if (leader) mbar_arrive_expect_tx(&full_hi[stage], 4 * GP_PLANE);          // both CTAs' hi boxes (A and B) land on this barrier
                     if (A_MN) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j) tma_load_3d_2cta(sA_hi + j * 8192, &p.ta_hi, &full_hi[stage], m0 + 64 * j, k0, z);
@@ -87,6 +94,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
                         for (int j = 0; j < 2; ++j) tma_load_3d_2cta(sB_hi + j * 8192, &p.tb_hi, &full_hi[stage], n0 + 64 * j, k0, z);
                     } else {
                         tma_load_3d_2cta(sB_hi, &p.tb_hi, &full_hi[stage], k0, n0, z);
+                    }
+                    if (PLANES == 1) {
+                        if (++stage == GP_STAGES) { stage = 0; phase ^= 1; }
+                        continue;
                     }
                     if (leader) mbar_arrive_expect_tx(&full_lo[stage], 4 * GP_PLANE);
                     if (A_MN) {
@@ -108,7 +119,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
     } else if (warp == 1) {
         // ===================== MMA issuer (even CTA only) =====================
         if (lane == 0 && leader) {
-            constexpr uint32_t idesc = make_idesc_bf16(GP_BM, GP_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            constexpr uint32_t idesc = (PLANES == 1) ? make_idesc_f16(GP_BM, GP_BN, A_MN ? 1 : 0, B_MN ? 1 : 0)
+                                                     : make_idesc_bf16(GP_BM, GP_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
             constexpr uint32_t a_lbo = A_MN ? GEMM_BK * 128 : 16, b_lbo = B_MN ? GEMM_BK * 128 : 16;
             constexpr uint32_t a_kstep = A_MN ? (2048 >> 4) : (32 >> 4), b_kstep = B_MN ? (2048 >> 4) : (32 >> 4);
             int stage = 0; uint32_t phase = 0;
@@ -130,12 +142,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) gem
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k)
                         umma_f16_2cta(d_tmem, dA_hi + k * a_kstep, dB_hi + k * b_kstep, idesc, (kb | k) ? 1u : 0u);
-                    mbar_wait(&full_lo[stage], phase);
-                    tc_fence_after();
+                    if (PLANES == 3) {
+                        mbar_wait(&full_lo[stage], phase);
+                        tc_fence_after();
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        umma_f16_2cta(d_tmem, dA_lo + k * a_kstep, dB_hi + k * b_kstep, idesc, 1u);
-                        umma_f16_2cta(d_tmem, dA_hi + k * a_kstep, dB_lo + k * b_kstep, idesc, 1u);
+                        for (int k = 0; k < GEMM_BK / 16; ++k) {
+                            umma_f16_2cta(d_tmem, dA_lo + k * a_kstep, dB_hi + k * b_kstep, idesc, 1u);
+                            umma_f16_2cta(d_tmem, dA_hi + k * a_kstep, dB_lo + k * b_kstep, idesc, 1u);
+                        }
                     }
                     umma_commit_2cta(&empty[stage]);               // frees the stage in BOTH CTAs once these MMAs retire
                     if (kb == num_kb - 1) umma_commit_2cta(&tmem_full[acc]);

@@ -46,7 +46,9 @@ for mask in (3, 19):
 rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
 print("pair vs single-CTA kernel: f_uncorr %.2e  f_corr %.2e  dx %.2e  d f1.w %.2e" %
       tuple(rel(a, b) for a, b in zip(res[3], res[19])), flush=True)
+NAMES = {3: "default (pairs where K >= 1024 and >= 1 wave)", 19: "single-CTA kernels only", 35: "fp16 GEMMs on the single-CTA kernel",
+         67: "pairs for every 256-wide tile"}
 for rep in range(3):
-    for mask in (3, 19):
+    for mask in (3, 35, 67, 19):
         lib.grl_set_overlap(h, mask)
-        print("mask %2d (%s)  fwd+bwd %.3f ms" % (mask, "CTA pairs" if mask == 3 else "single CTA", timeit()), flush=True)
+        print("mask %2d (%s)  fwd+bwd %.3f ms" % (mask, NAMES[mask], timeit()), flush=True)
