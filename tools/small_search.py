@@ -1,0 +1,24 @@
+"""GPU: one small search that exercises the 256 x 256 CTA-pair coarse GEMM, the warp-level list merges, the re-score, the proof,
+the second chance and the brute-force leg (for compute-sanitizer runs: tools/sanitize.sh)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from grl_b200 import evaluator as ev  # noqa: E402
+
+rng = np.random.default_rng(3)
+nq, ng, dim, k = 1100, 3072, 64, 20
+q = rng.standard_normal((nq, dim)).astype(np.float32)
+g = rng.standard_normal((ng, dim)).astype(np.float32)
+g[::13] = g[5]                                      # duplicates: some proofs fail -> second chance / brute force
+q /= np.linalg.norm(q, axis=1, keepdims=True)
+g /= np.linalg.norm(g, axis=1, keepdims=True)
+stats = torch.zeros(8, dtype=torch.int32, device="cuda")
+d, i = ev.sharded_topk(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda(), k, 0, stats=stats)
+dx, ix = ev.CudaSearchStages.exact(torch.from_numpy(q[:64]).cuda(), torch.from_numpy(g).cuda(), k, 0, 0)
+torch.cuda.synchronize()
+assert torch.equal(i[:64], ix) and torch.equal(d[:64], dx)
+print("small search OK, stats", stats.cpu().tolist())
