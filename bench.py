@@ -620,8 +620,10 @@ def run_ours(args):
 
             def search():
                 evaluator.sharded_retrieve(q_slice_host.to(dev, non_blocking=True), gallery, KTOP, lo, nq=NQ, out=dev_out, stats=stats)
-                out_d.copy_(dev_out[0], non_blocking=True)
-                out_i.copy_(dev_out[1], non_blocking=True)
+                # every rank holds the full result on the device; each returns the rows of ITS query slice to the host (the union
+                # over the ranks is the whole result: it crosses PCIe once, like the queries did)
+                out_d[qlo:qlo + qn].copy_(dev_out[0][qlo:qlo + qn], non_blocking=True)
+                out_i[qlo:qlo + qn].copy_(dev_out[1][qlo:qlo + qn], non_blocking=True)
             for _ in range(2):
                 search()
             barrier()
@@ -671,7 +673,7 @@ def run_ours(args):
                             "search index prepared once (untimed); per search: every rank uploads its query slice from pinned host memory -> "
                             "grl_sharded_topk (NCCL all-gather of the query slices, per-shard coarse fp16 tensor-core pass, all-to-all of the "
                             "coarse lists by query slice + merge + all-gather, owned fixed-order fp32 re-scores, reduce-scatter, completeness "
-                            "proof per slice, all-gather of the results) -> results to the host on every rank" % world,
+                            "proof per slice, all-gather of the results) -> every rank returns the rows of its query slice to the host" % world,
                 "queries_per_s": NQ / (rms * 1e-3), "ms_per_search": rms, "timed_searches": 5, "alg_tflops": alg_tf,
                 "stages_ms": stages, "checksum": checksum,
                 "flagged_queries": st_host[0], "second_chance_proven": st_host[4], "brute_forced_queries": st_host[5],
@@ -684,7 +686,7 @@ def run_ours(args):
                              "note": "achieved = 2*Nq*nc*D per launch / event-timed launch duration over one search (algorithmic == "
                                      "issued: one MMA per product); whole_search_* divides the algorithmic 2*Nq*Ng*D by the full search "
                                      "time (uploads, conversion, list merges, collectives, re-score, proof, downloads included)"},
-                "h2d_bytes": qn * D * 4, "d2h_bytes": NQ * KTOP * 12}
+                "h2d_bytes_per_rank": qn * D * 4, "d2h_bytes_per_rank": qn * KTOP * 12}
         # the same search on a CLUSTERED gallery (625 identities x 1,600 near-duplicates each, the re-ID case): proofs can fail here
         rms_c, st_c, stages_c, _, checksum_c = run_case(True, 3)
         retr["clustered"] = {"workload": "same sizes; gallery rows = normalize(centroid[row %% 625] + 0.3 * noise), queries likewise",

@@ -214,6 +214,138 @@ __device__ __forceinline__ void warp_merge_row(int cnt, const unsigned long long
     }
 }
 
+// ---- the first chunk of a search: no threshold exists yet, so its distance tile IS stored and every row selects its k smallest
+// entries from it.  One block per row; the row (<= BOOT_MAX columns) lives in registers as orderable 32-bit distances, thread t
+// holding the contiguous columns [t * BOOT_PER, (t + 1) * BOOT_PER).  Selection = radix refinement of the k-th smallest VALUE:
+// histogram the values still in range over BOOT_BINS equal-width bins, descend into the bin that holds the k-th, repeat until
+// the range is a single value (two or three rounds in practice); then one ordered compaction (everything below the value, and
+// as many entries EQUAL to it as are still needed, lowest column first) and one block sort of the k selected keys.  O(ncols)
+// work per row instead of a full sort, which is what lets the first chunk be thousands of columns wide and spares the
+// search the first four "doubling" list merges.
+constexpr int BOOT_THREADS = 256, BOOT_PER = 32, BOOT_MAX = BOOT_THREADS * BOOT_PER, BOOT_BINS = 2048;
+
+__device__ __forceinline__ int block_excl_scan_256(int v, int* smem_warp, int& total) {
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+    if (lane == 31) smem_warp[warp] = x;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < BOOT_THREADS / 32; ++w) { const int s = smem_warp[w]; if (w < warp) base += s; tot += s; }
+    __syncthreads();
+    total = tot;
+    return base + x - v;
+}
+
+__global__ void __launch_bounds__(BOOT_THREADS) list_boot_select_kernel(const float* __restrict__ tile, long long ld, int ncols, int k,
+                                                                        int64_t idx_base, uint64_t* __restrict__ list, float* __restrict__ thresh_out,
+                                                                        int* __restrict__ cand_cnt) {
+    __shared__ unsigned int hist[BOOT_BINS];
+    __shared__ uint64_t sel[TOPK_MAXK];
+    __shared__ int warp_tmp[BOOT_THREADS / 32];
+    __shared__ unsigned int s_lo, s_hi, s_bin, s_before;
+    const int row = blockIdx.x;
+    const float* drow = tile + (long long)row * ld;
+    const int c_begin = threadIdx.x * BOOT_PER;
+    uint32_t v[BOOT_PER];
+#pragma unroll
+    for (int j = 0; j < BOOT_PER / 4; ++j) {
+        const int c = c_begin + 4 * j;
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c + 3 < ncols) f = __ldg(reinterpret_cast<const float4*>(drow + c));
+        else { if (c < ncols) f.x = drow[c]; if (c + 1 < ncols) f.y = drow[c + 1]; if (c + 2 < ncols) f.z = drow[c + 2]; }
+        v[4 * j] = orderable(f.x); v[4 * j + 1] = orderable(f.y); v[4 * j + 2] = orderable(f.z); v[4 * j + 3] = orderable(f.w);
+    }
+    uint64_t* lrow = list + (long long)row * k;
+    if (ncols <= k) {                                 // fewer columns than list slots: everything is selected
+        for (int i = threadIdx.x; i < k; i += BOOT_THREADS) sel[i] = KEY_EMPTY;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < BOOT_PER; ++j)
+            if (c_begin + j < ncols) sel[c_begin + j] = ((uint64_t)v[j] << 32) | (uint32_t)(idx_base + c_begin + j);
+    } else {
+        // ---- value of the k-th smallest entry: T, and how many entries equal to T are still needed
+        uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+#pragma unroll
+        for (int j = 0; j < BOOT_PER; ++j)
+            if (c_begin + j < ncols) { lo = min(lo, v[j]); hi = max(hi, v[j]); }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off)); }
+        if (threadIdx.x == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; }
+        __syncthreads();
+        if (lane_id() == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+        __syncthreads();
+        lo = s_lo; hi = s_hi;
+        int need = k;                                 // entries still to take from [lo, hi]
+        while (lo != hi) {
+            for (int i = threadIdx.x; i < BOOT_BINS; i += BOOT_THREADS) hist[i] = 0;
+            __syncthreads();
+            const unsigned long long range = (unsigned long long)(hi - lo);
+#pragma unroll
+            for (int j = 0; j < BOOT_PER; ++j)
+                if (c_begin + j < ncols && v[j] >= lo && v[j] <= hi)
+                    atomicAdd(&hist[(unsigned int)(((unsigned long long)(v[j] - lo) * (BOOT_BINS - 1)) / range)], 1u);
+            __syncthreads();
+            // the bin holding the `need`-th entry: each thread owns BOOT_BINS / BOOT_THREADS consecutive bins
+            constexpr int PER = BOOT_BINS / BOOT_THREADS;
+            int mine = 0;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) mine += (int)hist[threadIdx.x * PER + j];
+            int total;
+            const int before = block_excl_scan_256(mine, warp_tmp, total);
+            if (before < need && need <= before + mine) {
+                int run = before;
+#pragma unroll
+                for (int j = 0; j < PER; ++j) {
+                    const int h = (int)hist[threadIdx.x * PER + j];
+                    if (run < need && need <= run + h) { s_bin = threadIdx.x * PER + j; s_before = run; }
+                    run += h;
+                }
+            }
+            if (threadIdx.x == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; }
+            __syncthreads();
+            const unsigned int bin = s_bin;
+            need -= (int)s_before;
+            uint32_t nlo = 0xFFFFFFFFu, nhi = 0u;      // the value range actually present in that bin
+#pragma unroll
+            for (int j = 0; j < BOOT_PER; ++j)
+                if (c_begin + j < ncols && v[j] >= lo && v[j] <= hi &&
+                    (unsigned int)(((unsigned long long)(v[j] - lo) * (BOOT_BINS - 1)) / range) == bin) { nlo = min(nlo, v[j]); nhi = max(nhi, v[j]); }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) { nlo = min(nlo, __shfl_xor_sync(0xffffffffu, nlo, off)); nhi = max(nhi, __shfl_xor_sync(0xffffffffu, nhi, off)); }
+            if (lane_id() == 0 && nlo <= nhi) { atomicMin(&s_lo, nlo); atomicMax(&s_hi, nhi); }
+            __syncthreads();
+            lo = s_lo; hi = s_hi;
+            __syncthreads();
+        }
+        const uint32_t T = lo;
+        // ---- ordered compaction: entries below T, then the first `need` entries equal to T (lowest column first)
+        int n_less = 0, n_eq = 0;
+#pragma unroll
+        for (int j = 0; j < BOOT_PER; ++j)
+            if (c_begin + j < ncols) { n_less += v[j] < T ? 1 : 0; n_eq += v[j] == T ? 1 : 0; }
+        int tot_less, tot_eq;
+        int off_less = block_excl_scan_256(n_less, warp_tmp, tot_less);
+        int off_eq = block_excl_scan_256(n_eq, warp_tmp, tot_eq);
+#pragma unroll
+        for (int j = 0; j < BOOT_PER; ++j) {
+            if (c_begin + j < ncols) {
+                const uint64_t key = ((uint64_t)v[j] << 32) | (uint32_t)(idx_base + c_begin + j);
+                if (v[j] < T) sel[off_less++] = key;
+                else if (v[j] == T) { if (off_eq < need) sel[tot_less + off_eq] = key; ++off_eq; }
+            }
+        }
+    }
+    int npad = 2;
+    while (npad < k) npad <<= 1;
+    for (int i = k + threadIdx.x; i < npad; i += BOOT_THREADS) sel[i] = KEY_EMPTY;      // (k <= TOPK_MAXK, a power of two in practice)
+    block_bitonic_sort(sel, npad);
+    for (int i = threadIdx.x; i < k; i += BOOT_THREADS) lrow[i] = sel[i];
+    if (threadIdx.x == 0) { thresh_out[row] = thresh_of(sel[k - 1]); cand_cnt[row] = 0; }
+}
+
 constexpr int LIST_WARPS = 4;          // rows per block of list_update_warp_kernel
 constexpr int LIST_WARP_MAX = 512;     // candidates one warp sorts in registers (16 keys per lane)
 
@@ -576,10 +708,10 @@ using namespace grl;
 static int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 // Column chunks of one coarse pass.  The first chunk has no thresholds yet: its tile IS stored and every row is rescanned, so it
-// is kept small (TOPK_FIRST_CHUNK columns: what one warp sorts in registers).  Afterwards the K'-th best of n_seen columns lets
+// holds TOPK_FIRST_CHUNK columns (one block selects a row's K' smallest in O(columns), list_boot_select_kernel).  Afterwards the K'-th best of n_seen columns lets
 // ~K' * nc / n_seen candidates per row through, so chunks grow with n_seen (at most doubling the columns seen) up to the
 // steady-state size, whose 256 x 256 tiles fill whole waves of the persistent grid; their tiles are never stored.
-constexpr int TOPK_FIRST_CHUNK = LIST_WARP_MAX;
+constexpr int TOPK_FIRST_CHUNK = BOOT_MAX;          // 8192 columns: list_boot_select_kernel keeps a row in registers
 // candidates per query row and column chunk: a chunk at most doubles the columns seen, so ~K' candidates per row are expected;
 // the buffer holds twice that (an overflow outside the first chunk marks the row dirty -> brute force)
 static int cand_cap(int kprime) { return std::max(512, 2 * kprime); }
@@ -623,7 +755,7 @@ static void coarse_layout(int nq, int ng, int dim, int kprime, bool prepared, Co
     // the conversion buffers of an unprepared shard are sized for the largest chunk any query count can pick, so that a layout
     // computed for fewer rows (the second chance over the flagged queries) always fits the reservation made for all of them
     L->chunk_alloc = (int)std::min<long long>(16384, ((long long)ng + 7) / 8 * 8);
-    L->first = ng < TOPK_FIRST_CHUNK ? (ng + 7) / 8 * 8 : TOPK_FIRST_CHUNK;
+    L->first = (topk_next_chunk(0, ng, L->chunk) + 7) / 8 * 8;     // leading dimension of the stored first tile
     L->cap = cand_cap(kprime);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
@@ -734,15 +866,19 @@ static int coarse_pass(grl_handle* h, cudaStream_t st, int metric, const float* 
         // Merge when the buffers could overflow during the next chunk (1.6x the expectation + 48 of slack), and at the end.
         const int c_end = c0 + nc;
         const bool last = c_end >= ng;
-        bool merge = first || last;
+        bool merge = last;
         if (!merge) {
             const int nc_next = topk_next_chunk(c_end, ng, L.chunk);
             const double pending = (double)kprime * (double)(c_end - c_merge + nc_next) / (double)c_merge;
             merge = 1.6 * pending + 48.0 > (double)L.cap;
         }
-        if (merge) {
+        if (first) {
+            list_boot_select_kernel<<<nq, BOOT_THREADS, 0, st>>>(tile, L.first, nc, kprime, idx_base, list, thresh, cand_cnt);
+            GRL_LAUNCH_CHECK(h);
+            c_merge = c_end;
+        } else if (merge) {
             list_update_warp_kernel<<<(nq + LIST_WARPS - 1) / LIST_WARPS, LIST_WARPS * 32, list_smem, st>>>(
-                nq, kprime, first ? tile : nullptr, L.first, nc, idx_base + c0, list, thresh, cand, cand_cnt, L.cap, dirty);
+                nq, kprime, nullptr, 0, nc, idx_base + c0, list, thresh, cand, cand_cnt, L.cap, dirty);
             GRL_LAUNCH_CHECK(h);
             if (L.cap > LIST_WARP_MAX && !first) {    // K' >= 512: a row can hold more candidates than one warp sorts
                 list_update_kernel<<<nq, TOPK_THREADS, 0, st>>>(kprime, LIST_WARP_MAX, list, thresh, cand, cand_cnt, L.cap);

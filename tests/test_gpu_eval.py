@@ -250,7 +250,7 @@ def test_dist_topk_adversarial_order_overflows_to_brute_force(nq):
     dirty and must come back exact from the brute-force leg.  nq = 8: gemm.cuh single-plane kernel; 1100: coarse_gemm.cuh."""
     _, ev = _mods()
     from oracle import eval_oracle as eo
-    ng, dim, k = 6000, 64, 30
+    ng, dim, k = 20000, 64, 30                        # > 8192 columns: the first (stored, exactly selected) chunk does not cover the gallery
     q, g = _retrieval_inputs(nq, ng, dim, 77, dup_every=0)
     g = g[np.argsort(-(g @ q[0]), kind="stable")[::-1].copy()]            # ascending similarity to q[0] == descending distance
     qd, gd = torch.from_numpy(q).cuda(), torch.from_numpy(np.ascontiguousarray(g)).cuda()
