@@ -239,7 +239,7 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int* smem_warp, int& t
     return base + x - v;
 }
 
-__global__ void __launch_bounds__(BOOT_THREADS) list_boot_select_kernel(const float* __restrict__ tile, long long ld, int ncols, int k,
+__global__ void __launch_bounds__(BOOT_THREADS, 3) list_boot_select_kernel(const float* __restrict__ tile, long long ld, int ncols, int k,
                                                                         int64_t idx_base, uint64_t* __restrict__ list, float* __restrict__ thresh_out,
                                                                         int* __restrict__ cand_cnt) {
     __shared__ unsigned int hist[BOOT_BINS];
@@ -282,11 +282,13 @@ __global__ void __launch_bounds__(BOOT_THREADS) list_boot_select_kernel(const fl
         while (lo != hi) {
             for (int i = threadIdx.x; i < BOOT_BINS; i += BOOT_THREADS) hist[i] = 0;
             __syncthreads();
-            const unsigned long long range = (unsigned long long)(hi - lo);
+            // bin = a monotone map of [lo, hi] onto 0 .. BOOT_BINS-1 (float arithmetic: the bins need not be exactly equal, only
+            // ordered, with lo and hi in different ones -- an integer division per entry would cost more than the whole selection)
+            const float scale = (float)(BOOT_BINS - 1) / (float)(hi - lo);
+            auto bin_of = [&](uint32_t x) { return min((unsigned int)(BOOT_BINS - 1), (unsigned int)((float)(x - lo) * scale)); };
 #pragma unroll
             for (int j = 0; j < BOOT_PER; ++j)
-                if (c_begin + j < ncols && v[j] >= lo && v[j] <= hi)
-                    atomicAdd(&hist[(unsigned int)(((unsigned long long)(v[j] - lo) * (BOOT_BINS - 1)) / range)], 1u);
+                if (c_begin + j < ncols && v[j] >= lo && v[j] <= hi) atomicAdd(&hist[bin_of(v[j])], 1u);
             __syncthreads();
             // the bin holding the `need`-th entry: each thread owns BOOT_BINS / BOOT_THREADS consecutive bins
             constexpr int PER = BOOT_BINS / BOOT_THREADS;
@@ -311,8 +313,7 @@ __global__ void __launch_bounds__(BOOT_THREADS) list_boot_select_kernel(const fl
             uint32_t nlo = 0xFFFFFFFFu, nhi = 0u;      // the value range actually present in that bin
 #pragma unroll
             for (int j = 0; j < BOOT_PER; ++j)
-                if (c_begin + j < ncols && v[j] >= lo && v[j] <= hi &&
-                    (unsigned int)(((unsigned long long)(v[j] - lo) * (BOOT_BINS - 1)) / range) == bin) { nlo = min(nlo, v[j]); nhi = max(nhi, v[j]); }
+                if (c_begin + j < ncols && v[j] >= lo && v[j] <= hi && bin_of(v[j]) == bin) { nlo = min(nlo, v[j]); nhi = max(nhi, v[j]); }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) { nlo = min(nlo, __shfl_xor_sync(0xffffffffu, nlo, off)); nhi = max(nhi, __shfl_xor_sync(0xffffffffu, nhi, off)); }
             if (lane_id() == 0 && nlo <= nhi) { atomicMin(&s_lo, nlo); atomicMax(&s_hi, nhi); }
@@ -337,6 +338,19 @@ __global__ void __launch_bounds__(BOOT_THREADS) list_boot_select_kernel(const fl
                 else if (v[j] == T) { if (off_eq < need) sel[tot_less + off_eq] = key; ++off_eq; }
             }
         }
+    }
+    __syncthreads();
+    if (k == 256) {                                   // the common list length: one warp sorts the selection in registers, no barriers
+        if (threadIdx.x < 32) {
+            uint64_t r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = sel[threadIdx.x * 8 + j];
+            warp_sort_keys<8>(r, threadIdx.x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) lrow[threadIdx.x * 8 + j] = r[j];
+            if (threadIdx.x == 31) { thresh_out[row] = thresh_of(r[7]); cand_cnt[row] = 0; }
+        }
+        return;
     }
     int npad = 2;
     while (npad < k) npad <<= 1;
