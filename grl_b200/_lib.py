@@ -144,6 +144,10 @@ _SIGNATURES = {
     "grl_head_backward": (C.c_int, [C.c_void_p, C.POINTER(HeadParams), C.c_void_p, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(HeadGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "grl_basic_block_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "grl_basic_block_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(BnParams), C.c_void_p, C.POINTER(BnParams), C.c_void_p,
+                                          C.POINTER(BnParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                          C.c_void_p]),
     "grl_gce_forward": (C.c_int, [C.c_void_p, C.POINTER(HeadParams), C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "grl_gce_backward": (C.c_int, [C.c_void_p, C.POINTER(HeadParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

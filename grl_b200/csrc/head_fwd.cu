@@ -13,14 +13,19 @@ namespace grl {
 
 // ------------------------------------------------------------------ K1: NCHW -> pixel-major planes + per-frame sums
 __global__ void __launch_bounds__(256) nchw_to_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
-                                                             __nv_bfloat16* __restrict__ lo, float* __restrict__ gx, float gx_scale) {
+                                                             __nv_bfloat16* __restrict__ lo, float* __restrict__ gx, float gx_scale,
+                                                             const float* __restrict__ x2 = nullptr) {
     __shared__ float tile[64][129];
     const int n = blockIdx.y, c0 = blockIdx.x * 64;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = warp * 8 + i;
-        const float4 v = *reinterpret_cast<const float4*>(x + ((size_t)n * HC + c0 + c) * HS + lane * 4);
+        float4 v = *reinterpret_cast<const float4*>(x + ((size_t)n * HC + c0 + c) * HS + lane * 4);
+        if (x2) {                                     // BasicBlock.forward(x1, x2): the block works on x1 + x2
+            const float4 u = *reinterpret_cast<const float4*>(x2 + ((size_t)n * HC + c0 + c) * HS + lane * 4);
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
         tile[c][lane * 4 + 0] = v.x; tile[c][lane * 4 + 1] = v.y; tile[c][lane * 4 + 2] = v.z; tile[c][lane * 4 + 3] = v.w;
         const float s = warp_sum(v.x + v.y + v.z + v.w);
         if (lane == 0 && gx) gx[(size_t)n * HC + c0 + c] = s * gx_scale;
@@ -800,4 +805,74 @@ extern "C" int grl_trl_forward(grl_handle* h, const grl_head_params* p, const fl
     nchw_to_planes_kernel<<<dim3(HC / 64, w.N), 256, 0, st>>>(x_uncorr, WS_BF(w, xu_hi), WS_BF(w, xu_lo), nullptr, 1.f);
     GRL_LAUNCH_CHECK(h);
     return trl_forward_part(h, st, p, w, train, f_uncorr, f_corr);
+}
+
+// ------------------------------------------------------------------ BasicBlock.forward(x1, x2) as a stand-alone operator
+// reid/models/grl_model.py:67-85: relu(bn3(conv3(relu(bn2(conv2(relu(bn1(conv1(x1 + x2)))))))) + (x1 + x2)), x* [n][2048][16][8].
+// The same kernels as one memory-update step of the TRL recurrence (one "direction", n frames = n 128-row tiles).
+struct BlockWs { size_t z_hi, z_lo, w1_hi, w1_lo, w2_hi, w2_lo, w3_hi, w3_lo, h1, h1p_hi, h1p_lo, h2, h2p_hi, h2p_lo, h3, s1, s2, s3, pa, pb, o_hi, o_lo, total; };
+static BlockWs block_ws_layout(int n) {
+    BlockWs L;
+    const size_t R = (size_t)n * HS;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    L.z_hi = take(R * HC * 2); L.z_lo = take(R * HC * 2);
+    L.w1_hi = take((size_t)HB * HC * 2); L.w1_lo = take((size_t)HB * HC * 2);
+    L.w2_hi = take((size_t)HB * HB * 2); L.w2_lo = take((size_t)HB * HB * 2);
+    L.w3_hi = take((size_t)HC * HB * 2); L.w3_lo = take((size_t)HC * HB * 2);
+    L.h1 = take(R * HB * 4); L.h1p_hi = take(R * HB * 2); L.h1p_lo = take(R * HB * 2);
+    L.h2 = take(R * HB * 4); L.h2p_hi = take(R * HB * 2); L.h2p_lo = take(R * HB * 2);
+    L.h3 = take(R * HC * 4);
+    L.s1 = take((size_t)4 * HB * 4); L.s2 = take((size_t)4 * HB * 4); L.s3 = take((size_t)4 * HC * 4);
+    L.pa = take((size_t)4 * n * HC * 4); L.pb = take((size_t)4 * n * HC * 4);
+    L.o_hi = take(R * HC * 2); L.o_lo = take(R * HC * 2);
+    L.total = off;
+    return L;
+}
+extern "C" size_t grl_basic_block_workspace_bytes(int n) { return n > 0 ? block_ws_layout(n).total : 0; }
+
+extern "C" int grl_basic_block_forward(grl_handle* h, const float* conv1_w, const grl_bn_params* bn1, const float* conv2_w, const grl_bn_params* bn2,
+                                       const float* conv3_w, const grl_bn_params* bn3, const float* x1, const float* x2, int n, int train,
+                                       float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !conv1_w || !conv2_w || !conv3_w || !bn1 || !bn2 || !bn3 || !x1 || !x2 || !out || !workspace)
+        return set_error(h, GRL_EINVAL, "grl_basic_block_forward: NULL argument");
+    if (n <= 0) return set_error(h, GRL_EINVAL, "grl_basic_block_forward: need n > 0");
+    const BlockWs L = block_ws_layout(n);
+    if (workspace_bytes < L.total) return set_error(h, GRL_ENOMEM, "grl_basic_block_forward: workspace %zu < %zu bytes", workspace_bytes, L.total);
+    if (reinterpret_cast<uintptr_t>(workspace) & 1023) return set_error(h, GRL_EINVAL, "grl_basic_block_forward: workspace must be 1024-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* w = (uint8_t*)workspace;
+    auto BF = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(w + o); };
+    auto F32 = [&](size_t o) { return reinterpret_cast<float*>(w + o); };
+    const int R = n * HS;
+    nchw_to_planes_kernel<<<dim3(HC / 64, n), 256, 0, st>>>(x1, BF(L.z_hi), BF(L.z_lo), nullptr, 1.f, x2);
+    GRL_LAUNCH_CHECK(h);
+    GRL_TRY(split_planes(h, st, conv1_w, HC, BF(L.w1_hi), BF(L.w1_lo), HC, HB, HC));
+    GRL_TRY(split_planes(h, st, conv2_w, HB, BF(L.w2_hi), BF(L.w2_lo), HB, HB, HB));
+    GRL_TRY(split_planes(h, st, conv3_w, HB, BF(L.w3_hi), BF(L.w3_lo), HB, HC, HB));
+    struct Stage { const __nv_bfloat16 *a_hi, *a_lo; int K; const __nv_bfloat16 *w_hi, *w_lo; int N; float* hraw; const grl_bn_params* bn; float* stat;
+                   __nv_bfloat16 *p_hi, *p_lo; };
+    const Stage stages[3] = {
+        {BF(L.z_hi), BF(L.z_lo), HC, BF(L.w1_hi), BF(L.w1_lo), HB, F32(L.h1), bn1, F32(L.s1), BF(L.h1p_hi), BF(L.h1p_lo)},
+        {BF(L.h1p_hi), BF(L.h1p_lo), HB, BF(L.w2_hi), BF(L.w2_lo), HB, F32(L.h2), bn2, F32(L.s2), BF(L.h2p_hi), BF(L.h2p_lo)},
+        {BF(L.h2p_hi), BF(L.h2p_lo), HB, BF(L.w3_hi), BF(L.w3_lo), HC, F32(L.h3), bn3, F32(L.s3), nullptr, nullptr}};
+    for (int i = 0; i < 3; ++i) {
+        const Stage& S = stages[i];
+        GemmEpi e = epi_default();
+        e.C = S.hraw; e.ldc = S.N;
+        if (train) { e.col_sum = F32(L.pa); e.col_sq = F32(L.pb); }
+        Operand a{S.a_hi, S.a_lo, S.K, 0, 0}, b{S.w_hi, S.w_lo, S.K, 0, 0};
+        GRL_TRY(gemm_launch(h, st, R, S.N, S.K, 1, a, b, e, 0));
+        GRL_TRY(bn_finalize(h, st, F32(L.pa), F32(L.pb), 4 * n, 0, S.N, (double)R, bn_ptrs(*S.bn, *S.bn), S.stat, train, 1));
+        if (S.p_hi) {
+            bnrelu_split_kernel<<<dim3(S.N / 64, R / 128, 1), 256, 0, st>>>(S.hraw, S.stat, S.N, R, S.p_hi, S.p_lo);
+            GRL_LAUNCH_CHECK(h);
+        }
+    }
+    memo_update_kernel<<<dim3(HC / 64, n, 1), 256, 0, st>>>(F32(L.h3), F32(L.s3), BF(L.z_hi), BF(L.z_lo), nullptr, nullptr, 1, R, 0, 0, 0, BF(L.o_hi),
+                                                            BF(L.o_lo), nullptr, nullptr, nullptr);
+    GRL_LAUNCH_CHECK(h);
+    planes_to_nchw_kernel<<<dim3(HC / 64, n), 256, 0, st>>>(BF(L.o_hi), BF(L.o_lo), out);
+    GRL_LAUNCH_CHECK(h);
+    return GRL_OK;
 }

@@ -562,7 +562,8 @@ class Backbone(nn.Module):
 
 
 class BasicBlock(nn.Module):
-    """reid/models/grl_model.py:51-85 (parameter container; the math runs inside the fused TRL kernels)."""
+    """reid/models/grl_model.py:51-85.  Inside TRLBlock the math runs in the fused recurrence kernels (forward and backward);
+    called on its own, forward(x1, x2) runs one memory update through grl_basic_block_forward (forward only)."""
 
     def __init__(self, inplanes, planes, stride=1, downsample=None):
         super(BasicBlock, self).__init__()
@@ -573,6 +574,38 @@ class BasicBlock(nn.Module):
         self.conv3 = nn.Conv2d(planes, planes * 4, kernel_size=1, bias=False)
         self.bn3 = nn.BatchNorm2d(planes * 4)
         self.relu = nn.ReLU()
+
+    def forward(self, x1, x2):
+        """grl_model.py:67-85: relu(bn3(conv3(relu(bn2(conv2(relu(bn1(conv1(x1 + x2)))))))) + (x1 + x2)); x* [n, 2048, 16, 8]."""
+        if torch.is_grad_enabled() and (x1.requires_grad or x2.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError("grl_b200 BasicBlock.forward is forward-only (call it under torch.no_grad()); its gradients are "
+                               "computed inside TRLBlock's fused backward")
+        if not (x1.is_cuda and x2.is_cuda):
+            raise RuntimeError("grl_b200 head needs CUDA tensors (no CPU path exists)")
+        x1, x2 = x1.contiguous().float(), x2.contiguous().float()
+        if x1.shape != x2.shape or x1.dim() != 4 or tuple(x1.shape[1:]) != (2048, 16, 8) or self.conv1.weight.shape != (512, 2048, 1, 1):
+            raise RuntimeError("BasicBlock.forward: the memory block works on [n, 2048, 16, 8] maps, got %s / %s" % (tuple(x1.shape), tuple(x2.shape)))
+        lib = _lib.load_library()
+        dev, n = x1.device, x1.size(0)
+        bn = []
+        for m in (self.bn1, self.bn2, self.bn3):
+            r = _lib.BnParams()
+            r.weight, r.bias = m.weight.data_ptr(), m.bias.data_ptr()
+            r.running_mean, r.running_var = m.running_mean.data_ptr(), m.running_var.data_ptr()
+            bn.append(r)
+        with torch.cuda.device(dev):
+            h = _lib.get_handle(dev)
+            out = torch.empty_like(x1)
+            ws = _alloc_ws(int(lib.grl_basic_block_workspace_bytes(n)), dev)
+            rc = lib.grl_basic_block_forward(h, self.conv1.weight.data_ptr(), C.byref(bn[0]), self.conv2.weight.data_ptr(), C.byref(bn[1]),
+                                             self.conv3.weight.data_ptr(), C.byref(bn[2]), x1.data_ptr(), x2.data_ptr(), n,
+                                             1 if self.training else 0, out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+            _lib.check(h, rc, "grl_basic_block_forward")
+        if self.training:
+            with torch.no_grad():
+                for m in (self.bn1, self.bn2, self.bn3):
+                    m.num_batches_tracked += 1
+        return out
 
 
 class TRLBlock(nn.Module):

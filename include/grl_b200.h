@@ -282,6 +282,16 @@ typedef struct grl_head_grads {
  * (needed by grl_head_backward); 0 reuses one step slot (inference).                          */
 size_t grl_head_workspace_bytes(int B, int T, int save_for_backward);
 
+/* BasicBlock.forward(x1, x2)                 reid/models/grl_model.py:67-85 (the memory-update module of TRLBlock, :88-128)
+ *   relu(bn3(conv3(relu(bn2(conv2(relu(bn1(conv1(x1 + x2)))))))) + (x1 + x2));  x1, x2, out [n][2048][16][8] (NCHW fp32).
+ * conv1_w [512][2048], conv2_w [512][512], conv3_w [2048][512] (1x1, no bias); train = 1: batch statistics over the n*128
+ * pixels + running-buffer update (like one step of the recurrence), 0: running statistics.  Forward only: inside the head
+ * the block is differentiated by grl_head_backward / grl_trl_backward.                                                    */
+size_t grl_basic_block_workspace_bytes(int n);
+int grl_basic_block_forward(grl_handle* h, const float* conv1_w, const grl_bn_params* bn1, const float* conv2_w, const grl_bn_params* bn2,
+                            const float* conv3_w, const grl_bn_params* bn3, const float* x1, const float* x2, int n, int train,
+                            float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Fused GCE + TRL forward.
  *   Backbone.forward after self.base     reid/models/basebranch.py:56-68
  *   TRLBlock.forward                     reid/models/grl_model.py:131-180

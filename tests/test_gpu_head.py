@@ -491,3 +491,31 @@ def test_two_devices_in_one_process():
         outs.append((fu.cpu(), fc.cpu(), dx.cpu(), td.cpu(), ti.cpu()))
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_basic_block_forward_callable(training):
+    """BasicBlock.forward(x1, x2) (grl_model.py:67-85) on its own: one memory update through grl_basic_block_forward, against the
+    fp64 transcription of the reference module; train mode updates the running buffers like nn.BatchNorm2d."""
+    _, head, ho = _mods()
+    n = 5
+    blk = head.BasicBlock(2048, 512).cuda()
+    p = synth.make_head_params(0)
+    pre = "temporal_learning_block.uncorr_memo_forward."
+    sd = {k[len(pre):]: v for k, v in p.items() if k.startswith(pre)}
+    blk.load_state_dict(sd)
+    blk.train(training)
+    g = torch.Generator().manual_seed(3)
+    x1 = torch.relu(torch.randn((n, 2048, 16, 8), generator=g))
+    x2 = torch.relu(torch.randn((n, 2048, 16, 8), generator=g))
+    with torch.no_grad():
+        out = blk(x1.cuda(), x2.cuda())
+    p64 = {k: v.double().clone() for k, v in p.items()}
+    ref = ho._ref_basic_block(p64, pre[:-1], x1.double(), x2.double(), training)
+    assert out.shape == x1.shape and rel(out, ref) < 1e-4, rel(out, ref)
+    if training:
+        for k in ("bn1", "bn2", "bn3"):
+            assert rel(getattr(blk, k).running_var, p64[pre + k + ".running_var"]) < 2e-5, k
+            assert int(getattr(blk, k).num_batches_tracked) == 1
+    with pytest.raises(RuntimeError):
+        blk(x1.cuda().requires_grad_(True), x2.cuda())      # forward-only: gradients belong to TRLBlock's fused backward
