@@ -66,7 +66,15 @@ class OIMLoss(nn.Module):
         self.register_buffer('lut', torch.zeros(num_classes, num_features))
         self.size_average = size_average
 
+    #: F.cross_entropy / `self.lut[y]` in the reference raise on a label outside [0, num_classes); the kernels index the table with
+    #: it, so the range is checked first (one tiny device reduction + a read-back; set False to skip it in a tuned loop)
+    check_targets = True
+
     def forward(self, inputs, targets):
+        if self.check_targets and targets.numel():
+            lo, hi = int(targets.min()), int(targets.max())
+            if lo < 0 or hi >= self.num_classes:
+                raise IndexError("OIMLoss: target %d is out of bounds for %d classes" % (lo if lo < 0 else hi, self.num_classes))
         loss, logits = _OIMLossFunction.apply(inputs, targets, self.lut, self.scalar, self.momentum)
         return loss, logits
 

@@ -97,3 +97,13 @@ def test_losses_reject_unsupported_configurations():
         TripletLoss('soft', False)(torch.zeros((4, 8), device="cuda"), torch.zeros(4, dtype=torch.long, device="cuda"))
     with pytest.raises(NotImplementedError):
         OIMLoss(8, 4, weight=torch.ones(4))
+
+
+def test_oim_rejects_out_of_range_targets():
+    """A label outside [0, C) raises (the reference's F.cross_entropy / lut[y] do), instead of indexing the table with it."""
+    from grl_b200.losses import OIMLoss
+    crit = OIMLoss(64, 10, scalar=30.0).cuda()
+    x = torch.randn(4, 64, device="cuda")
+    for bad in (torch.tensor([0, 1, 10, 2]), torch.tensor([0, -1, 3, 2])):
+        with pytest.raises(IndexError):
+            crit(x, bad.cuda())
