@@ -177,6 +177,27 @@ def eval_fixture(att, eva, name, nq, ng_extra, dim, seed, noise, max_rank=100, q
     print("wrote", name, "mAP %.4f rank1 %.4f" % (mAP, cmc[0]))
 
 
+def eval_props_fixture(att, eva, name, nq, ng_extra, dim, seed, noise, topk=50):
+    """The reference's OTHER two evaluators on the same distance matrix (they are never called by the
+    live path, which makes them an independent cross-check of `evaluate`): `cmc(..., first_match_break=True)`
+    (eva_functions.py:18-78) counts the rank of the first true match exactly like `evaluate`'s CMC, and `mean_ap`
+    (:81-115, sklearn's average_precision_score) is the same mAP when no two distances tie."""
+    from grl_b200 import synth
+    qf, gf, qp, gp, qc, gc = synth.make_eval_set(nq, ng_extra, dim, seed=seed, num_ids=25, noise=noise, missing_query_frac=0.05)
+    gf = (gf + np.float32(1e-3) * np.random.default_rng(seed).standard_normal(gf.shape).astype(np.float32))   # break exact ties
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d_cos = att.cosin_dist(torch.from_numpy(qf), torch.from_numpy(gf)).numpy()
+    assert all(len(np.unique(r)) == len(r) for r in d_cos), "fixture needs a tie-free matrix"
+    with contextlib.redirect_stdout(io.StringIO()):
+        cmc_ev, map_ev = eva.evaluate(d_cos, qp, gp, qc, gc, max_rank=topk)
+    cmc_fmb = eva.cmc(d_cos, qp, gp, qc, gc, topk=topk, first_match_break=True)
+    map_sk = eva.mean_ap(d_cos, qp, gp, qc, gc)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), nq=nq, ng_extra=ng_extra, dim=dim, seed=seed, noise=noise, topk=topk,
+                        cmc_evaluate=cmc_ev, mAP_evaluate=map_ev, cmc_first_match_break=cmc_fmb, mAP_sklearn=map_sk)
+    print("wrote", name, "mAP evaluate %.6f sklearn %.6f | max |cmc - cmc_fmb| %.1e" % (map_ev, map_sk, np.abs(cmc_ev - cmc_fmb).max()))
+
+
 def tail_fixture(Model, name, n, T):
     """Eval feature tail on the REAL reference modules: model.corr_bn / uncorr_bn (grl_model.py:222-226) and
     reid.models.Siamese.Siamese(2048, 512, 2).self_attention (mars_train.py:77), all in eval mode, float64."""
@@ -321,6 +342,9 @@ def main():
         loss_fixture("loss_b32", 32, 2048, 625, seed=21, n_ids=8)
         loss_fixture("loss_b12", 12, 256, 40, seed=22, n_ids=5)
         return
+    if "--eval-props" in sys.argv:         # only the evaluator cross-check fixture
+        eval_props_fixture(att, eva, "eval_props", 80, 400, 64, seed=6, noise=1.5)
+        return
     if "--full-size" in sys.argv:          # only the benchmark-size head fixture (minutes, ~25 GB of RAM)
         head_fixture_full_size(Model)
         return
@@ -334,6 +358,7 @@ def main():
     # fewer than max_rank gallery rows, so "num_g < max_rank" (:136-138) cannot be pinned; use max_rank=10.
     eval_fixture(att, eva, "eval_rank10", 20, 100, 32, seed=4, noise=1.0, max_rank=10)
     eval_fixture(att, eva, "eval_ties", 40, 160, 16, seed=5, noise=1.0, quantize=8)  # exact ties
+    eval_props_fixture(att, eva, "eval_props", 80, 400, 64, seed=6, noise=1.5)
     siamese_fixture("siamese_n32t8", 32, 8, seed=31)
     siamese_fixture("siamese_n6t3", 6, 3, seed=32)
     loss_fixture("loss_b32", 32, 2048, 625, seed=21, n_ids=8)

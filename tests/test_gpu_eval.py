@@ -515,3 +515,21 @@ def test_second_chance_proves_clustered_queries(metric):
     v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q2, g2, metric), k)
     assert np.array_equal(i2.cpu().numpy(), i_ref) and np.array_equal(d2.cpu().numpy(), v_ref)
     assert int(stats[5]) >= 1
+
+
+def test_evaluate_property_checks_vs_reference_cmc_and_mean_ap(golden_dir):
+    """SURVEY.md section 4 property tests on the GPU path: `evaluate` agrees with the reference's independent evaluators
+    cmc(first_match_break=True) and mean_ap (sklearn) as computed by the REAL reference (tests/golden/eval_props.npz), and is
+    invariant under a permutation of the gallery (tie-free matrix)."""
+    _, ev = _mods()
+    g = np.load(os.path.join(golden_dir, "eval_props.npz"))
+    qf, gf, qp, gp, qc, gc = synth.make_eval_set(int(g["nq"]), int(g["ng_extra"]), int(g["dim"]), seed=int(g["seed"]), num_ids=25,
+                                                 noise=float(g["noise"]), missing_query_frac=0.05)
+    gf = gf + np.float32(1e-3) * np.random.default_rng(int(g["seed"])).standard_normal(gf.shape).astype(np.float32)
+    topk = int(g["topk"])
+    d = ev.cosin_dist(torch.from_numpy(qf).cuda(), torch.from_numpy(gf).cuda())
+    cmc, mAP = ev.evaluate(d, qp, gp, qc, gc, topk)
+    assert np.abs(cmc - g["cmc_first_match_break"]).max() < 1e-4 and abs(mAP - float(g["mAP_sklearn"])) < 1e-4
+    perm = np.random.default_rng(0).permutation(gf.shape[0])
+    cmc_p, mAP_p = ev.evaluate(d[:, torch.from_numpy(perm).cuda()].contiguous(), qp, gp[perm], qc, gc[perm], topk)
+    assert np.array_equal(cmc_p, cmc) and abs(mAP_p - mAP) < 1e-12

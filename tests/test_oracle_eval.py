@@ -84,3 +84,29 @@ def test_two_stage_search_with_skipped_rescores_is_exact(metric, dup):
     assert n_with < n_without                                               # ... and it does skip work
     if dup:
         assert flags[:6].all()
+
+
+def _props_inputs(g):
+    qf, gf, qp, gp, qc, gc = synth.make_eval_set(int(g["nq"]), int(g["ng_extra"]), int(g["dim"]), seed=int(g["seed"]), num_ids=25,
+                                                 noise=float(g["noise"]), missing_query_frac=0.05)
+    gf = gf + np.float32(1e-3) * np.random.default_rng(int(g["seed"])).standard_normal(gf.shape).astype(np.float32)
+    return qf, gf, qp, gp, qc, gc
+
+
+def test_evaluate_agrees_with_the_references_other_evaluators(golden_dir):
+    """the reference carries two more evaluators that the live path never calls -- cmc(first_match_break=True)
+    (eva_functions.py:18-78) and mean_ap (:81-115, sklearn's average_precision_score).  On a tie-free matrix they must agree
+    with `evaluate`; the fixture holds all three as computed by the REAL reference, the oracle (both forms) must match them."""
+    g = np.load(os.path.join(golden_dir, "eval_props.npz"))
+    qf, gf, qp, gp, qc, gc = _props_inputs(g)
+    topk = int(g["topk"])
+    assert np.abs(g["cmc_evaluate"] - g["cmc_first_match_break"]).max() < 1e-6 and abs(float(g["mAP_evaluate"]) - float(g["mAP_sklearn"])) < 1e-12
+    d = eo.cosin_dist(qf, gf)
+    cmc, mAP = eo.evaluate_literal(d, qp, gp, qc, gc, topk)
+    assert np.abs(cmc - g["cmc_first_match_break"]).max() < 1e-6 and abs(mAP - float(g["mAP_sklearn"])) < 1e-9
+    cmc2, mAP2, _, _ = eo.evaluate_rankcount(d, qp, gp, qc, gc, topk)
+    assert np.abs(cmc2 - g["cmc_first_match_break"]).max() < 1e-6 and abs(mAP2 - float(g["mAP_sklearn"])) < 1e-9
+    # gallery-permutation invariance (tie-free): the metrics depend on the set of gallery rows, not on their order
+    perm = np.random.default_rng(0).permutation(gf.shape[0])
+    cmc3, mAP3, _, _ = eo.evaluate_rankcount(d[:, perm], qp, gp[perm], qc, gc[perm], topk)
+    assert np.array_equal(cmc3, cmc2) and abs(mAP3 - mAP2) < 1e-12
