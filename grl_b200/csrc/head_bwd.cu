@@ -254,12 +254,14 @@ __global__ void __launch_bounds__(256) trl_bwd_f1_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ srcA, const float* __restrict__ srcB,
                                                             const __nv_bfloat16* __restrict__ mask_hi, const float* __restrict__ hraw,
                                                             const float* __restrict__ stat, int Cn, int R, float* __restrict__ psum,
-                                                            float* __restrict__ pxh) {
+                                                            float* __restrict__ pxh, unsigned int* __restrict__ scal) {
     __shared__ float red[32 * 65];
+    __shared__ float wmx[2][8];
     const int z = blockIdx.z, c0 = blockIdx.x * 64;
     const Tile t;
     const float* st = stat + (size_t)z * 4 * Cn;
     float mean[8], rstd[8], as[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ax[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float gmax = 0.f, xmax = 0.f;
     load8(st + 2 * Cn + c0 + t.cg * 8, mean); load8(st + 3 * Cn + c0 + t.cg * 8, rstd);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -277,18 +279,33 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float gv = mk[i] > 0.f ? g[i] : 0.f;
+            const float xh = (h[i] - mean[i]) * rstd[i];
             as[i] += gv;
-            ax[i] += gv * (h[i] - mean[i]) * rstd[i];
+            ax[i] += gv * xh;
+            gmax = fmaxf(gmax, fabsf(gv)); xmax = fmaxf(xmax, fabsf(xh));
         }
     }
     const size_t pidx = ((size_t)z * gridDim.y + blockIdx.y) * Cn + c0;
     tile_colsum(as, red, psum + pidx, t);
     tile_colsum(ax, red, pxh + pidx, t);
+    if (scal) {     // scal[0] = max |g|, scal[1] = max |xhat| over the launch: bn_bwd_finalize turns them into a bound on |dH|
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) { gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, off)); }
+        if (lane_id() == 0) { wmx[0][threadIdx.x >> 5] = gmax; wmx[1][threadIdx.x >> 5] = xmax; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = 0.f, b = 0.f;
+            for (int i = 0; i < 8; ++i) { a = fmaxf(a, wmx[0][i]); b = fmaxf(b, wmx[1][i]); }
+            if (a == a && a > 0.f) atomicMax(scal + 0, __float_as_uint(a));
+            if (b == b && b > 0.f) atomicMax(scal + 1, __float_as_uint(b));
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ pxh, int nparts, int Cn,
                                                               double count, BnPtrs2 bp, const float* __restrict__ stat,
-                                                              float* __restrict__ kcoef, OutPtrs2 dgamma, OutPtrs2 dbeta, int accumulate) {
+                                                              float* __restrict__ kcoef, OutPtrs2 dgamma, OutPtrs2 dbeta, int accumulate,
+                                                              unsigned int* __restrict__ scal) {
     __shared__ double sh[2][8][33];
     const int z = blockIdx.y;
     const int c = blockIdx.x * 32 + threadIdx.x;          // block (32, 8): 8 lanes share the partials of a channel
@@ -309,6 +326,10 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
     kc[c] = bp.gamma[z][c] * rstd;
     kc[Cn + c] = (float)(s / count);
     kc[2 * Cn + c] = (float)(x / count);
+    if (scal) {     // |dH| = |k0 (g - k1 - xhat k2)| <= |k0| (max|g| + |k1| + max|xhat| |k2|): scal[2] = the largest such bound
+        const float bnd = 1.01f * fabsf(kc[c]) * (__uint_as_float(scal[0]) + fabsf(kc[Cn + c]) + __uint_as_float(scal[1]) * fabsf(kc[2 * Cn + c]));
+        if (bnd == bnd && bnd > 0.f) atomicMax(scal + 2, __float_as_uint(bnd));
+    }
     if (accumulate) { dgamma.p[z][c] += (float)x; dbeta.p[z][c] += (float)s; }
     else { dgamma.p[z][c] = (float)x; dbeta.p[z][c] = (float)s; }
 }
@@ -317,11 +338,20 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const __nv_bfloat16* __restrict__ mask_hi, const float* __restrict__ hraw,
                                                            const float* __restrict__ stat, const float* __restrict__ kcoef, int Cn, int R,
                                                            __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                                                           float* __restrict__ g_out) {
+                                                           float* __restrict__ g_out, float* __restrict__ scal, __half* __restrict__ out16) {
     const int z = blockIdx.z, c0 = blockIdx.x * 64;
     const Tile t;
     const float* st = stat + (size_t)z * 4 * Cn;
     const float* kc = kcoef + (size_t)z * 3 * Cn;
+    float sc16 = 1.f;
+    if (out16) {    // one more copy of dH as ONE fp16 plane (the operand of the single-pass weight-gradient GEMM): power-of-two scale
+                    // from the bound in scal[2]; scal[3] = 1 / scale for that GEMM's epilogue
+        const unsigned int mb = __float_as_uint(scal[2]);
+        int ex = (int)((mb >> 23) & 0xff) - 127;
+        if (mb == 0 || ((mb >> 23) & 0xff) == 0xff) ex = 14;
+        sc16 = ldexpf(1.f, 14 - ex);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) scal[3] = ldexpf(1.f, ex - 14);
+    }
     float mean[8], rstd[8], k0[8], k1[8], k2[8];
     load8(st + 2 * Cn + c0 + t.cg * 8, mean); load8(st + 3 * Cn + c0 + t.cg * 8, rstd);
     load8(kc + c0 + t.cg * 8, k0); load8(kc + Cn + c0 + t.cg * 8, k1); load8(kc + 2 * Cn + c0 + t.cg * 8, k2);
@@ -344,6 +374,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
             o[i] = k0[i] * (g[i] - k1[i] - (h[i] - mean[i]) * rstd[i] * k2[i]);
         }
         store8_planes(out_hi + off, out_lo + off, o);
+        if (out16) store8_f16(out16 + off, o, sc16);
         if (g_out) store8(g_out + off, g);
     }
 }
@@ -746,17 +777,19 @@ __global__ void __launch_bounds__(256) pm_to_nchw_bias_kernel(const float* __res
 static int bn_backward(grl_handle* h, cudaStream_t st, const HeadWs& w, const float* srcA, const float* srcB, const __nv_bfloat16* mask_hi,
                        const float* hraw, const float* stat, int Cn, const float* gamma0, const float* gamma1, float* dgamma0,
                        float* dgamma1, float* dbeta0, float* dbeta1, int accumulate, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
-                       float* g_out) {
+                       float* g_out, float* scal = nullptr, __half* out16 = nullptr) {
+    // scal (4 floats, zeroed by the caller): max |g|, max |xhat|, bound of |dH|, 1 / scale of the fp16 copy `out16`
     const int R = w.R, B = w.B;
     dim3 grid(Cn / 64, R / 128, 2);
-    bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(srcA, srcB, mask_hi, hraw, stat, Cn, R, WS_F32(w, part_a), WS_F32(w, part_b));
+    unsigned int* su = reinterpret_cast<unsigned int*>(scal);
+    bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(srcA, srcB, mask_hi, hraw, stat, Cn, R, WS_F32(w, part_a), WS_F32(w, part_b), su);
     GRL_LAUNCH_CHECK(h);
     BnPtrs2 bp; bp.gamma[0] = gamma0; bp.gamma[1] = gamma1;
     OutPtrs2 dg, db; dg.p[0] = dgamma0; dg.p[1] = dgamma1; db.p[0] = dbeta0; db.p[1] = dbeta1;
     bn_bwd_finalize_kernel<<<dim3((Cn + 31) / 32, 2), dim3(32, 8), 0, st>>>(WS_F32(w, part_a), WS_F32(w, part_b), B, Cn, (double)R, bp, stat,
-                                                                      WS_F32(w, kcoef), dg, db, accumulate);
+                                                                      WS_F32(w, kcoef), dg, db, accumulate, su);
     GRL_LAUNCH_CHECK(h);
-    bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(srcA, srcB, mask_hi, hraw, stat, WS_F32(w, kcoef), Cn, R, out_hi, out_lo, g_out);
+    bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(srcA, srcB, mask_hi, hraw, stat, WS_F32(w, kcoef), Cn, R, out_hi, out_lo, g_out, scal, out16);
     GRL_LAUNCH_CHECK(h);
     return GRL_OK;
 }
@@ -796,7 +829,7 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
     // ---------------- squeeze-excite backward for every step (independent of the recurrence) ----------------
     {
         SePtrsB sp; sp.l1[0] = p->se1_w[0]; sp.l1[1] = p->se1_w[1]; sp.l2[0] = p->se2_w[0]; sp.l2[1] = p->se2_w[1];
-        GRL_CUDA(h, cudaMemsetAsync(WS_F32(w, f16_scal), 0, 8, st));      // [0] bound of |dF1|, |dF2| (bits), [1] 1 / their scale
+        GRL_CUDA(h, cudaMemsetAsync(WS_F32(w, f16_scal), 0, (size_t)(64 + 12 * T) * 4, st));   // [0] bound of |dF1|, |dF2| (bits), [1] 1 / their scale; ...
         se_bwd_kernel<<<dim3(B, 2, T), 256, 0, st>>>(d_f_corr, WS_F32(w, gc), WS_F32(w, se_a), WS_F32(w, se_h), sp, B, T, WS_F32(w, se_ds),
                                                      WS_F32(w, se_dh), WS_F32(w, se_dq), WS_F32(w, se_q),
                                                      reinterpret_cast<unsigned int*>(WS_F32(w, f16_scal)));
@@ -872,12 +905,23 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
         __nv_bfloat16 *dh3_hi = WS_BF(w, dh3_hi) + (size_t)i * slotM, *dh3_lo = WS_BF(w, dh3_lo) + (size_t)i * slotM;
         __nv_bfloat16 *dh2_hi = WS_BF(w, dh2_hi) + (size_t)i * slotB, *dh2_lo = WS_BF(w, dh2_lo) + (size_t)i * slotB;
         __nv_bfloat16 *dh1_hi = WS_BF(w, dh1_hi) + (size_t)i * slotB, *dh1_lo = WS_BF(w, dh1_lo) + (size_t)i * slotB;
+        // single-pass fp16 operands of this step's three weight-gradient GEMMs (leaf sums, no error propagation):
+        // dH as scaled fp16 from bn_bwd_apply, the activations as fp16 planes from the forward; 4 scalars per BatchNorm and step
+        __half* dh3_16 = reinterpret_cast<__half*>(WS_BF(w, dh3_16)) + (size_t)i * slotM;
+        __half* dh2_16 = reinterpret_cast<__half*>(WS_BF(w, dh2_16)) + (size_t)i * slotB;
+        __half* dh1_16 = reinterpret_cast<__half*>(WS_BF(w, dh1_16)) + (size_t)i * slotB;
+        const __half* h2p_16 = reinterpret_cast<const __half*>(WS_BF(w, h2p_16)) + (size_t)i * slotB;
+        const __half* h1p_16 = reinterpret_cast<const __half*>(WS_BF(w, h1p_16)) + (size_t)i * slotB;
+        const __half* z_16 = reinterpret_cast<const __half*>(WS_BF(w, z_16)) + (size_t)i * slotM;
+        float* sc3 = WS_F32(w, f16_scal) + 64 + (size_t)(i * 3 + 0) * 4;
+        float* sc2 = WS_F32(w, f16_scal) + 64 + (size_t)(i * 3 + 1) * 4;
+        float* sc1 = WS_F32(w, f16_scal) + 64 + (size_t)(i * 3 + 2) * 4;
 
         // ---- critical path (caller's stream) ----
         if (two && !first) GRL_TRY(ev_wait(h, EV_DMEM(i + 1), st));
         // bn3 + residual ReLU:  dPre = dMn [Mn>0] -> dz (fp32);  dH3 planes
         GRL_TRY(bn_backward(h, st, w, dmem_in, dz_prev, memn_hi, h3, s3, HC, p->memo_bn3[0].weight, p->memo_bn3[1].weight, g->memo_bn3_w[0],
-                            g->memo_bn3_w[1], g->memo_bn3_b[0], g->memo_bn3_b[1], acc, dh3_hi, dh3_lo, dz));
+                            g->memo_bn3_w[1], g->memo_bn3_b[0], g->memo_bn3_b[1], acc, dh3_hi, dh3_lo, dz, sc3, dh3_16));
         if (two) GRL_TRY(ev_record(h, EV_DH3(i), st));
         {   // conv3 dgrad: dH2p = dH3 Wc3
             GemmEpi e = epi_default();
@@ -886,7 +930,7 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
             GRL_TRY(gemm_launch(h, st, R, HB, HC, 2, a, b, e, 0));
         }
         GRL_TRY(bn_backward(h, st, w, WS_F32(w, dh2p), nullptr, h2p_hi, h2, s2, HB, p->memo_bn2[0].weight, p->memo_bn2[1].weight,
-                            g->memo_bn2_w[0], g->memo_bn2_w[1], g->memo_bn2_b[0], g->memo_bn2_b[1], acc, dh2_hi, dh2_lo, nullptr));
+                            g->memo_bn2_w[0], g->memo_bn2_w[1], g->memo_bn2_b[0], g->memo_bn2_b[1], acc, dh2_hi, dh2_lo, nullptr, sc2, dh2_16));
         if (two) GRL_TRY(ev_record(h, EV_DH2(i), st));
         {   // conv2 dgrad
             GemmEpi e = epi_default();
@@ -895,7 +939,7 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
             GRL_TRY(gemm_launch(h, st, R, HB, HB, 2, a, b, e, 0));
         }
         GRL_TRY(bn_backward(h, st, w, WS_F32(w, dh1p), nullptr, h1p_hi, h1, s1, HB, p->memo_bn1[0].weight, p->memo_bn1[1].weight,
-                            g->memo_bn1_w[0], g->memo_bn1_w[1], g->memo_bn1_b[0], g->memo_bn1_b[1], acc, dh1_hi, dh1_lo, nullptr));
+                            g->memo_bn1_w[0], g->memo_bn1_w[1], g->memo_bn1_b[0], g->memo_bn1_b[1], acc, dh1_hi, dh1_lo, nullptr, sc1, dh1_16));
         if (two) GRL_TRY(ev_record(h, EV_DH1(i), st));
         {   // conv1 dgrad: dZ = dPre + dH1 Wc1   (accumulates onto dPre)
             GemmEpi e = epi_default();
@@ -909,22 +953,22 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
         {   // conv3 wgrad: gw_c3[z] (+)= dH3^T H2p
             GemmEpi e = epi_default();
             e.C = WS_F32(w, gw_c3); e.ldc = HB; e.c_bstride = (long long)HC * HB; e.accumulate = acc;
-            Operand a{dh3_hi, dh3_lo, HC, (long long)R * HC, 1}, b{h2p_hi, h2p_lo, HB, (long long)R * HB, 1};
-            GRL_TRY(gemm_launch(h, sd, HC, HB, R, 2, a, b, e, 0));
+            e.dscale_a = sc3 + 3;
+            GRL_TRY(gemm_launch_x1(h, sd, HC, HB, R, 2, dh3_16, HC, (long long)R * HC, 1, h2p_16, HB, (long long)R * HB, 1, e));
         }
         if (two) GRL_TRY(ev_wait(h, EV_DH2(i), sd));
         {   // conv2 wgrad
             GemmEpi e = epi_default();
             e.C = WS_F32(w, gw_c2); e.ldc = HB; e.c_bstride = (long long)HB * HB; e.accumulate = acc;
-            Operand a{dh2_hi, dh2_lo, HB, (long long)R * HB, 1}, b{h1p_hi, h1p_lo, HB, (long long)R * HB, 1};
-            GRL_TRY(gemm_launch(h, sd, HB, HB, R, 2, a, b, e, 0));
+            e.dscale_a = sc2 + 3;
+            GRL_TRY(gemm_launch_x1(h, sd, HB, HB, R, 2, dh2_16, HB, (long long)R * HB, 1, h1p_16, HB, (long long)R * HB, 1, e));
         }
         if (two) GRL_TRY(ev_wait(h, EV_DH1(i), sd));
         {   // conv1 wgrad: gw_c1[z] (+)= dH1^T Z
             GemmEpi e = epi_default();
             e.C = WS_F32(w, gw_c1); e.ldc = HC; e.c_bstride = (long long)HB * HC; e.accumulate = acc;
-            Operand a{dh1_hi, dh1_lo, HB, (long long)R * HB, 1}, b{z_hi, z_lo, HC, (long long)R * HC, 1};
-            GRL_TRY(gemm_launch(h, sd, HB, HC, R, 2, a, b, e, 0));
+            e.dscale_a = sc1 + 3;
+            GRL_TRY(gemm_launch_x1(h, sd, HB, HC, R, 2, dh1_16, HB, (long long)R * HB, 1, z_16, HC, (long long)R * HC, 1, e));
         }
     }
     // ---------------- parameter gradients accumulated over the steps; f2 over all frames (side stream) ----------------

@@ -67,7 +67,10 @@ constexpr float BN_MOM = 0.1f;
     X(gsmall, 4, BW * 8192)                                                                        \
     /* --- single-plane fp16 operands of the f1 / f2 gradient GEMMs (one MMA per k-step) + their device-side scales --- */ \
     X(df1_16, 2, BW * 2 * R * HC) X(mem_16, 2, BW * SLM * 2 * R * HC) X(df2_16, 2, BW * P * 2 * HC) X(xc_16, 2, BW * P * HC) \
-    X(wf1_16, 2, BW * 2 * HC * HC) X(wf2_16, 2, BW * 2 * HC * HC) X(f16_scal, 4, BW * 64)
+    X(wf1_16, 2, BW * 2 * HC * HC) X(wf2_16, 2, BW * 2 * HC * HC) X(f16_scal, 4, BW * (64 + 12 * T))  \
+    /* --- ... and of the memory block's WEIGHT gradients: activations (written by the training forward), gradients (bn_bwd_apply) --- */ \
+    X(h1p_16, 2, BW * SL * 2 * R * HB) X(h2p_16, 2, BW * SL * 2 * R * HB) X(z_16, 2, BW * SLZ * 2 * R * HC)            \
+    X(dh3_16, 2, BW * T * 2 * R * HC) X(dh2_16, 2, BW * T * 2 * R * HB) X(dh1_16, 2, BW * T * 2 * R * HB)
 
 struct HeadWs {
     int B, T, N, P, R, save, SL, SLM, SLZ;

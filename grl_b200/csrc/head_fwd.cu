@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) gap_planes_kernel(const __nv_bfloat16* __
 __global__ void __launch_bounds__(256) trl_init_kernel(const __nv_bfloat16* __restrict__ uh, const __nv_bfloat16* __restrict__ ul, int T, int R,
                                                        __nv_bfloat16* __restrict__ mem_hi, __nv_bfloat16* __restrict__ mem_lo,
                                                        __nv_bfloat16* __restrict__ z_hi, __nv_bfloat16* __restrict__ z_lo,
-                                                       __half* __restrict__ mem16) {
+                                                       __half* __restrict__ mem16, __half* __restrict__ z16) {
     const int b = blockIdx.y, c0 = blockIdx.x * 64;
     const Tile t;
     float acc[4][8], first[4][8], last[4][8];
@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(256) trl_init_kernel(const __nv_bfloat16* __re
         if (mem16) { store8_f16(mem16 + off, m0); store8_f16(mem16 + dstride + off, m0); }   // the f1 weight-gradient operand (training)
         store8_planes(z_hi + off, z_lo + off, zf);
         store8_planes(z_hi + dstride + off, z_lo + dstride + off, zb);
+        if (z16) { store8_f16(z16 + off, zf); store8_f16(z16 + dstride + off, zb); }
     }
 }
 
@@ -420,7 +421,8 @@ __global__ void __launch_bounds__(SE_THREADS) se_fwd_kernel(const float* __restr
 
 // ------------------------------------------------------------------ BN + ReLU + re-split   grid (Cn/64, R/128, 2)
 __global__ void __launch_bounds__(256) bnrelu_split_kernel(const float* __restrict__ hraw, const float* __restrict__ stat, int Cn, int R,
-                                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                           __half* __restrict__ p16 = nullptr) {
     const int z = blockIdx.z, c0 = blockIdx.x * 64;
     const Tile t;
     const float* st = stat + (size_t)z * 4 * Cn;
@@ -434,6 +436,7 @@ __global__ void __launch_bounds__(256) bnrelu_split_kernel(const float* __restri
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = fmaxf(a[i] * v[i] + c[i], 0.f);
         store8_planes(hi + off, lo + off, v);
+        if (p16) store8_f16(p16 + off, v);            // training: the operand of the single-pass weight-gradient GEMM
     }
 }
 
@@ -445,7 +448,7 @@ __global__ void __launch_bounds__(256) memo_update_kernel(const float* __restric
                                                           int has_next, int tau_next0, int tau_next1,
                                                           __nv_bfloat16* __restrict__ mem_hi, __nv_bfloat16* __restrict__ mem_lo,
                                                           __nv_bfloat16* __restrict__ zn_hi, __nv_bfloat16* __restrict__ zn_lo,
-                                                          __half* __restrict__ mem16) {
+                                                          __half* __restrict__ mem16, __half* __restrict__ zn16 = nullptr) {
     const int z = blockIdx.z, b = blockIdx.y, c0 = blockIdx.x * 64;
     const Tile t;
     const float* st = stat3 + (size_t)z * 4 * HC;
@@ -470,6 +473,7 @@ __global__ void __launch_bounds__(256) memo_update_kernel(const float* __restric
 #pragma unroll
             for (int i = 0; i < 8; ++i) xu[i] += mn[i];
             store8_planes(zn_hi + off, zn_lo + off, xu);
+            if (zn16) store8_f16(zn16 + off, xu);
         }
     }
 }
@@ -660,8 +664,11 @@ static int trl_forward_part(grl_handle* h, cudaStream_t st, const grl_head_param
     const size_t slotM = (size_t)2 * R * HC;     // elements per mem / z slot (both directions)
     // training keeps every memory slot also as ONE fp16 plane: the operand of the single-pass f1 weight-gradient GEMM (head_bwd.cu)
     __half* mem16 = w.save ? reinterpret_cast<__half*>(WS_BF(w, mem_16)) : nullptr;
+    __half* z16 = w.save ? reinterpret_cast<__half*>(WS_BF(w, z_16)) : nullptr;
+    __half* h1p16 = w.save ? reinterpret_cast<__half*>(WS_BF(w, h1p_16)) : nullptr;
+    __half* h2p16 = w.save ? reinterpret_cast<__half*>(WS_BF(w, h2p_16)) : nullptr;
     trl_init_kernel<<<dim3(HC / 64, B), 256, 0, st>>>(WS_BF(w, xu_hi), WS_BF(w, xu_lo), T, R, WS_BF(w, mem_hi), WS_BF(w, mem_lo),
-                                                      WS_BF(w, z_hi), WS_BF(w, z_lo), mem16);
+                                                      WS_BF(w, z_hi), WS_BF(w, z_lo), mem16, z16);
     GRL_LAUNCH_CHECK(h);
     if (two) GRL_TRY(ev_record(h, EV_M(0), st));
     const int save = w.save;
@@ -703,7 +710,8 @@ static int trl_forward_part(grl_handle* h, cudaStream_t st, const grl_head_param
             GRL_TRY(gemm_launch(h, st, R, HB, HC, 2, a, b, e, 0));
             GRL_TRY(bn_finalize(h, st, WS_F32(w, part_a), WS_F32(w, part_b), 4 * B, (long long)4 * B * HB, HB, (double)R,
                                 bn_ptrs(p->memo_bn1[0], p->memo_bn1[1]), s1, train, 2));
-            bnrelu_split_kernel<<<dim3(HB / 64, R / 128, 2), 256, 0, st>>>(h1, s1, HB, R, h1ph, h1pl);
+            bnrelu_split_kernel<<<dim3(HB / 64, R / 128, 2), 256, 0, st>>>(h1, s1, HB, R, h1ph, h1pl,
+                                                                           h1p16 ? h1p16 + (size_t)sl * 2 * R * HB : nullptr);
             GRL_LAUNCH_CHECK(h);
         }
         {
@@ -714,7 +722,8 @@ static int trl_forward_part(grl_handle* h, cudaStream_t st, const grl_head_param
             GRL_TRY(gemm_launch(h, st, R, HB, HB, 2, a, b, e, 0));
             GRL_TRY(bn_finalize(h, st, WS_F32(w, part_a), WS_F32(w, part_b), 4 * B, (long long)4 * B * HB, HB, (double)R,
                                 bn_ptrs(p->memo_bn2[0], p->memo_bn2[1]), s2, train, 2));
-            bnrelu_split_kernel<<<dim3(HB / 64, R / 128, 2), 256, 0, st>>>(h2, s2, HB, R, h2ph, h2pl);
+            bnrelu_split_kernel<<<dim3(HB / 64, R / 128, 2), 256, 0, st>>>(h2, s2, HB, R, h2ph, h2pl,
+                                                                           h2p16 ? h2p16 + (size_t)sl * 2 * R * HB : nullptr);
             GRL_LAUNCH_CHECK(h);
         }
         {
@@ -733,7 +742,8 @@ static int trl_forward_part(grl_handle* h, cudaStream_t st, const grl_head_param
                                                                 T - 2 - i, WS_BF(w, mem_hi) + ms_next * slotM, WS_BF(w, mem_lo) + ms_next * slotM,
                                                                 WS_BF(w, z_hi) + (has_next ? zs_next : zs) * slotM,
                                                                 WS_BF(w, z_lo) + (has_next ? zs_next : zs) * slotM,
-                                                                mem16 ? mem16 + ms_next * slotM : nullptr);
+                                                                mem16 ? mem16 + ms_next * slotM : nullptr,
+                                                                (z16 && has_next) ? z16 + zs_next * slotM : nullptr);
         GRL_LAUNCH_CHECK(h);
         if (two) GRL_TRY(ev_record(h, EV_M(i + 1), st));
     }

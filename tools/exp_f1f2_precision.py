@@ -80,7 +80,8 @@ for name, mm in VARIANTS.items() if "--all" in sys.argv else []:
 # ---- the memory block (conv1/2/3 of BasicBlock): f1/f2 as adopted (forward x3, gradients fp16 x1) + block variants
 adopted = VARIANTS["fwd x3, dgrad+wgrad fp16 x1"]
 print("memory block variants (f1/f2 as adopted):")
-for name, blk in (("block fwd exact, dgrad+wgrad fp16 x1", mixed(torch.matmul, f16mm, f16mm)), ("block all x3", mixed(x3, x3, x3)), ("block fwd x3, dgrad+wgrad fp16 x1", mixed(x3, f16mm, f16mm)),
+for name, blk in (("block fwd exact, wgrad fp16 x1", mixed(torch.matmul, torch.matmul, f16mm)),
+                  ("block fwd exact, dgrad+wgrad fp16 x1", mixed(torch.matmul, f16mm, f16mm)), ("block all x3", mixed(x3, x3, x3)), ("block fwd x3, dgrad+wgrad fp16 x1", mixed(x3, f16mm, f16mm)),
                   ("block fwd x3, wgrad fp16 x1", mixed(x3, x3, f16mm)), ("block all fp16 x1", mixed(f16mm, f16mm, f16mm))):
     o = run(adopted, blk)
     worst = sorted(((rel(o["grads"][k], ref["grads"][k]), k) for k in ref["grads"] if float(ref["grads"][k].norm()) > 1e-9), reverse=True)
