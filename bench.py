@@ -42,8 +42,8 @@ B_HEAD, T_HEAD = 32, 8
 ALG_FLOPS_PER_CLIP_FWD_BWD = 146.6e9        # 48.9 GFLOP/clip forward (F1 form), x3 with backward
 METRIC = "GRL head clips/s fwd+bwd (B32,T8)"
 # MMAs issued per algorithmic product over one step: 3 (split-bf16) everywhere except the f1/f2 weight / input gradients
-# (2 x 34.4 of the 146.6 GFLOP per clip), which run as one fp16 MMA
-ISSUED_MMA_PER_ALG_FLOP = (3.0 * (146.6 - 68.8) + 1.0 * 68.8) / 146.6
+# (2 x 34.4 of the 146.6 GFLOP per clip) and the memory block's weight gradients (9.66), which run as one fp16 MMA
+ISSUED_MMA_PER_ALG_FLOP = (3.0 * (146.6 - 68.8 - 9.66) + 1.0 * (68.8 + 9.66)) / 146.6
 
 
 def parse():
@@ -311,7 +311,7 @@ def run_ours(args):
                 "issued_frac": issued_per_alg * achieved / peaks["tflops"],
                 "note": "achieved = algorithmic 2*M*N*K per launch / event-timed launch duration, averaged over %d launches of %d "
                         "profiled single-stream steps run right after the timed region; split-bf16 contractions issue 3 MMAs per algorithmic "
-                        "product (fp32-grade accuracy), the f1/f2 gradient GEMMs one: %.2f issued per algorithmic FLOP over the step, so "
+                        "product (fp32-grade accuracy), the f1/f2 gradient GEMMs and the memory block's weight gradients one: %.2f issued per algorithmic FLOP over the step, so "
                         "frac <= %.2f by construction and issued_frac is the tensor-pipe load"
                         % (g_n.value, PROF_STEPS, issued_per_alg, 1.0 / issued_per_alg),
                 "gemm_share_of_step": g_ms.value / p0.elapsed_time(p1),
@@ -753,10 +753,10 @@ def run_ours(args):
                            "parallelism": "dp%d" % world,
                            "arithmetic": "fp32 in/out; every forward contraction and the gradients of the memory block / GCE: split-bf16 "
                                          "(hi+lo planes, 3 tcgen05 MMAs per product) with fp32 TMEM accumulation; the weight and input "
-                                         "gradients of the attention convs f1/f2 (47% of the algorithmic FLOPs): ONE fp16 MMA per product with "
-                                         "device-chosen power-of-two scales -- emulated on the fp64 oracle, that leaves every output and "
-                                         "gradient where the 3-MMA form puts them (tools/exp_f1f2_precision.py, DESIGN.md section 4); all head "
-                                         "parity gates unchanged",
+                                         "gradients of the attention convs f1/f2 and the weight gradients of the memory block (54% of the algorithmic "
+                                         "FLOPs): ONE fp16 MMA per product with device-chosen power-of-two scales -- emulated on the fp64 oracle, "
+                                         "that leaves every output and gradient where the 3-MMA form puts them (tools/exp_f1f2_precision.py, "
+                                         "DESIGN.md section 4); all head parity gates unchanged",
                            "l2": "inputs larger than L2 (268 MB maps + >5 GB of saved activations per step vs 126 MB L2)",
                            "alg_tflop_per_step": ALG_FLOPS_PER_CLIP_FWD_BWD * B / 1e12},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "inference": infer,
