@@ -1202,7 +1202,7 @@ static int search_core(grl_handle* h, const NcclApi* api, ncclComm_t comm, int w
 static int search_impl(grl_handle* h, int world, int rank, int metric, const float* q, int q_rows, const float* g, const void* prepared, int nq,
                        int ng, int dim, int k, int64_t idx_base, int max_flagged, float* top_d, int64_t* top_i, int32_t* stats, void* workspace,
                        size_t workspace_bytes, void* stream, const char* who) {
-    if (!h || !q || !g || !top_d || !top_i || !workspace) return set_error(h, GRL_EINVAL, "%s: NULL argument", who);
+    if (!h || (!q && q_rows > 0) || !g || !top_d || !top_i || !workspace) return set_error(h, GRL_EINVAL, "%s: NULL argument", who);   // (an empty query slice may be NULL)
     if (nq <= 0 || ng <= 0 || dim <= 0 || (dim & 7) || dim > 32768) return set_error(h, GRL_EINVAL, "%s: need nq,ng > 0, dim %% 8 == 0, dim <= 32768 (dim=%d)", who, dim);
     if (k <= 0 || k > TOPK_MAXK / 2) return set_error(h, GRL_EINVAL, "%s: need 0 < k <= %d", who, TOPK_MAXK / 2);
     if (metric != GRL_METRIC_NEG_DOT && metric != GRL_METRIC_L2) return set_error(h, GRL_EINVAL, "%s: unknown metric %d", who, metric);

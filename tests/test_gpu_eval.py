@@ -421,6 +421,11 @@ def test_evaluate_sharded_single_rank_equals_evaluate(golden_dir):
         assert np.array_equal(cmc0, cmc1) and map0 == map1
 
 
+# (nq, ng, dim, k, duplicated rows): a large block (256 x 256 coarse kernel, brute-force leg), a small ragged one, and a single
+# query (the second rank's query slice is EMPTY)
+_NCCL_CASES = ((1101, 30011, 128, 100, 13), (37, 9001, 72, 30, 0), (1, 5000, 64, 10, 0))
+
+
 def _nccl_worker(rank, world, port, out_dir):
     import os
     import torch.distributed as dist
@@ -430,7 +435,8 @@ def _nccl_worker(rank, world, port, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from grl_b200 import evaluator as ev
     res = {}
-    for metric, (nq, ng, dim, k, dup) in enumerate(((1101, 30011, 128, 100, 13), (37, 9001, 72, 30, 0))):
+    for metric, (nq, ng, dim, k, dup) in enumerate(_NCCL_CASES):
+        metric = metric & 1
         q, g = _retrieval_inputs(nq, ng, dim, 500 + metric, dup)
         lo, n = ev.shard_bounds(ng, world, rank)
         qlo, qn = ev.query_slice(nq, world, rank)
@@ -441,7 +447,8 @@ def _nccl_worker(rank, world, port, out_dir):
         # ... the same with replicated queries and a prepared gallery
         d2, i2 = ev.sharded_retrieve(torch.from_numpy(q).cuda(), ev.PreparedGallery(gd), k, lo, metric=metric)
         assert torch.equal(d, d2) and torch.equal(i, i2)
-        res["d%d" % metric], res["i%d" % metric], res["s%d" % metric] = d.cpu().numpy(), i.cpu().numpy(), stats.cpu().numpy()
+        tag = "%d_%d" % (nq, metric)
+        res["d" + tag], res["i" + tag], res["s" + tag] = d.cpu().numpy(), i.cpu().numpy(), stats.cpu().numpy()
     # sharded CMC / mAP
     qf, gf, qp, gp, qc, gc = synth.make_eval_set(300, 2500, 64, seed=9, num_ids=25, noise=1.5, missing_query_frac=0.05)
     ngt = gf.shape[0]
@@ -467,16 +474,18 @@ def test_sharded_search_and_eval_over_nccl_two_ranks(tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0, r1 = np.load(str(tmp_path / "rank0.npz")), np.load(str(tmp_path / "rank1.npz"))
-    for metric, (nq, ng, dim, k, dup) in enumerate(((1101, 30011, 128, 100, 13), (37, 9001, 72, 30, 0))):
+    for metric, (nq, ng, dim, k, dup) in enumerate(_NCCL_CASES):
+        metric = metric & 1
+        tag = "%d_%d" % (nq, metric)
         q, g = _retrieval_inputs(nq, ng, dim, 500 + metric, dup)
         d, i = ev.retrieve_topk(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda(), k, metric=metric)     # one GPU, whole gallery
         for r in (r0, r1):
-            assert np.array_equal(r["i%d" % metric], i.cpu().numpy()) and np.array_equal(r["d%d" % metric], d.cpu().numpy())
+            assert np.array_equal(r["i" + tag], i.cpu().numpy()) and np.array_equal(r["d" + tag], d.cpu().numpy())
         if nq <= 64:
             v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q, g, metric), k)
-            assert np.array_equal(r0["i%d" % metric], i_ref) and np.array_equal(r0["d%d" % metric], v_ref)
+            assert np.array_equal(r0["i" + tag], i_ref) and np.array_equal(r0["d" + tag], v_ref)
         if dup:
-            assert int(r0["s%d" % metric][0]) > 0               # the brute-force leg ran over NCCL too
+            assert int(r0["s" + tag][0]) > 0                    # queries without a proof were handled over NCCL too
     qf, gf, qp, gp, qc, gc = synth.make_eval_set(300, 2500, 64, seed=9, num_ids=25, noise=1.5, missing_query_frac=0.05)
     cmc, mAP = ev.evaluate(ev.cosin_dist(torch.from_numpy(qf).cuda(), torch.from_numpy(gf).cuda()), qp, gp, qc, gc, 50)
     for r in (r0, r1):
