@@ -1199,10 +1199,10 @@ static int search_core(grl_handle* h, const NcclApi* api, ncclComm_t comm, int w
     return GRL_OK;
 }
 
-static int search_impl(grl_handle* h, int world, int rank, int metric, const float* q, int q_rows, const float* g, const void* prepared, int nq,
+static int search_impl(grl_handle* h, int world, int rank, int metric, const float* q, int q_is_slice, const float* g, const void* prepared, int nq,
                        int ng, int dim, int k, int64_t idx_base, int max_flagged, float* top_d, int64_t* top_i, int32_t* stats, void* workspace,
                        size_t workspace_bytes, void* stream, const char* who) {
-    if (!h || (!q && q_rows > 0) || !g || !top_d || !top_i || !workspace) return set_error(h, GRL_EINVAL, "%s: NULL argument", who);   // (an empty query slice may be NULL)
+    if (!h || !g || !top_d || !top_i || !workspace) return set_error(h, GRL_EINVAL, "%s: NULL argument", who);
     if (nq <= 0 || ng <= 0 || dim <= 0 || (dim & 7) || dim > 32768) return set_error(h, GRL_EINVAL, "%s: need nq,ng > 0, dim %% 8 == 0, dim <= 32768 (dim=%d)", who, dim);
     if (k <= 0 || k > TOPK_MAXK / 2) return set_error(h, GRL_EINVAL, "%s: need 0 < k <= %d", who, TOPK_MAXK / 2);
     if (metric != GRL_METRIC_NEG_DOT && metric != GRL_METRIC_L2) return set_error(h, GRL_EINVAL, "%s: unknown metric %d", who, metric);
@@ -1214,8 +1214,9 @@ static int search_impl(grl_handle* h, int world, int rank, int metric, const flo
     if ((long long)world * TOPK_MAXK > 16384) return set_error(h, GRL_EINVAL, "%s: world * K' must be <= 16384", who);
     const int qs = S.P1.qs, nqp = S.P1.nqp;
     const int my_rows = std::max(0, std::min(qs, nq - rank * qs));           // valid rows of this rank's query slice
-    if (q_rows != nq && q_rows != my_rows)
-        return set_error(h, GRL_EINVAL, "%s: q_rows must be nq (%d, all queries) or this rank's slice (%d rows), got %d", who, nq, my_rows, q_rows);
+    // q_is_slice decides which collectives run, so every rank must pass the same value (it cannot be inferred from a row count: a
+    // slice can be as long as the whole block, e.g. one query on two ranks)
+    if (!q && !(q_is_slice && my_rows == 0)) return set_error(h, GRL_EINVAL, "%s: NULL argument", who);   // (an empty query slice may be NULL)
     const NcclApi* api = nullptr;
     ncclComm_t comm = nullptr;
     if (world > 1) {
@@ -1235,7 +1236,7 @@ static int search_impl(grl_handle* h, int world, int rank, int metric, const flo
     const float* Q = q;
     if (world > 1) {
         float* Qw = (float*)(w + S.Q);
-        if (q_rows == nq) {
+        if (!q_is_slice) {
             GRL_CUDA(h, cudaMemcpyAsync(Qw, q, (size_t)nq * dim * 4, cudaMemcpyDeviceToDevice, st));
             if (nqp > nq) GRL_CUDA(h, cudaMemsetAsync(Qw + (size_t)nq * dim, 0, (size_t)(nqp - nq) * dim * 4, st));
         } else {
@@ -1342,12 +1343,12 @@ extern "C" size_t grl_sharded_topk_workspace_bytes(const grl_handle* h, int nq, 
     return S.total;
 }
 
-extern "C" int grl_sharded_topk(grl_handle* h, int metric, const float* q, int q_rows, const float* g_local, const void* prepared, int nq,
+extern "C" int grl_sharded_topk(grl_handle* h, int metric, const float* q, int q_is_slice, const float* g_local, const void* prepared, int nq,
                                 int ng_local, int dim, int k, int64_t idx_base, int max_flagged, float* top_d, int64_t* top_i, int32_t* stats,
                                 void* workspace, size_t workspace_bytes, void* stream) {
     if (!h) return GRL_EINVAL;
     const int world = h->comm ? h->comm_world : 1, rank = h->comm ? h->comm_rank : 0;
-    return search_impl(h, world, rank, metric, q, q_rows, g_local, prepared, nq, ng_local, dim, k, idx_base, max_flagged, top_d, top_i, stats,
+    return search_impl(h, world, rank, metric, q, q_is_slice, g_local, prepared, nq, ng_local, dim, k, idx_base, max_flagged, top_d, top_i, stats,
                        workspace, workspace_bytes, stream, "grl_sharded_topk");
 }
 
@@ -1364,13 +1365,13 @@ extern "C" size_t grl_dist_topk_workspace_bytes(int nq, int ng, int dim) {
 }
 extern "C" int grl_dist_topk(grl_handle* h, int metric, const float* q, const float* g, int nq, int ng, int dim, int k,
                              int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes, void* stream) {
-    return search_impl(h, 1, 0, metric, q, nq, g, nullptr, nq, ng, dim, k, idx_base, -1, top_d, top_i, nullptr, workspace, workspace_bytes, stream,
+    return search_impl(h, 1, 0, metric, q, 0, g, nullptr, nq, ng, dim, k, idx_base, -1, top_d, top_i, nullptr, workspace, workspace_bytes, stream,
                        "grl_dist_topk");
 }
 extern "C" int grl_dist_topk_prepared(grl_handle* h, int metric, const float* q, const float* g, const void* prepared, int nq, int ng, int dim,
                                       int k, int64_t idx_base, float* top_d, int64_t* top_i, void* workspace, size_t workspace_bytes,
                                       void* stream) {
     if (!prepared) return set_error(h, GRL_EINVAL, "grl_dist_topk_prepared: NULL argument");
-    return search_impl(h, 1, 0, metric, q, nq, g, prepared, nq, ng, dim, k, idx_base, -1, top_d, top_i, nullptr, workspace, workspace_bytes, stream,
+    return search_impl(h, 1, 0, metric, q, 0, g, prepared, nq, ng, dim, k, idx_base, -1, top_d, top_i, nullptr, workspace, workspace_bytes, stream,
                        "grl_dist_topk_prepared");
 }

@@ -307,12 +307,13 @@ def search_stage_ms(device=None):
     return {n: float(v) for n, v in zip(names, ms)}
 
 
-def sharded_topk(qf, gf_local, k, idx_base, nq=None, metric=0, max_flagged=-1, out=None, stats=None):
+def sharded_topk(qf, gf_local, k, idx_base, nq=None, metric=0, max_flagged=-1, out=None, stats=None):  # noqa: C901
     """grl_sharded_topk: one search over a gallery sharded across the ranks of the library's search communicator
     (init_search_comm), the whole protocol -- coarse tensor-core pass, NCCL exchanges, owned re-scores, completeness proof,
     brute-force leg -- behind one C call on the current stream.
 
-    qf        all `nq` query rows, or (when `nq` is given and larger than qf.size(0)) this rank's query_slice of them
+    qf        all query rows (nq=None), or -- when `nq` is given -- this rank's query_slice of the nq queries (EVERY rank must
+              then pass its slice: the mode decides which collectives run)
     gf_local  this rank's gallery rows [ng_local, dim] or a PreparedGallery of them; idx_base = global index of its first row
     out       optional (top_d f32 [nq, k], top_i i64 [nq, k]) CUDA tensors to fill;  stats: optional int32[8] CUDA tensor
     Returns (top_d, top_i): the exact stable top-k of the fixed-order fp32 distances, identical on every rank."""
@@ -324,7 +325,13 @@ def sharded_topk(qf, gf_local, k, idx_base, nq=None, metric=0, max_flagged=-1, o
         qf, gf = _padded_features(qf, gf_local)
     dev = qf.device
     q_rows, dim, ng = qf.size(0), qf.size(1), gf.size(0)
+    is_slice = nq is not None
     nq = q_rows if nq is None else int(nq)
+    if is_slice:
+        world, rank = comm_info(dev)
+        if q_rows != query_slice(nq, world, rank)[1]:
+            raise RuntimeError("sharded_topk: rank %d of %d must pass %d query rows of %d (query_slice), got %d" %
+                               (rank, world, query_slice(nq, world, rank)[1], nq, q_rows))
     lib = _lib.load_library()
     with torch.cuda.device(dev):
         h = _lib.get_handle(dev)
@@ -335,7 +342,8 @@ def sharded_topk(qf, gf_local, k, idx_base, nq=None, metric=0, max_flagged=-1, o
         if nbytes == 0:
             raise RuntimeError("grl_sharded_topk: bad sizes nq=%d ng=%d dim=%d k=%d" % (nq, ng, dim, k))
         ws = _search_workspace(dev, nbytes)
-        _lib.check(h, lib.grl_sharded_topk(h, metric, qf.data_ptr(), q_rows, gf.data_ptr(), None if prepared is None else prepared.buf.data_ptr(),
+        _lib.check(h, lib.grl_sharded_topk(h, metric, qf.data_ptr() if q_rows else None, 1 if is_slice else 0, gf.data_ptr(),
+                                           None if prepared is None else prepared.buf.data_ptr(),
                                            nq, ng, dim, k, idx_base, max_flagged, top_d.data_ptr(), top_i.data_ptr(), _lib.ptr(stats),
                                            ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)), "grl_sharded_topk")
     return top_d, top_i

@@ -186,9 +186,10 @@ int grl_comm_info(const grl_handle* h, int* world, int* rank);
 
 /* One search over a gallery whose rows are split contiguously over the W ranks of the handle's communicator (W = 1 without
  * one): the whole protocol behind ONE call, every collective on the caller's stream.
- *   q         query rows (device, fp32, [q_rows][dim]).  q_rows == nq: all queries (replicated by the caller);
- *             otherwise this rank's slice, rows [rank*qs, min(nq, (rank+1)*qs)) with qs = ceil(nq / W) -- the ranks then
- *             all-gather the slices over NVLink instead of each uploading all nq rows over PCIe
+ *   q         query rows (device, fp32).  q_is_slice == 0: all nq queries (replicated by the caller); q_is_slice != 0: this
+ *             rank's slice, rows [rank*qs, min(nq, (rank+1)*qs)) with qs = ceil(nq / W) (may be empty, then q may be NULL) --
+ *             the ranks all-gather the slices over NVLink instead of each uploading all nq rows over PCIe.  The flag selects
+ *             which collectives run: every rank must pass the same value
  *   g_local   this rank's gallery rows [ng_local][dim] (fp32; needed for the exact re-score), idx_base = global index of row 0
  *   prepared  grl_gallery_prepare'd index of g_local, or NULL (the shard is then converted chunk by chunk in every search)
  *   top_d / top_i [nq][k]: the exact stable top-k of the fixed-order fp32 distances, identical on every rank and for every W
@@ -208,7 +209,7 @@ int grl_comm_info(const grl_handle* h, int* world, int* rank);
  * grl_search_profile(h, 1) records an event at every stage boundary of the following calls; grl_search_stage_ms returns the
  * nine stage durations of the last one (synchronises on its last event).                                                 */
 size_t grl_sharded_topk_workspace_bytes(const grl_handle* h, int nq, int ng_local, int dim, int k, int prepared);
-int grl_sharded_topk(grl_handle* h, int metric, const float* q, int q_rows, const float* g_local, const void* prepared, int nq,
+int grl_sharded_topk(grl_handle* h, int metric, const float* q, int q_is_slice, const float* g_local, const void* prepared, int nq,
                      int ng_local, int dim, int k, int64_t idx_base, int max_flagged, float* top_d, int64_t* top_i, int32_t* stats,
                      void* workspace, size_t workspace_bytes, void* stream);
 #define GRL_SEARCH_STAGES 9

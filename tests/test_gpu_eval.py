@@ -1,6 +1,7 @@
 """GPU parity: matching / evaluation kernels through the C ABI vs the oracle (tests only)."""
 import ctypes
 import os
+import time
 
 import numpy as np
 import pytest
@@ -472,7 +473,13 @@ def test_sharded_search_and_eval_over_nccl_two_ranks(tmp_path):
     _, ev = _mods()
     from oracle import eval_oracle as eo
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ctx = mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=False)
+    deadline = time.time() + 150                       # a rank that dies leaves its peer inside a collective: never wait forever
+    while not ctx.join(timeout=5):
+        if time.time() > deadline:
+            for p_ in ctx.processes:
+                p_.kill()
+            pytest.fail("NCCL workers did not finish within 150 s (one rank failed or the collectives are mismatched)")
     r0, r1 = np.load(str(tmp_path / "rank0.npz")), np.load(str(tmp_path / "rank1.npz"))
     for metric, (nq, ng, dim, k, dup) in enumerate(_NCCL_CASES):
         metric = metric & 1
