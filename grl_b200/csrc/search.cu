@@ -215,14 +215,32 @@ __device__ __forceinline__ void warp_merge_row(int cnt, const unsigned long long
 }
 
 // ---- the first chunk of a search: no threshold exists yet, so its distance tile IS stored and every row selects its k smallest
-// entries from it.  One block per row; the row (<= BOOT_MAX columns) lives in registers as orderable 32-bit distances, thread t
-// holding the contiguous columns [t * BOOT_PER, (t + 1) * BOOT_PER).  Selection = radix refinement of the k-th smallest VALUE:
-// histogram the values still in range over BOOT_BINS equal-width bins, descend into the bin that holds the k-th, repeat until
-// the range is a single value (two or three rounds in practice); then one ordered compaction (everything below the value, and
-// as many entries EQUAL to it as are still needed, lowest column first) and one block sort of the k selected keys.  O(ncols)
-// work per row instead of a full sort, which is what lets the first chunk be thousands of columns wide and spares the
-// search the first four "doubling" list merges.
+// entries from it.  One block per row; the row (<= BOOT_MAX columns) lives in registers as orderable 32-bit distances, value
+// j = 4 i + e of thread t being column 4 * BOOT_THREADS * i + 4 t + e (coalesced 16-byte loads).  O(ncols) work per row instead
+// of a full sort, which is what lets the first chunk be thousands of columns wide and spares the search the first four
+// "doubling" list merges.  Two selection paths, both exact (the k smallest (value, column) keys, whatever the data):
+//  * exact path (boot_select_exact): histogram the values over BOOT_BINS ordered bins, find the bin that holds the k-th
+//    smallest; everything in a lower bin is selected, the entries of that boundary bin are ranked and the smallest still needed
+//    are taken; a boundary bin too large for that (degenerate data) is refined by another round on its own range.
+//  * sampled pre-filter (boot_select_sampled, full chunks only): the same bin search over a 1-in-8 SAMPLE of the row gives a cut
+//    t0 that about 1.8 k of the row's values pass; those are compacted into shared memory (one compare per value instead of a
+//    bin computation and an atomic) and the exact path's bin search then runs over the few hundred survivors.  The cut is only
+//    a work-saving guess: whenever fewer than k or more than BOOT_BUF values pass it (a few rows in 10^5 for continuous data;
+//    every row of a gallery of duplicates) the row takes the exact path from its registers.
 constexpr int BOOT_THREADS = 256, BOOT_PER = 32, BOOT_MAX = BOOT_THREADS * BOOT_PER, BOOT_BINS = 2048;
+constexpr int BOOT_EDGE = 1024;        // boundary-bin entries resolved by ranking/sorting (more: another refinement round)
+constexpr int BOOT_BUF = 2048;         // values the sampled pre-filter may pass on
+constexpr int BOOT_SAMPLE = 8;         // the pre-filter looks at one value in BOOT_SAMPLE
+
+struct BootSmem {
+    unsigned int hist[BOOT_BINS];
+    uint64_t sel[TOPK_MAXK];
+    uint64_t edge[BOOT_EDGE];
+    uint64_t buf[BOOT_BUF];
+    int warp_tmp[BOOT_THREADS / 32];
+    unsigned int lo, hi, bin, before, t0;
+    int n_sel, n_edge, n_buf;
+};
 
 __device__ __forceinline__ int block_excl_scan_256(int v, int* smem_warp, int& total) {
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -239,112 +257,245 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int* smem_warp, int& t
     return base + x - v;
 }
 
-__global__ void __launch_bounds__(BOOT_THREADS, 3) list_boot_select_kernel(const float* __restrict__ tile, long long ld, int ncols, int k,
+// A monotone map of [lo, hi] onto the bins 0 .. BOOT_BINS-1 (float arithmetic: the bins need not be equal, only ordered, with
+// lo and hi in different ones -- an integer division per value would cost more than the whole selection); values below lo
+// fall into bin 0.
+struct BootBins {
+    uint32_t lo;
+    float scale;
+    __device__ __forceinline__ BootBins(uint32_t lo_, uint32_t hi_) : lo(lo_), scale(hi_ > lo_ ? (float)(BOOT_BINS - 1) / (float)(hi_ - lo_) : 0.f) {}
+    __device__ __forceinline__ unsigned int operator()(uint32_t x) const {
+        return x <= lo ? 0u : min((unsigned int)(BOOT_BINS - 1), (unsigned int)((float)(x - lo) * scale));
+    }
+};
+
+// With the histogram complete and visible: S.bin = the bin that holds the need-th smallest entry (1 <= need <= entries),
+// S.before = the number of entries in lower bins.  Ends with a barrier.
+__device__ __forceinline__ void boot_find_bin(BootSmem& S, int need) {
+    constexpr int PER = BOOT_BINS / BOOT_THREADS;             // each thread owns PER consecutive bins
+    static_assert(PER == 8, "boot_find_bin reads two uint4 per thread");
+    const uint4 h0 = reinterpret_cast<const uint4*>(S.hist)[2 * threadIdx.x], h1 = reinterpret_cast<const uint4*>(S.hist)[2 * threadIdx.x + 1];
+    const int c[PER] = {(int)h0.x, (int)h0.y, (int)h0.z, (int)h0.w, (int)h1.x, (int)h1.y, (int)h1.z, (int)h1.w};
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) mine += c[j];
+    int total;
+    const int before = block_excl_scan_256(mine, S.warp_tmp, total);
+    if (before < need && need <= before + mine) {
+        int run = before;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (run < need && need <= run + c[j]) { S.bin = threadIdx.x * PER + j; S.before = run; }
+            run += c[j];
+        }
+    }
+    __syncthreads();
+}
+
+// The `need` smallest of the distinct keys edge[0 .. ne) -> sel[base ..] (any order).  Callers put a barrier on both sides.
+__device__ __forceinline__ void boot_take_edge(BootSmem& S, int ne, int base, int need) {
+    if (ne <= 64) {                                   // the normal case, a handful of keys: rank each against the others
+        if ((int)threadIdx.x < ne) {
+            const uint64_t key = S.edge[threadIdx.x];
+            int rank = 0;
+            for (int l = 0; l < ne; ++l) rank += S.edge[l] < key ? 1 : 0;
+            if (rank < need) S.sel[base + rank] = key;
+        }
+        return;
+    }
+    int npe = 128;
+    while (npe < ne) npe <<= 1;
+    for (int i = ne + threadIdx.x; i < npe; i += BOOT_THREADS) S.edge[i] = KEY_EMPTY;
+    block_bitonic_sort(S.edge, npe);
+    for (int i = threadIdx.x; i < need; i += BOOT_THREADS) S.sel[base + i] = S.edge[i];
+}
+
+#define BOOT_COL(j) (((j) >> 2) * (4 * BOOT_THREADS) + 4 * (int)threadIdx.x + ((j) & 3))
+#define BOOT_KEY(j) (((uint64_t)v[j] << 32) | (uint32_t)((uint32_t)idx_base + (uint32_t)BOOT_COL(j)))
+
+// The k smallest keys of the row in registers -> S.sel[0 .. k) (any order); k < ncols.
+__device__ __forceinline__ void boot_select_exact(BootSmem& S, const uint32_t (&v)[BOOT_PER], int ncols, int k, int64_t idx_base) {
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+#pragma unroll
+    for (int j = 0; j < BOOT_PER; ++j)
+        if (BOOT_COL(j) < ncols) { lo = min(lo, v[j]); hi = max(hi, v[j]); }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off)); }
+    __syncthreads();                                  // (a row sent here by the pre-filter: every thread is done with S)
+    if (threadIdx.x == 0) { S.lo = 0xFFFFFFFFu; S.hi = 0u; S.n_sel = 0; S.n_edge = 0; }
+    __syncthreads();
+    if (lane_id() == 0) { atomicMin(&S.lo, lo); atomicMax(&S.hi, hi); }
+    __syncthreads();
+    lo = S.lo; hi = S.hi;
+    int need = k;                                     // entries still to take from [lo, hi]
+    // Rounds of: histogram of the values still in range -> the bin holding the `need`-th of them.  Everything in a lower bin is
+    // selected; a boundary bin of at most BOOT_EDGE entries (the normal case after ONE round: a handful) is resolved by
+    // ranking its keys, otherwise the range narrows to that bin and the round repeats (the range strictly shrinks: lo and hi
+    // always land in different bins).
+    bool resolve;
+    while (true) {
+        for (int i = threadIdx.x; i < BOOT_BINS; i += BOOT_THREADS) S.hist[i] = 0;
+        __syncthreads();
+        const BootBins bins(lo, hi);
+#pragma unroll
+        for (int j = 0; j < BOOT_PER; ++j)
+            if (BOOT_COL(j) < ncols && v[j] >= lo && v[j] <= hi) atomicAdd(&S.hist[bins(v[j])], 1u);
+        __syncthreads();
+        boot_find_bin(S, need);
+        const unsigned int bin = S.bin;
+        resolve = (int)S.hist[bin] <= BOOT_EDGE || lo == hi;         // (lo == hi: all remaining values are equal -> ties by column)
+        uint32_t nlo = 0xFFFFFFFFu, nhi = 0u;
+#pragma unroll
+        for (int j = 0; j < BOOT_PER; ++j) {
+            if (BOOT_COL(j) < ncols && v[j] >= lo && v[j] <= hi) {
+                const unsigned int bj = bins(v[j]);
+                if (bj < bin) S.sel[atomicAdd(&S.n_sel, 1)] = BOOT_KEY(j);
+                else if (bj == bin) {
+                    if (resolve) { const int e = atomicAdd(&S.n_edge, 1); if (e < BOOT_EDGE) S.edge[e] = BOOT_KEY(j); }
+                    else { nlo = min(nlo, v[j]); nhi = max(nhi, v[j]); }
+                }
+            }
+        }
+        need -= (int)S.before;
+        if (resolve) break;
+        if (threadIdx.x == 0) { S.lo = 0xFFFFFFFFu; S.hi = 0u; }
+        __syncthreads();
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) { nlo = min(nlo, __shfl_xor_sync(0xffffffffu, nlo, off)); nhi = max(nhi, __shfl_xor_sync(0xffffffffu, nhi, off)); }
+        if (lane_id() == 0 && nlo <= nhi) { atomicMin(&S.lo, nlo); atomicMax(&S.hi, nhi); }
+        __syncthreads();
+        lo = S.lo; hi = S.hi;
+        __syncthreads();
+    }
+    __syncthreads();
+    const int base = S.n_sel;
+    if (S.n_edge <= BOOT_EDGE) { boot_take_edge(S, S.n_edge, base, need); return; }
+    // more EQUAL values than the edge buffer holds: the lowest columns among them, by ordered scans (column order = i, thread, e)
+    int taken = 0;
+    for (int i = 0; i < BOOT_PER / 4 && taken < need; ++i) {
+        int n_eq = 0;
+#pragma unroll
+        for (int j = 0; j < BOOT_PER; ++j)
+            if ((j >> 2) == i && BOOT_COL(j) < ncols && v[j] == lo) ++n_eq;
+        int tot;
+        int off = taken + block_excl_scan_256(n_eq, S.warp_tmp, tot);
+#pragma unroll
+        for (int j = 0; j < BOOT_PER; ++j)
+            if ((j >> 2) == i && BOOT_COL(j) < ncols && v[j] == lo) { if (off < need) S.sel[base + off] = BOOT_KEY(j); ++off; }
+        taken += tot;
+    }
+}
+
+// The sampled pre-filter (see above).  Returns false, block-uniformly and with S.sel untouched, when the row must take the
+// exact path; true with the k smallest keys in S.sel[0 .. k).  ncols == BOOT_MAX.
+__device__ __forceinline__ bool boot_select_sampled(BootSmem& S, const uint32_t (&v)[BOOT_PER], int k, int64_t idx_base) {
+    // the sample: one component of every other 16-byte load (columns spread over the whole chunk)
+    const uint32_t sv[4] = {v[0], v[9], v[18], v[27]};
+    static_assert(BOOT_PER / 4 == BOOT_SAMPLE, "the sample below is 4 of a thread's 32 values");
+    uint32_t lo = min(min(sv[0], sv[1]), min(sv[2], sv[3])), hi = max(max(sv[0], sv[1]), max(sv[2], sv[3]));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off)); }
+    if (threadIdx.x == 0) { S.lo = 0xFFFFFFFFu; S.hi = 0u; S.t0 = 0u; S.n_sel = 0; S.n_edge = 0; S.n_buf = 0; }
+    for (int i = threadIdx.x; i < BOOT_BINS; i += BOOT_THREADS) S.hist[i] = 0;
+    __syncthreads();
+    if (lane_id() == 0) { atomicMin(&S.lo, lo); atomicMax(&S.hi, hi); }
+    __syncthreads();
+    lo = S.lo; hi = S.hi;
+    if (lo == hi) return false;
+    // sample rank whose value about k + 4.5 sigma of the row's values pass (sigma^2 ~ BOOT_SAMPLE * count)
+    const int want = k + (int)(4.5f * sqrtf((float)(k * BOOT_SAMPLE))) + 2 * BOOT_SAMPLE;
+    const int rank = (want + BOOT_SAMPLE - 1) / BOOT_SAMPLE;            // <= 181 of the 1024 samples for k <= TOPK_MAXK
+    unsigned int sb[4];
+    {
+        const BootBins bins(lo, hi);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sb[j] = bins(sv[j]); atomicAdd(&S.hist[sb[j]], 1u); }
+    }
+    __syncthreads();
+    boot_find_bin(S, rank);
+    {
+        const unsigned int bin = S.bin;
+        uint32_t t = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (sb[j] <= bin) t = max(t, sv[j]);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, off));
+        if (lane_id() == 0) atomicMax(&S.t0, t);
+    }
+    __syncthreads();
+    const uint32_t t0 = S.t0;
+    // compaction of the values <= t0 (any order: warp-aggregated reservation, then per-thread writes)
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < BOOT_PER; ++j) cnt += v[j] <= t0 ? 1 : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, off); if (lane_id() >= off) incl += y; }
+    int wbase = 0;
+    if (lane_id() == 31) wbase = atomicAdd(&S.n_buf, incl);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    int pos = wbase + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < BOOT_PER; ++j)
+        if (v[j] <= t0) { if (pos < BOOT_BUF) S.buf[pos] = BOOT_KEY(j); ++pos; }
+    for (int i = threadIdx.x; i < BOOT_BINS; i += BOOT_THREADS) S.hist[i] = 0;      // (the sample's bins were last read before the barrier above)
+    __syncthreads();
+    const int n = S.n_buf;
+    if (n < k || n > BOOT_BUF) return false;
+    // the exact bin search over the survivors
+    const BootBins bins(lo, t0);
+    for (int i = threadIdx.x; i < n; i += BOOT_THREADS) atomicAdd(&S.hist[bins((uint32_t)(S.buf[i] >> 32))], 1u);
+    __syncthreads();
+    boot_find_bin(S, k);
+    const unsigned int bin = S.bin;
+    const int before = (int)S.before, in_bin = (int)S.hist[bin];
+    if (in_bin > BOOT_EDGE) return false;
+    for (int i = threadIdx.x; i < n; i += BOOT_THREADS) {
+        const uint64_t key = S.buf[i];
+        const unsigned int bj = bins((uint32_t)(key >> 32));
+        if (bj < bin) S.sel[atomicAdd(&S.n_sel, 1)] = key;
+        else if (bj == bin) S.edge[atomicAdd(&S.n_edge, 1)] = key;
+    }
+    __syncthreads();
+    boot_take_edge(S, in_bin, before, k - before);
+    return true;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(BOOT_THREADS, MINB) list_boot_select_kernel(const float* __restrict__ tile, long long ld, int ncols, int k,
                                                                         int64_t idx_base, uint64_t* __restrict__ list, float* __restrict__ thresh_out,
                                                                         int* __restrict__ cand_cnt) {
-    __shared__ unsigned int hist[BOOT_BINS];
-    __shared__ uint64_t sel[TOPK_MAXK];
-    __shared__ int warp_tmp[BOOT_THREADS / 32];
-    __shared__ unsigned int s_lo, s_hi, s_bin, s_before;
+    __shared__ BootSmem S;
     const int row = blockIdx.x;
     const float* drow = tile + (long long)row * ld;
-    const int c_begin = threadIdx.x * BOOT_PER;
-    uint32_t v[BOOT_PER];
+    uint32_t v[BOOT_PER];                             // columns past ncols: the largest orderable value
 #pragma unroll
-    for (int j = 0; j < BOOT_PER / 4; ++j) {
-        const int c = c_begin + 4 * j;
-        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < BOOT_PER / 4; ++i) {
+        const int c = BOOT_COL(4 * i);
+        const float big = __uint_as_float(0x7FFFFFFFu);
+        float4 f = make_float4(big, big, big, big);
         if (c + 3 < ncols) f = __ldg(reinterpret_cast<const float4*>(drow + c));
         else { if (c < ncols) f.x = drow[c]; if (c + 1 < ncols) f.y = drow[c + 1]; if (c + 2 < ncols) f.z = drow[c + 2]; }
-        v[4 * j] = orderable(f.x); v[4 * j + 1] = orderable(f.y); v[4 * j + 2] = orderable(f.z); v[4 * j + 3] = orderable(f.w);
+        v[4 * i] = orderable(f.x); v[4 * i + 1] = orderable(f.y); v[4 * i + 2] = orderable(f.z); v[4 * i + 3] = orderable(f.w);
     }
     uint64_t* lrow = list + (long long)row * k;
     if (ncols <= k) {                                 // fewer columns than list slots: everything is selected
-        for (int i = threadIdx.x; i < k; i += BOOT_THREADS) sel[i] = KEY_EMPTY;
+        for (int i = threadIdx.x; i < k; i += BOOT_THREADS) S.sel[i] = KEY_EMPTY;
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < BOOT_PER; ++j)
-            if (c_begin + j < ncols) sel[c_begin + j] = ((uint64_t)v[j] << 32) | (uint32_t)(idx_base + c_begin + j);
+            if (BOOT_COL(j) < ncols) S.sel[BOOT_COL(j)] = BOOT_KEY(j);
     } else {
-        // ---- value of the k-th smallest entry: T, and how many entries equal to T are still needed
-        uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-#pragma unroll
-        for (int j = 0; j < BOOT_PER; ++j)
-            if (c_begin + j < ncols) { lo = min(lo, v[j]); hi = max(hi, v[j]); }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off)); }
-        if (threadIdx.x == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; }
-        __syncthreads();
-        if (lane_id() == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
-        __syncthreads();
-        lo = s_lo; hi = s_hi;
-        int need = k;                                 // entries still to take from [lo, hi]
-        while (lo != hi) {
-            for (int i = threadIdx.x; i < BOOT_BINS; i += BOOT_THREADS) hist[i] = 0;
-            __syncthreads();
-            // bin = a monotone map of [lo, hi] onto 0 .. BOOT_BINS-1 (float arithmetic: the bins need not be exactly equal, only
-            // ordered, with lo and hi in different ones -- an integer division per entry would cost more than the whole selection)
-            const float scale = (float)(BOOT_BINS - 1) / (float)(hi - lo);
-            auto bin_of = [&](uint32_t x) { return min((unsigned int)(BOOT_BINS - 1), (unsigned int)((float)(x - lo) * scale)); };
-#pragma unroll
-            for (int j = 0; j < BOOT_PER; ++j)
-                if (c_begin + j < ncols && v[j] >= lo && v[j] <= hi) atomicAdd(&hist[bin_of(v[j])], 1u);
-            __syncthreads();
-            // the bin holding the `need`-th entry: each thread owns BOOT_BINS / BOOT_THREADS consecutive bins
-            constexpr int PER = BOOT_BINS / BOOT_THREADS;
-            int mine = 0;
-#pragma unroll
-            for (int j = 0; j < PER; ++j) mine += (int)hist[threadIdx.x * PER + j];
-            int total;
-            const int before = block_excl_scan_256(mine, warp_tmp, total);
-            if (before < need && need <= before + mine) {
-                int run = before;
-#pragma unroll
-                for (int j = 0; j < PER; ++j) {
-                    const int h = (int)hist[threadIdx.x * PER + j];
-                    if (run < need && need <= run + h) { s_bin = threadIdx.x * PER + j; s_before = run; }
-                    run += h;
-                }
-            }
-            if (threadIdx.x == 0) { s_lo = 0xFFFFFFFFu; s_hi = 0u; }
-            __syncthreads();
-            const unsigned int bin = s_bin;
-            need -= (int)s_before;
-            uint32_t nlo = 0xFFFFFFFFu, nhi = 0u;      // the value range actually present in that bin
-#pragma unroll
-            for (int j = 0; j < BOOT_PER; ++j)
-                if (c_begin + j < ncols && v[j] >= lo && v[j] <= hi && bin_of(v[j]) == bin) { nlo = min(nlo, v[j]); nhi = max(nhi, v[j]); }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) { nlo = min(nlo, __shfl_xor_sync(0xffffffffu, nlo, off)); nhi = max(nhi, __shfl_xor_sync(0xffffffffu, nhi, off)); }
-            if (lane_id() == 0 && nlo <= nhi) { atomicMin(&s_lo, nlo); atomicMax(&s_hi, nhi); }
-            __syncthreads();
-            lo = s_lo; hi = s_hi;
-            __syncthreads();
-        }
-        const uint32_t T = lo;
-        // ---- ordered compaction: entries below T, then the first `need` entries equal to T (lowest column first)
-        int n_less = 0, n_eq = 0;
-#pragma unroll
-        for (int j = 0; j < BOOT_PER; ++j)
-            if (c_begin + j < ncols) { n_less += v[j] < T ? 1 : 0; n_eq += v[j] == T ? 1 : 0; }
-        int tot_less, tot_eq;
-        int off_less = block_excl_scan_256(n_less, warp_tmp, tot_less);
-        int off_eq = block_excl_scan_256(n_eq, warp_tmp, tot_eq);
-#pragma unroll
-        for (int j = 0; j < BOOT_PER; ++j) {
-            if (c_begin + j < ncols) {
-                const uint64_t key = ((uint64_t)v[j] << 32) | (uint32_t)(idx_base + c_begin + j);
-                if (v[j] < T) sel[off_less++] = key;
-                else if (v[j] == T) { if (off_eq < need) sel[tot_less + off_eq] = key; ++off_eq; }
-            }
-        }
+        bool done = false;
+        if (ncols == BOOT_MAX) done = boot_select_sampled(S, v, k, idx_base);
+        if (!done) boot_select_exact(S, v, ncols, k, idx_base);
     }
     __syncthreads();
     if (k == 256) {                                   // the common list length: one warp sorts the selection in registers, no barriers
         if (threadIdx.x < 32) {
             uint64_t r[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = sel[threadIdx.x * 8 + j];
+            for (int j = 0; j < 8; ++j) r[j] = S.sel[threadIdx.x * 8 + j];
             warp_sort_keys<8>(r, threadIdx.x);
 #pragma unroll
             for (int j = 0; j < 8; ++j) lrow[threadIdx.x * 8 + j] = r[j];
@@ -354,11 +505,13 @@ __global__ void __launch_bounds__(BOOT_THREADS, 3) list_boot_select_kernel(const
     }
     int npad = 2;
     while (npad < k) npad <<= 1;
-    for (int i = k + threadIdx.x; i < npad; i += BOOT_THREADS) sel[i] = KEY_EMPTY;      // (k <= TOPK_MAXK, a power of two in practice)
-    block_bitonic_sort(sel, npad);
-    for (int i = threadIdx.x; i < k; i += BOOT_THREADS) lrow[i] = sel[i];
-    if (threadIdx.x == 0) { thresh_out[row] = thresh_of(sel[k - 1]); cand_cnt[row] = 0; }
+    for (int i = k + threadIdx.x; i < npad; i += BOOT_THREADS) S.sel[i] = KEY_EMPTY;      // (k <= TOPK_MAXK, a power of two in practice)
+    block_bitonic_sort(S.sel, npad);
+    for (int i = threadIdx.x; i < k; i += BOOT_THREADS) lrow[i] = S.sel[i];
+    if (threadIdx.x == 0) { thresh_out[row] = thresh_of(S.sel[k - 1]); cand_cnt[row] = 0; }
 }
+#undef BOOT_COL
+#undef BOOT_KEY
 
 constexpr int LIST_WARPS = 4;          // rows per block of list_update_warp_kernel
 constexpr int LIST_WARP_MAX = 512;     // candidates one warp sorts in registers (16 keys per lane)
@@ -887,7 +1040,9 @@ static int coarse_pass(grl_handle* h, cudaStream_t st, int metric, const float* 
             merge = 1.6 * pending + 48.0 > (double)L.cap;
         }
         if (first) {
-            list_boot_select_kernel<<<nq, BOOT_THREADS, 0, st>>>(tile, L.first, nc, kprime, idx_base, list, thresh, cand_cnt);
+            static const int minb = getenv("GRL_BOOT_MINB") ? atoi(getenv("GRL_BOOT_MINB")) : 3;
+            if (minb == 2) list_boot_select_kernel<2><<<nq, BOOT_THREADS, 0, st>>>(tile, L.first, nc, kprime, idx_base, list, thresh, cand_cnt);
+            else list_boot_select_kernel<3><<<nq, BOOT_THREADS, 0, st>>>(tile, L.first, nc, kprime, idx_base, list, thresh, cand_cnt);
             GRL_LAUNCH_CHECK(h);
             c_merge = c_end;
         } else if (merge) {

@@ -264,6 +264,42 @@ def test_dist_topk_adversarial_order_overflows_to_brute_force(nq):
         assert np.array_equal(i.cpu().numpy(), i_ref) and np.array_equal(d.cpu().numpy(), v_ref)
 
 
+@pytest.mark.parametrize("dups", ["all", "cycle3", 1500, 500, 100, 0])
+def test_first_chunk_selection_with_duplicate_rows(dups):
+    """The first chunk's selection (list_boot_select_kernel: sampled pre-filter, exact bin search, ordered scans for equal values)
+    on galleries full of EXACT ties inside a full 8192-column chunk: every gallery row identical; three rows repeated; 1500 /
+    500 / 100 copies of every query's nearest row scattered among random rows (pre-filter passes too many -> exact path;
+    boundary bin sorted; boundary bin ranked); and no duplicates.  Ties must come back lowest index first, like the stable sort
+    of the reference (eva_functions.py:73)."""
+    _, ev = _mods()
+    from oracle import eval_oracle as eo
+    nq, ng, dim, k = 8, 9000, 64, 30
+    q, g = _retrieval_inputs(nq, ng, dim, 311, dup_every=0)
+    rng = np.random.default_rng(5)
+    if dups == "all":
+        g[:] = g[7]
+    elif dups == "cycle3":
+        g[:] = g[np.arange(ng) % 3]
+    elif dups:
+        near = q.mean(axis=0)
+        g[rng.permutation(8192)[:dups]] = near / np.linalg.norm(near)       # closer to every query than any random row
+    qd, gd = torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda()
+    for metric in (0, 1):
+        d, i = ev.retrieve_topk(qd, gd, k, metric=metric)
+        v_ref, i_ref = eo.topk_stable(eo.exact_distance_fixed(q, g, metric), k)
+        assert np.array_equal(i.cpu().numpy(), i_ref) and np.array_equal(d.cpu().numpy(), v_ref), (dups, metric)
+    # the selection alone: a single full chunk -> the coarse list is the K' smallest (coarse distance, index) keys, ascending
+    st = ev.CudaSearchStages
+    cd, ci, _, dirty = st.coarse(qd, gd[:8192], st.kprime(k), 0, 0)
+    cd, ci = cd.cpu().numpy(), ci.cpu().numpy()
+    assert int(dirty.sum()) == 0
+    assert all(len(set(r.tolist())) == r.size for r in ci) and bool((np.diff(cd, axis=1) >= 0).all())
+    same = np.diff(cd, axis=1) == 0
+    assert bool((np.diff(ci, axis=1)[same] > 0).all())                    # equal coarse distances: ascending index
+    if dups == "all":
+        assert np.array_equal(ci, np.tile(np.arange(ci.shape[1]), (nq, 1)))
+
+
 def test_exact_topk_brute_force_matches_oracle():
     _, ev = _mods()
     from oracle import eval_oracle as eo
