@@ -244,6 +244,8 @@ int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, 
     if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return set_error(h, GRL_EINVAL, "gemm: empty problem %dx%dx%d", M, N, K);
     if (A.mn_major && !B.mn_major) return set_error(h, GRL_EINVAL, "gemm: MN-major A with K-major B is not instantiated");
     if ((A.mn_major || B.mn_major) && (K % GEMM_BK)) return set_error(h, GRL_EINVAL, "gemm: MN-major operands need K %% 64 == 0");
+    if (epi.bnb_mask && ((N % 32) || (M % GEMM_BM) || !epi.col_sum || !epi.col_sq || !epi.bnb_hraw || !epi.bnb_stat))
+        return set_error(h, GRL_EINVAL, "gemm: the BatchNorm-backward epilogue needs N %% 32 == 0, M %% 128 == 0 and both partial-sum buffers");
     const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
     if (bn == 0) {
         const long long t256 = (long long)m_tiles * ((N + 255) / 256) * batch;
@@ -441,7 +443,7 @@ extern "C" void grl_destroy(grl_handle* h) {
 
 extern "C" int grl_set_overlap(grl_handle* h, int on) {
     if (!h) return GRL_EINVAL;
-    h->overlap = on & 127;
+    h->overlap = on & 255;
     return GRL_OK;
 }
 

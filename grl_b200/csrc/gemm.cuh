@@ -70,6 +70,15 @@ struct GemmEpi {
     long long sub_tile_rows;  // sub_row = m_tile*sub_tile_rows + sub_row_off[z] + row_in_tile
     long long sub_row_off[2];
     long long sub_col_off[2];
+    // ---- "BatchNorm backward" statistics of the stored tile (the dgrad GEMM that PRODUCES the gradient of a BN + ReLU output):
+    //      g = v where the ReLU output bnb_mask > 0 else 0, xhat = (bnb_hraw - mean[n]) * rstd[n] (bnb_stat: [z][4][N], mean in
+    //      row 2, rstd in row 3); col_sum receives the column sums of g, col_sq those of g * xhat (same [z][4*num_m_tiles][N]
+    //      partial layout), bnb_scal[0] / [1] the launch-wide max |g| / max |xhat| as float bits (atomicMax; may be NULL) ----
+    const __nv_bfloat16* bnb_mask;    // [z][M][bnb_ld]
+    const float* bnb_hraw;            // [z][M][bnb_ld]
+    const float* bnb_stat;
+    long long bnb_ld, bnb_bstride;
+    unsigned int* bnb_scal;
 };
 
 struct GemmParams {
@@ -135,6 +144,7 @@ __device__ __forceinline__ void epi_tile(const GemmParams& p, const EpiRow& R, i
     const float* gb_row = R.gb_row;
     const float* sub_row = R.sub_row;
     float* c_row = R.c_row;
+    float bnb_gmax = 0.f, bnb_xmax = 0.f;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n0 + c * 32;
@@ -224,6 +234,45 @@ __device__ __forceinline__ void epi_tile(const GemmParams& p, const EpiRow& R, i
                 }
             }
         }
+        // ---- BatchNorm-backward partial sums of the stored gradient tile ----
+        if (e.bnb_mask) {
+            float w[32];
+            if (row_ok) {
+                const long long off = z * e.bnb_bstride + (long long)grow * e.bnb_ld + col0;
+                const uint4* m4 = reinterpret_cast<const uint4*>(e.bnb_mask + off);
+                const float4* h4 = reinterpret_cast<const float4*>(e.bnb_hraw + off);
+                const float* mean = e.bnb_stat + (long long)z * 4 * p.N + 2 * p.N + col0;
+                const float* rstd = mean + p.N;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 mk = __ldg(m4 + j);
+                    const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const float4 hv = __ldg(h4 + 2 * j + q);
+                        const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int jj = 8 * j + 4 * q + i;
+                            const uint32_t bits = (mw[2 * q + (i >> 1)] >> ((i & 1) * 16)) & 0xFFFFu;     // bf16 > 0: 0x0001 .. 0x7F80
+                            const float gv = (bits - 1u < 0x7F80u) ? v[jj] : 0.f;
+                            const float xh = (hh[i] - __ldg(mean + jj)) * __ldg(rstd + jj);
+                            v[jj] = gv; w[jj] = gv * xh;
+                            bnb_gmax = fmaxf(bnb_gmax, fabsf(gv)); bnb_xmax = fmaxf(bnb_xmax, fabsf(xh));
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { v[j] = 0.f; w[j] = 0.f; }
+            }
+            const long long sidx = z * e.stat_bstride + (long long)(m_tile * 4 + quad) * p.N + col0 + lane;
+            const float s2 = warp_transpose_sum32(w);
+            e.col_sq[sidx] = s2;
+            const float s1 = warp_transpose_sum32(v);
+            e.col_sum[sidx] = s1;
+            continue;
+        }
         // ---- column reductions (BN statistics / squared-difference pooling) ----
         if (e.col_sum || e.col_sq) {
             if (sub_row) {
@@ -250,6 +299,17 @@ __device__ __forceinline__ void epi_tile(const GemmParams& p, const EpiRow& R, i
                 const float s1 = warp_transpose_sum32(v);
                 if (col0 + lane < p.N) e.col_sum[sidx] = s1;
             }
+        }
+    }
+    if (e.bnb_mask && e.bnb_scal) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            bnb_gmax = fmaxf(bnb_gmax, __shfl_xor_sync(0xffffffffu, bnb_gmax, off));
+            bnb_xmax = fmaxf(bnb_xmax, __shfl_xor_sync(0xffffffffu, bnb_xmax, off));
+        }
+        if (lane == 0) {
+            if (bnb_gmax == bnb_gmax && bnb_gmax > 0.f) atomicMax(e.bnb_scal + 0, __float_as_uint(bnb_gmax));
+            if (bnb_xmax == bnb_xmax && bnb_xmax > 0.f) atomicMax(e.bnb_scal + 1, __float_as_uint(bnb_xmax));
         }
     }
 }

@@ -777,21 +777,35 @@ __global__ void __launch_bounds__(256) pm_to_nchw_bias_kernel(const float* __res
 static int bn_backward(grl_handle* h, cudaStream_t st, const HeadWs& w, const float* srcA, const float* srcB, const __nv_bfloat16* mask_hi,
                        const float* hraw, const float* stat, int Cn, const float* gamma0, const float* gamma1, float* dgamma0,
                        float* dgamma1, float* dbeta0, float* dbeta1, int accumulate, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
-                       float* g_out, float* scal = nullptr, __half* out16 = nullptr) {
+                       float* g_out, float* scal = nullptr, __half* out16 = nullptr, bool reduced = false) {
     // scal (4 floats, zeroed by the caller): max |g|, max |xhat|, bound of |dH|, 1 / scale of the fp16 copy `out16`
+    // reduced: the GEMM that produced srcA already left the partial sums (4 per 128-row tile) in part_a / part_b and the two
+    // maxima in scal (bn_reduce_in_epilogue below) -- the reduce pass over srcA, the mask and the raw activations is skipped
     const int R = w.R, B = w.B;
     dim3 grid(Cn / 64, R / 128, 2);
     unsigned int* su = reinterpret_cast<unsigned int*>(scal);
-    bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(srcA, srcB, mask_hi, hraw, stat, Cn, R, WS_F32(w, part_a), WS_F32(w, part_b), su);
-    GRL_LAUNCH_CHECK(h);
+    if (!reduced) {
+        bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(srcA, srcB, mask_hi, hraw, stat, Cn, R, WS_F32(w, part_a), WS_F32(w, part_b), su);
+        GRL_LAUNCH_CHECK(h);
+    }
     BnPtrs2 bp; bp.gamma[0] = gamma0; bp.gamma[1] = gamma1;
     OutPtrs2 dg, db; dg.p[0] = dgamma0; dg.p[1] = dgamma1; db.p[0] = dbeta0; db.p[1] = dbeta1;
-    bn_bwd_finalize_kernel<<<dim3((Cn + 31) / 32, 2), dim3(32, 8), 0, st>>>(WS_F32(w, part_a), WS_F32(w, part_b), B, Cn, (double)R, bp, stat,
+    bn_bwd_finalize_kernel<<<dim3((Cn + 31) / 32, 2), dim3(32, 8), 0, st>>>(WS_F32(w, part_a), WS_F32(w, part_b), reduced ? 4 * (R / 128) : B, Cn, (double)R, bp, stat,
                                                                       WS_F32(w, kcoef), dg, db, accumulate, su);
     GRL_LAUNCH_CHECK(h);
     bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(srcA, srcB, mask_hi, hraw, stat, WS_F32(w, kcoef), Cn, R, out_hi, out_lo, g_out, scal, out16);
     GRL_LAUNCH_CHECK(h);
     return GRL_OK;
+}
+
+// The dgrad GEMM that produces the gradient of a BatchNorm + ReLU output [2][R][Cn] also leaves the BatchNorm-backward partial
+// sums (sum g, sum g xhat per 32-row slab and channel) and the two maxima: bn_backward(..., reduced = true) follows.
+static void bn_reduce_in_epilogue(GemmEpi& e, const HeadWs& w, const __nv_bfloat16* mask_hi, const float* hraw, const float* stat, int Cn, float* scal) {
+    e.col_sum = WS_F32(w, part_a); e.col_sq = WS_F32(w, part_b);
+    e.stat_bstride = (long long)4 * (w.R / 128) * Cn;
+    e.bnb_mask = mask_hi; e.bnb_hraw = hraw; e.bnb_stat = stat;
+    e.bnb_ld = Cn; e.bnb_bstride = (long long)w.R * Cn;
+    e.bnb_scal = reinterpret_cast<unsigned int*>(scal);
 }
 
 static int outer(grl_handle* h, cudaStream_t st, const float* A, long long a_os, long long a_is, const float* Bm, long long b_os,
@@ -885,6 +899,7 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
     GRL_TRY(planes_to_f16(h, sd, WS_BF(w, wf1_hi), WS_BF(w, wf1_lo), (size_t)2 * HC * HC, WS_F32(w, f16_scal) + 4,
                           reinterpret_cast<__half*>(WS_BF(w, wf1_16))));
     GRL_TRY(f1_path(T - 1));
+    const bool fuse_bn = (h->overlap & 128) == 0;      // debug bit 7: separate bn_bwd_reduce passes for bn1 / bn2 (A/B)
     for (int i = T - 1; i >= 0; --i) {
         const int first = (i == T - 1) ? 1 : 0;
         const int acc = first ? 0 : 1;
@@ -927,19 +942,21 @@ static int trl_backward_part(grl_handle* h, cudaStream_t st, const grl_head_para
             GemmEpi e = epi_default();
             e.C = WS_F32(w, dh2p); e.ldc = HB; e.c_bstride = (long long)R * HB;
             Operand a{dh3_hi, dh3_lo, HC, (long long)R * HC, 0}, b{WS_BF(w, wc3_hi), WS_BF(w, wc3_lo), HB, (long long)HC * HB, 1};
+            if (fuse_bn) bn_reduce_in_epilogue(e, w, h2p_hi, h2, s2, HB, sc2);
             GRL_TRY(gemm_launch(h, st, R, HB, HC, 2, a, b, e, 0));
         }
         GRL_TRY(bn_backward(h, st, w, WS_F32(w, dh2p), nullptr, h2p_hi, h2, s2, HB, p->memo_bn2[0].weight, p->memo_bn2[1].weight,
-                            g->memo_bn2_w[0], g->memo_bn2_w[1], g->memo_bn2_b[0], g->memo_bn2_b[1], acc, dh2_hi, dh2_lo, nullptr, sc2, dh2_16));
+                            g->memo_bn2_w[0], g->memo_bn2_w[1], g->memo_bn2_b[0], g->memo_bn2_b[1], acc, dh2_hi, dh2_lo, nullptr, sc2, dh2_16, fuse_bn));
         if (two) GRL_TRY(ev_record(h, EV_DH2(i), st));
         {   // conv2 dgrad
             GemmEpi e = epi_default();
             e.C = WS_F32(w, dh1p); e.ldc = HB; e.c_bstride = (long long)R * HB;
             Operand a{dh2_hi, dh2_lo, HB, (long long)R * HB, 0}, b{WS_BF(w, wc2_hi), WS_BF(w, wc2_lo), HB, (long long)HB * HB, 1};
+            if (fuse_bn) bn_reduce_in_epilogue(e, w, h1p_hi, h1, s1, HB, sc1);
             GRL_TRY(gemm_launch(h, st, R, HB, HB, 2, a, b, e, 0));
         }
         GRL_TRY(bn_backward(h, st, w, WS_F32(w, dh1p), nullptr, h1p_hi, h1, s1, HB, p->memo_bn1[0].weight, p->memo_bn1[1].weight,
-                            g->memo_bn1_w[0], g->memo_bn1_w[1], g->memo_bn1_b[0], g->memo_bn1_b[1], acc, dh1_hi, dh1_lo, nullptr, sc1, dh1_16));
+                            g->memo_bn1_w[0], g->memo_bn1_w[1], g->memo_bn1_b[0], g->memo_bn1_b[1], acc, dh1_hi, dh1_lo, nullptr, sc1, dh1_16, fuse_bn));
         if (two) GRL_TRY(ev_record(h, EV_DH1(i), st));
         {   // conv1 dgrad: dZ = dPre + dH1 Wc1   (accumulates onto dPre)
             GemmEpi e = epi_default();

@@ -410,7 +410,9 @@ long long grl_launch_count(const grl_handle* h);
  * gradients) onto an internal low-priority stream and join it back into the caller's stream before returning, so
  * HBM-bound glue overlaps tensor-core work.  `mask`: bit 0 = forward, bit 1 = backward; default 3; 0 runs everything
  * on the caller's stream (debugging, per-kernel profiling).  Bit 3 (value 8) is a debugging switch of the retrieval search: it
- * replaces the CTA-pair (cta_group::2) coarse GEMM by the single-CTA 256 x 256-tile kernel.                                                          */
+ * replaces the CTA-pair (cta_group::2) coarse GEMM by the single-CTA 256 x 256-tile kernel.  Bits 4-7 are A/B switches of the head
+ * step (tools/ab_head_pairs.py, tools/ab_bn_fuse.py): 16 = single-CTA GEMM kernels only, 32 = fp16 GEMMs on the single-CTA kernel,
+ * 64 = CTA pairs for every 256-wide tile, 128 = separate BatchNorm-backward reduce passes for the memory block's bn1 / bn2.                  */
 int grl_set_overlap(grl_handle* h, int mask);
 
 /* Profiling aid for bench.py's roofline: while enabled, every tcgen05 GEMM launch is bracketed by CUDA
