@@ -149,6 +149,19 @@ __device__ __forceinline__ void epi_tile(const GemmParams& p, const EpiRow& R, i
     for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;                   // warp-uniform
+        // BatchNorm-backward statistics: the ReLU outputs and raw activations of this chunk are requested first (their latency
+        // hides behind the accumulator read and the stores of the tile)
+        uint4 bnb_mk[4];
+        float4 bnb_hv[8];
+        if (e.bnb_mask && row_ok) {
+            const long long off = z * e.bnb_bstride + (long long)grow * e.bnb_ld + col0;
+            const uint4* m4 = reinterpret_cast<const uint4*>(e.bnb_mask + off);
+            const float4* h4 = reinterpret_cast<const float4*>(e.bnb_hraw + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bnb_mk[j] = __ldg(m4 + j);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bnb_hv[j] = __ldg(h4 + j);
+        }
         float v[32];
         tmem_ld_32x32(t_acc + uint32_t(c * 32), v);
         tmem_ld_wait();
@@ -238,18 +251,15 @@ __device__ __forceinline__ void epi_tile(const GemmParams& p, const EpiRow& R, i
         if (e.bnb_mask) {
             float w[32];
             if (row_ok) {
-                const long long off = z * e.bnb_bstride + (long long)grow * e.bnb_ld + col0;
-                const uint4* m4 = reinterpret_cast<const uint4*>(e.bnb_mask + off);
-                const float4* h4 = reinterpret_cast<const float4*>(e.bnb_hraw + off);
                 const float* mean = e.bnb_stat + (long long)z * 4 * p.N + 2 * p.N + col0;
                 const float* rstd = mean + p.N;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint4 mk = __ldg(m4 + j);
+                    const uint4 mk = bnb_mk[j];
                     const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        const float4 hv = __ldg(h4 + 2 * j + q);
+                        const float4 hv = bnb_hv[2 * j + q];
                         const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {

@@ -461,8 +461,8 @@ __device__ __forceinline__ bool boot_select_sampled(BootSmem& S, const uint32_t 
     return true;
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(BOOT_THREADS, MINB) list_boot_select_kernel(const float* __restrict__ tile, long long ld, int ncols, int k,
+// (four resident blocks per SM = 64 registers per thread: the row load of one block hides behind the selection of the others)
+__global__ void __launch_bounds__(BOOT_THREADS, 4) list_boot_select_kernel(const float* __restrict__ tile, long long ld, int ncols, int k,
                                                                         int64_t idx_base, uint64_t* __restrict__ list, float* __restrict__ thresh_out,
                                                                         int* __restrict__ cand_cnt) {
     __shared__ BootSmem S;
@@ -1040,9 +1040,7 @@ static int coarse_pass(grl_handle* h, cudaStream_t st, int metric, const float* 
             merge = 1.6 * pending + 48.0 > (double)L.cap;
         }
         if (first) {
-            static const int minb = getenv("GRL_BOOT_MINB") ? atoi(getenv("GRL_BOOT_MINB")) : 3;
-            if (minb == 2) list_boot_select_kernel<2><<<nq, BOOT_THREADS, 0, st>>>(tile, L.first, nc, kprime, idx_base, list, thresh, cand_cnt);
-            else list_boot_select_kernel<3><<<nq, BOOT_THREADS, 0, st>>>(tile, L.first, nc, kprime, idx_base, list, thresh, cand_cnt);
+            list_boot_select_kernel<<<nq, BOOT_THREADS, 0, st>>>(tile, L.first, nc, kprime, idx_base, list, thresh, cand_cnt);
             GRL_LAUNCH_CHECK(h);
             c_merge = c_end;
         } else if (merge) {
