@@ -230,13 +230,14 @@ static int gemm_launch_pair(grl_handle* h, cudaStream_t st, int M, int N, int K,
     return launch_pair_variant<false, false>(h, st, p, grid);
 }
 
-// Pairs pay off when the k-loop is long enough to amortise the cross-CTA handshakes and there is at least a wave of 256 x 256
-// tiles (measured: the K = 512 / one-wave GEMMs of the memory block run a few percent faster on the single-CTA kernel).
+// Pairs pay off when the k-loop is long enough to amortise the cross-CTA handshakes and the 256 x 256 tiles keep most SMs busy as
+// pairs (measured: the K = 512 GEMMs of the memory block run a few percent faster on the single-CTA kernel; its K = 2048 ones --
+// conv1 forward, conv3 dgrad: 64 tiles -- 0.1 ms per step faster on pairs, which halve the B-operand traffic per CTA).
 static bool use_pair_kernel(const grl_handle* h, int M, int N, int K, int batch) {
     if ((h->overlap & 16) != 0 || M <= GEMM_BM) return false;
     if ((h->overlap & 64) != 0) return true;                                              // debug bit 6: pairs for every 256-wide tile
     const long long tiles = (long long)((M + GP_BM - 1) / GP_BM) * ((N + GP_BN - 1) / GP_BN) * batch;
-    return K >= 1024 && tiles >= (long long)(h->num_sms / 2);
+    return K >= 1024 && 2 * tiles >= (long long)(h->num_sms - h->num_sms / 7);            // >= 64 pairs on 148 SMs
 }
 
 int gemm_launch(grl_handle* h, cudaStream_t st, int M, int N, int K, int batch, const Operand& A, const Operand& B,
