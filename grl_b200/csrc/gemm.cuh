@@ -136,7 +136,8 @@ __device__ __forceinline__ EpiRow epi_row_setup(const GemmParams& p, int z, int 
 
 // Drains one 128 x BN accumulator (TMEM address t_acc: lane quadrant and first column included) through the fused epilogue.
 template <int BN>
-__device__ __forceinline__ void epi_tile(const GemmParams& p, const EpiRow& R, int z, int m_tile, int n0, uint32_t t_acc, int quad, int lane) {
+__device__ __forceinline__ void epi_tile(const GemmParams& p, const EpiRow& R, int z, int m_tile, int n0, uint32_t t_acc, int quad, int lane,
+                                         int c_begin = 0, int c_end = BN / 32) {
     const GemmEpi& e = p.epi;
     const int grow = R.grow;
     const bool row_ok = R.row_ok;
@@ -146,7 +147,7 @@ __device__ __forceinline__ void epi_tile(const GemmParams& p, const EpiRow& R, i
     float* c_row = R.c_row;
     float bnb_gmax = 0.f, bnb_xmax = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {       // (the 32-column chunks of the tile this warp drains: all of them, or one half)
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;                   // warp-uniform
         // BatchNorm-backward statistics: the ReLU outputs and raw activations of this chunk are requested first (their latency
@@ -336,8 +337,11 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, bool B_MN, int PLANES = 3>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmParams p) {
+// EW = 4 or 8 epilogue warps.  A warp may only read its own TMEM lane quadrant (warp % 4), so with eight the two warps of a
+// quadrant split the tile's columns: two warps per scheduler instead of one for the latency-bound epilogue of the short-K GEMMs.
+template <int BN, bool A_MN, bool B_MN, int PLANES = 3, int EW = 4>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_bf16x3_kernel(const __grid_constant__ GemmParams p) {
+    static_assert(EW == 4 || EW == 8, "four or eight epilogue warps");
     using Cfg = GemmCfg<BN, PLANES>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
         tma_prefetch_desc(&p.ta_hi); tma_prefetch_desc(&p.ta_lo);
         tma_prefetch_desc(&p.tb_hi); tma_prefetch_desc(&p.tb_lo);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_hi[s], 1); mbar_init(&full_lo[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EW); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
@@ -480,7 +484,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16x3_kernel(const __gr
             const EpiRow R = epi_row_setup(p, z, m_tile, row_in_tile);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            epi_tile<BN>(p, R, z, m_tile, n0, tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN), quad, lane);
+            constexpr int CH = BN / 32 / (EW / 4);            // chunks per epilogue warp
+            const int c_begin = (EW == 8) ? ((warp - 2) >> 2) * CH : 0;
+            epi_tile<BN>(p, R, z, m_tile, n0, tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * BN), quad, lane, c_begin, c_begin + CH);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
