@@ -452,6 +452,8 @@ def run_ours(args):
     out_host2 = [out_host, [torch.empty((B, 2048)).pin_memory(), torch.empty((B, T, 2048)).pin_memory()]]
     chk_host = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
     done = [torch.cuda.Event(), torch.cuda.Event()]
+    computed = [torch.cuda.Event(), torch.cuda.Event()]
+    d2h_stream = torch.cuda.Stream(dev)
     e2e_sink = []
 
     def consume(i):
@@ -466,11 +468,17 @@ def run_ours(args):
         xin = xbuf[i].requires_grad_(True)
         f_uncorr, f_corr, _, _, _ = model.head(xin, B, T)
         torch.autograd.backward([f_uncorr, f_corr], [gu, gc])
-        out_host2[i][0].copy_(f_uncorr.detach(), non_blocking=True)
-        out_host2[i][1].copy_(f_corr.detach(), non_blocking=True)
-        chk_host[i].copy_(xin.grad.sum().reshape(1), non_blocking=True)   # d loss / d layer4 maps stays on the device for the backbone; read a checksum
+        chk = xin.grad.sum().reshape(1)                    # d loss / d layer4 maps stays on the device for the backbone; read a checksum
         free[i].record(cur)
-        done[i].record(cur)
+        computed[i].record(cur)
+        with torch.cuda.stream(d2h_stream):                # read-backs on their own stream: the next step's kernels do not queue behind them
+            d2h_stream.wait_event(computed[i])
+            for t_ in (f_uncorr, f_corr, chk):
+                t_.record_stream(d2h_stream)
+            out_host2[i][0].copy_(f_uncorr.detach(), non_blocking=True)
+            out_host2[i][1].copy_(f_corr.detach(), non_blocking=True)
+            chk_host[i].copy_(chk, non_blocking=True)
+            done[i].record(d2h_stream)
         xin.grad = None
         xbuf[i].requires_grad_(False)
         for p_ in model.parameters():
@@ -522,8 +530,8 @@ def run_ours(args):
            "d2h_bytes_per_step": (B * 2048 + B * T * 2048) * 4 + 4, "steps": KE,
            "api": "ResNet50_GRL_Model.head(x, b, t) + torch.autograd.backward (ctypes -> libgrl_b200.so); the H2D copy of step "
                   "s+1 overlaps step s on a side stream; every step's outputs and a dx checksum are copied to pinned host memory and read "
-                  "by the host one step late (all of them before the clock stops); the clock starts on an EMPTY pipeline: the first "
-                  "step waits for its own upload",
+                  "by the host one step late (all of them before the clock stops; the read-backs run on their own stream); the clock starts on "
+                  "an EMPTY pipeline: the first step waits for its own upload",
            "steady_state": {"value": world * B * KE / dt_s, "unit": "clips/s",
                             "what": "the same loop with the pipeline primed by two untimed steps: the first timed step's input was uploaded "
                                     "under its predecessor and every timed step (the last one too) issues its successor's upload, so the "
@@ -537,6 +545,8 @@ def run_ours(args):
     gstep.d_f_uncorr.copy_(gu)
     gstep.d_f_corr.copy_(gc)
 
+    stage = [[torch.empty((B, 2048), device=dev), torch.empty((B, T, 2048), device=dev)] for _ in range(2)]
+
     def graph_step(i, more, pending):
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(ready[i])
@@ -545,10 +555,18 @@ def run_ours(args):
         if more:
             prefetch(1 - i)
         f_uncorr, f_corr, dx, _ = gstep()
-        out_host2[i][0].copy_(f_uncorr, non_blocking=True)
-        out_host2[i][1].copy_(f_corr, non_blocking=True)
-        chk_host[i].copy_(dx.sum().reshape(1), non_blocking=True)
-        done[i].record(cur)
+        cur.wait_event(done[i])                            # (the read-back that last used this staging pair, two steps ago)
+        stage[i][0].copy_(f_uncorr)                        # the graph's output tensors are overwritten by the next replay
+        stage[i][1].copy_(f_corr)
+        chk = dx.sum().reshape(1)
+        computed[i].record(cur)
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(computed[i])
+            chk.record_stream(d2h_stream)
+            out_host2[i][0].copy_(stage[i][0], non_blocking=True)
+            out_host2[i][1].copy_(stage[i][1], non_blocking=True)
+            chk_host[i].copy_(chk, non_blocking=True)
+            done[i].record(d2h_stream)
         if pending is not None:
             consume(pending)
 

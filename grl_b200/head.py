@@ -285,10 +285,13 @@ class GraphedHeadStep(object):
         self.f_uncorr, self.f_corr, self.corr_map, _, _, _ = head_forward_raw(self.sd, self.x, B, T, True, save=True, ws=self._ws)
         self.dx, self.grads = head_backward_raw(self.sd, self.x, B, T, self._ws, self.d_f_uncorr, self.d_f_corr)
         with torch.no_grad():                            # torch/nn/modules/batchnorm.py: +1 per BN call in train mode
-            for prefix in head_buffer_names():
-                key = prefix + ".num_batches_tracked"
-                if key in self.sd:
-                    self.sd[key] += T if "uncorr_memo" in prefix else 1
+            keys = [p_ + ".num_batches_tracked" for p_ in head_buffer_names() if p_ + ".num_batches_tracked" in self.sd]
+            per_step = [self.sd[k] for k in keys if "uncorr_memo" in k]
+            once = [self.sd[k] for k in keys if "uncorr_memo" not in k]
+            if per_step:
+                torch._foreach_add_(per_step, T)
+            if once:
+                torch._foreach_add_(once, 1)
 
     def __call__(self):
         self.graph.replay()
@@ -509,11 +512,14 @@ def run_head(backbone, trl, x, b, t, want_maps=False):
     # grad mode is off inside Function.forward, so decide here whether activations must be kept for a backward
     need_grad = torch.is_grad_enabled() and (x.requires_grad or any(t_.requires_grad for t_ in plist))
     out = _HeadFunction.apply(x, b, t, training, want_maps, need_grad, names, buffers, *plist)
-    if training:    # num_batches_tracked bookkeeping (torch/nn/modules/batchnorm.py): +1 per BN call
+    if training:    # num_batches_tracked bookkeeping (torch/nn/modules/batchnorm.py): +1 per BN call; two fused launches
         with torch.no_grad():
-            for prefix in head_buffer_names():
-                steps = t if "uncorr_memo" in prefix else 1
-                buffers[prefix + ".num_batches_tracked"] += steps
+            per_step = [buffers[p_ + ".num_batches_tracked"] for p_ in head_buffer_names() if "uncorr_memo" in p_]
+            once = [buffers[p_ + ".num_batches_tracked"] for p_ in head_buffer_names() if "uncorr_memo" not in p_]
+            if per_step:
+                torch._foreach_add_(per_step, t)
+            if once:
+                torch._foreach_add_(once, 1)
     return out
 
 
