@@ -133,6 +133,7 @@ _SIGNATURES = {
     "grl_sharded_topk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "grl_search_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "grl_merge_key_lists": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "grl_search_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     "grl_rerank_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "grl_rerank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,

@@ -749,22 +749,53 @@ __global__ void __launch_bounds__(256) finalize_keys_kernel(int metric, const fl
     }
 }
 
-// lists [nlists][rows][kp] (sorted keys) -> out [rows][kp]: the kp smallest of each row's nlists * kp keys
-__global__ void __launch_bounds__(256) merge_key_lists_kernel(const uint64_t* __restrict__ lists, int nlists, int rows, int kp, int npad,
+static int next_pow2_host(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+// lists [nlists][rows][kp] (ascending keys) -> out [rows][kp]: the kp smallest of each row's nlists * kp keys, ascending.
+// A merge TREE over the sorted lists, not a sort of their union: for ascending A and B, C[i] = min(A[i], B[kp-1-i]) holds the kp
+// smallest keys of both as a bitonic sequence, which log2(kp) half-cleaner stages sort -- (1 + log2 kp) passes over kp keys per
+// pair and level instead of the log2^2 stages of a bitonic sort over all nlists * kp keys (8 lists of 256: 7.5x fewer compare-
+// exchanges).  smem: npl * kp keys, npl = nlists rounded up to a power of two (missing lists are empty); kp is a power of two.
+__global__ void __launch_bounds__(256) merge_key_lists_kernel(const uint64_t* __restrict__ lists, int nlists, int rows, int kp, int npl,
                                                               uint64_t* __restrict__ out) {
-    extern __shared__ uint64_t mkeys[];
+    extern __shared__ uint64_t mkeys[];               // [npl][kp]
     const int row = blockIdx.x;
-    const int n = nlists * kp;
-    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-        uint64_t key = KEY_EMPTY;
-        if (i < n) {
-            const int s = i / kp, j = i - s * kp;
-            key = lists[((long long)s * rows + row) * kp + j];
-        }
-        mkeys[i] = key;
+    const int lkp = 31 - __clz(kp);
+    for (int i = threadIdx.x; i < npl * kp; i += blockDim.x) {
+        const int s = i >> lkp, j = i & (kp - 1);
+        mkeys[i] = s < nlists ? lists[((long long)s * rows + row) * kp + j] : KEY_EMPTY;
     }
-    block_bitonic_sort(mkeys, npad);
+    __syncthreads();
+    for (int gap = 1; gap < npl; gap <<= 1) {         // this level merges list a + gap into list a, a = 0, 2 gap, 4 gap, ...
+        const int npairs = npl / (2 * gap);
+        for (int i = threadIdx.x; i < npairs * kp; i += blockDim.x) {
+            const int pr = i >> lkp, t = i & (kp - 1);
+            uint64_t* A = mkeys + (size_t)pr * 2 * gap * kp;
+            const uint64_t a = A[t], b = A[(size_t)gap * kp + (kp - 1 - t)];
+            A[t] = a < b ? a : b;                      // (A[t] is read and written by this thread only; the other list is read-only here)
+        }
+        __syncthreads();
+        for (int stride = kp >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < npairs * (kp >> 1); i += blockDim.x) {
+                const int pr = i >> (lkp - 1), j = i & ((kp >> 1) - 1);
+                uint64_t* A = mkeys + (size_t)pr * 2 * gap * kp;
+                const int lo = 2 * j - (j & (stride - 1)), hi = lo + stride;
+                const uint64_t a = A[lo], b = A[hi];
+                if (a > b) { A[lo] = b; A[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
     for (int i = threadIdx.x; i < kp; i += blockDim.x) out[(long long)row * kp + i] = mkeys[i];
+}
+
+static int merge_key_lists(grl_handle* h, cudaStream_t st, const uint64_t* lists, int nlists, int rows, int kp, uint64_t* out) {
+    const int npl = next_pow2_host(nlists);
+    const size_t smem = (size_t)npl * kp * 8;
+    GRL_TRY(ensure_dyn_smem(h, (const void*)merge_key_lists_kernel, (int)smem));
+    merge_key_lists_kernel<<<rows, 256, smem, st>>>(lists, nlists, rows, kp, npl, out);
+    GRL_LAUNCH_CHECK(h);
+    return GRL_OK;
 }
 
 // Flag column of the result keys -> ascending list of flagged rows + counters (ONE block: the order must be the same on every
@@ -1254,6 +1285,13 @@ static int stage_mark(grl_handle* h, cudaStream_t st, int i) {
     return GRL_OK;
 }
 
+extern "C" int grl_merge_key_lists(grl_handle* h, const unsigned long long* lists, int nlists, int rows, int kp, unsigned long long* out, void* stream) {
+    if (!h || !lists || !out) return set_error(h, GRL_EINVAL, "grl_merge_key_lists: NULL argument");
+    if (nlists <= 0 || rows <= 0 || kp < 2 || kp > TOPK_MAXK || (kp & (kp - 1))) return set_error(h, GRL_EINVAL, "grl_merge_key_lists: need nlists, rows > 0 and kp a power of two in [2, %d]", TOPK_MAXK);
+    if ((long long)next_pow2_host(nlists) * kp > 16384) return set_error(h, GRL_EINVAL, "grl_merge_key_lists: nlists * kp must be <= 16384");
+    return merge_key_lists(h, (cudaStream_t)stream, reinterpret_cast<const uint64_t*>(lists), nlists, rows, kp, reinterpret_cast<uint64_t*>(out));
+}
+
 extern "C" int grl_search_profile(grl_handle* h, int on) {
     if (!h) return GRL_EINVAL;
     h->stage_prof = on ? 1 : 0;
@@ -1309,11 +1347,8 @@ static int search_core(grl_handle* h, const NcclApi* api, ncclComm_t comm, int w
             GRL_NCCL(h, api, api->Recv(R + (size_t)p * cnt, cnt, ncclUint64, p, comm, st));
         }
         GRL_NCCL(h, api, api->GroupEnd());
-        const int npad = next_pow2(world * kp);
-        GRL_TRY(ensure_dyn_smem(h, (const void*)merge_key_lists_kernel, npad * 8));
         uint64_t* mine = MAw + (size_t)rank * cnt;
-        merge_key_lists_kernel<<<qs, 256, (size_t)npad * 8, st>>>(R, world, qs, kp, npad, mine);
-        GRL_LAUNCH_CHECK(h);
+        GRL_TRY(merge_key_lists(h, st, R, world, qs, kp, mine));
         GRL_NCCL(h, api, api->AllGather(mine, MAw, cnt, ncclUint64, comm, st));                      // in place
         MA = MAw;
     }

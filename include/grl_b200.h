@@ -214,6 +214,13 @@ int grl_sharded_topk(grl_handle* h, int metric, const float* q, int q_is_slice, 
                      void* workspace, size_t workspace_bytes, void* stream);
 #define GRL_SEARCH_STAGES 9
 int grl_search_profile(grl_handle* h, int on);
+
+/* The exchange step of grl_sharded_topk on its own (for callers that move the shards' lists themselves, and for the tests):
+ * `lists` [nlists][rows][kp] holds, per shard and query row, kp packed keys in ascending order (orderable(distance) << 32 | global
+ * gallery index, all-ones = empty slot -- the list format of the search); `out` [rows][kp] receives the kp smallest keys of every row,
+ * ascending.  A merge tree over the sorted lists (not a sort of their union).  kp: a power of two <= 1024; nlists (rounded up to a
+ * power of two) * kp <= 16384.  Replaces nothing in the reference (its evaluator holds one gallery, attevaluator.py:125-161).       */
+int grl_merge_key_lists(grl_handle* h, const unsigned long long* lists, int nlists, int rows, int kp, unsigned long long* out, void* stream);
 int grl_search_stage_ms(grl_handle* h, double* ms, int n);
 
 /* k-reciprocal re-ranking: re_ranking(q_g_dist, q_q_dist, g_g_dist, k1, k2, lambda_value)

@@ -300,6 +300,30 @@ def test_first_chunk_selection_with_duplicate_rows(dups):
         assert np.array_equal(ci, np.tile(np.arange(ci.shape[1]), (nq, 1)))
 
 
+@pytest.mark.parametrize("nlists,kp,rows", [(2, 256, 37), (3, 256, 5), (4, 512, 9), (8, 256, 50), (8, 1024, 3), (16, 1024, 2), (5, 2, 4), (1, 256, 3)])
+def test_merge_key_lists_is_the_sorted_union_prefix(nlists, kp, rows):
+    """grl_merge_key_lists (the exchange step of grl_sharded_topk: a merge tree over the shards' ascending key lists) ==
+    the kp smallest of the union, ascending -- for 1..16 lists, list counts that are not powers of two, lists with empty
+    (all-ones) tails and keys shared between lists."""
+    import ctypes as C
+    _lib, _ = _mods()
+    rng = np.random.default_rng(nlists * 1000 + kp)
+    keys = rng.integers(0, 2**63, size=(nlists, rows, kp), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(nlists, rows, kp), dtype=np.uint64)
+    keys[:, :, : kp // 4] = keys[0:1, :, : kp // 4]                      # keys present in every list
+    fill = rng.integers(0, kp + 1, size=(nlists, rows))
+    for s_ in range(nlists):
+        for r in range(rows):
+            keys[s_, r, kp - fill[s_, r] // 3:] = np.uint64(0xFFFFFFFFFFFFFFFF)           # an empty tail
+    keys.sort(axis=2)
+    want = np.sort(keys.transpose(1, 0, 2).reshape(rows, nlists * kp), axis=1)[:, :kp]
+    lists = torch.from_numpy(keys.view(np.int64)).cuda()
+    out = torch.empty((rows, kp), dtype=torch.int64, device="cuda")
+    lib = _lib.load_library()
+    h = _lib.get_handle(out.device)
+    _lib.check(h, lib.grl_merge_key_lists(h, lists.data_ptr(), nlists, rows, kp, out.data_ptr(), _lib.stream_ptr(out.device)), "grl_merge_key_lists")
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), want)
+
+
 def test_exact_topk_brute_force_matches_oracle():
     _, ev = _mods()
     from oracle import eval_oracle as eo
