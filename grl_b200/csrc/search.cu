@@ -223,7 +223,7 @@ __device__ __forceinline__ void warp_merge_row(int cnt, const unsigned long long
 //    smallest; everything in a lower bin is selected, the entries of that boundary bin are ranked and the smallest still needed
 //    are taken; a boundary bin too large for that (degenerate data) is refined by another round on its own range.
 //  * sampled pre-filter (boot_select_sampled, full chunks only): the same bin search over a 1-in-8 SAMPLE of the row gives a cut
-//    t0 that about 1.8 k of the row's values pass; those are compacted into shared memory (one compare per value instead of a
+//    t0 that about 2 k of the row's values pass; those are compacted into shared memory (one compare per value instead of a
 //    bin computation and an atomic) and the exact path's bin search then runs over the few hundred survivors.  The cut is only
 //    a work-saving guess: whenever fewer than k or more than BOOT_BUF values pass it (a few rows in 10^5 for continuous data;
 //    every row of a gallery of duplicates) the row takes the exact path from its registers.

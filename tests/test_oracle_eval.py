@@ -110,3 +110,37 @@ def test_evaluate_agrees_with_the_references_other_evaluators(golden_dir):
     perm = np.random.default_rng(0).permutation(gf.shape[0])
     cmc3, mAP3, _, _ = eo.evaluate_rankcount(d[:, perm], qp, gp[perm], qc, gc[perm], topk)
     assert np.array_equal(cmc3, cmc2) and abs(mAP3 - mAP2) < 1e-12
+
+
+def _prefilter_pass_count(row, kp):
+    """numpy restatement of the cut of boot_select_sampled (grl_b200/csrc/search.cu): one value in eight of the row (thread t of
+    256: columns 4t, 2048+4t+1, 4096+4t+2, 6144+4t+3) is histogrammed over 2,048 ordered bins between the sample's extremes;
+    t0 = the largest sample in the bins up to the one holding sample rank ceil((kp + 4.5 sqrt(8 kp) + 16) / 8).  Returns how many
+    of the row's 8,192 values pass `value <= t0` (the kernel then selects exactly among those, or falls back to its exact path
+    when fewer than kp or more than 2,048 pass)."""
+    b = np.ascontiguousarray(row, dtype=np.float32).view(np.uint32)
+    v = np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.uint32)       # order-preserving bits (common.cuh: orderable)
+    t = np.arange(256)
+    sv = v[np.concatenate([4 * t, 2048 + 4 * t + 1, 4096 + 4 * t + 2, 6144 + 4 * t + 3])]
+    lo, hi = sv.min(), sv.max()
+    if lo == hi:
+        return None
+    scale = np.float32(2047) / np.float32(hi - lo)
+    bins = np.minimum(2047, ((sv - lo).astype(np.float32) * scale).astype(np.uint32))
+    rank = (kp + int(np.float32(4.5) * np.sqrt(np.float32(kp * 8))) + 16 + 7) // 8
+    edge = np.searchsorted(np.cumsum(np.bincount(bins, minlength=2048)), rank)
+    return int((v <= sv[bins <= edge].max()).sum())
+
+
+@pytest.mark.parametrize("kp", [256, 512, 1024])
+def test_first_chunk_prefilter_cut_keeps_enough_and_not_too_many(kp):
+    """The sampled cut of the first-chunk selection is a work-saving guess, never a correctness condition (rows it misjudges take
+    the exact path) -- but it has to be a GOOD guess: on continuous data at least kp and at most 2,048 of the 8,192 values must
+    pass it for (nearly) every row.  4,000 Gaussian and 4,000 uniform rows per list length: no row may fall outside."""
+    rng = np.random.default_rng(kp)
+    counts = [_prefilter_pass_count(rng.standard_normal(8192), kp) for _ in range(4000)]
+    counts += [_prefilter_pass_count(rng.random(8192), kp) for _ in range(4000)]
+    counts = np.array(counts)
+    assert counts.min() >= kp and counts.max() <= 2048, (counts.min(), counts.max())
+    assert 1.3 * kp < counts.mean() < 2.4 * kp, counts.mean()
+    assert _prefilter_pass_count(np.full(8192, 0.25), kp) is None            # constant row: no cut, exact path
